@@ -1,0 +1,457 @@
+// HBM-bound kernels of the hot path: input quantisation, calibration amax, SiLU+quantise,
+// LayerNorm+modulate+quantise, stand-alone QKNorm+RoPE and the skinny-M fp8 GEMV used by Modulation.
+// All reproduce the reference's eager bf16 rounding points.
+#include "flux_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace fb {
+
+// ---------------------------------------------------------------------------------------------
+// quantize: y = fp8(clamp(bf16(x*s)))            float8_quantize.py:217-218, 274-276
+// ---------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) quantize_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y,
+                                                       int64_t n, const float* __restrict__ scale) {
+  const float s = __ldg(scale);
+  const int64_t nvec = n / 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    uint4 in = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    uint32_t w[4] = {in.x, in.y, in.z, in.w};
+    uint16_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = unpack_bf16x2(w[t]);
+      o[t] = to_fp8x2<FMT>(quant_pre<FMT>(f.x, s), quant_pre<FMT>(f.y, s));
+    }
+    uint2 out;
+    out.x = o[0] | (static_cast<uint32_t>(o[1]) << 16);
+    out.y = o[2] | (static_cast<uint32_t>(o[3]) << 16);
+    reinterpret_cast<uint2*>(y)[i] = out;
+  }
+  // tail
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    int64_t i = nvec * 8 + threadIdx.x;
+    y[i] = to_fp8<FMT>(quant_pre<FMT>(__bfloat162float(x[i]), s));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// amax: *amax = max(*amax, max|x|)               float8_quantize.py:197, 227
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) amax_kernel(const __nv_bfloat16* __restrict__ x, int64_t n,
+                                                   float* __restrict__ amax) {
+  float m = 0.f;
+  const int64_t nvec = n / 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    uint4 in = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    uint32_t w[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 f = unpack_bf16x2(w[t]);
+      m = fmaxf(m, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) m = fmaxf(m, fabsf(__bfloat162float(x[nvec * 8 + threadIdx.x])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    // non-negative floats order like their bit patterns (NaN propagates as a large pattern)
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// silu + quantise                                 modules/flux_model.py:249,252
+// ---------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) silu_quant_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y,
+                                                         __nv_bfloat16* __restrict__ yb, int64_t n,
+                                                         const float* __restrict__ scale) {
+  const float s = scale ? __ldg(scale) : 1.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = __bfloat162float(x[i]);
+    float a = bf16r(v / (1.f + expf(-v)));
+    if (yb) yb[i] = __float2bfloat16_rn(a);
+    if (y) y[i] = to_fp8<FMT>(quant_pre<FMT>(a, s));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (no affine) -> (1+scale)*x + shift -> quantise.  One warp per row.
+//   modules/flux_model.py:367-368 (and 374-375, 389, 395, 469-470)
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnMaxIter = 16;  // D <= 16*256 = 4096
+
+template <int FMT>
+__global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                           const __nv_bfloat16* __restrict__ shift,
+                                                           const __nv_bfloat16* __restrict__ scale,
+                                                           int64_t mod_stride, uint8_t* __restrict__ yq, int64_t ldy,
+                                                           __nv_bfloat16* __restrict__ yb, int64_t ldyb,
+                                                           const float* __restrict__ in_scale, int rows, int L, int D,
+                                                           float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int b = row / L;
+  const int ni = D / 256;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
+  uint4 xv[kLnMaxIter];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxIter; ++i) {
+    if (i < ni) {
+      xv[i] = __ldg(xp + i * 32 + lane);
+      uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        sum += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / D;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxIter; ++i) {
+    if (i < ni) {
+      uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        float d0 = f.x - mean, d1 = f.y - mean;
+        var = fmaf(d0, d0, var);
+        var = fmaf(d1, d1, var);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / D + eps);
+  const float s = in_scale ? __ldg(in_scale) : 1.f;
+  const uint4* shp = reinterpret_cast<const uint4*>(shift + static_cast<int64_t>(b) * mod_stride);
+  const uint4* scp = reinterpret_cast<const uint4*>(scale + static_cast<int64_t>(b) * mod_stride);
+#pragma unroll
+  for (int i = 0; i < kLnMaxIter; ++i) {
+    if (i < ni) {
+      uint4 sh = __ldg(shp + i * 32 + lane);
+      uint4 sc = __ldg(scp + i * 32 + lane);
+      uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+      uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w};
+      uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
+      float m[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 f = unpack_bf16x2(w[t]);
+        float2 fs = unpack_bf16x2(shw[t]);
+        float2 fc = unpack_bf16x2(scw[t]);
+        float n0 = bf16r((f.x - mean) * rstd);
+        float n1 = bf16r((f.y - mean) * rstd);
+        // (1 + scale) * ln + shift with eager bf16 rounding after each op
+        m[t * 2 + 0] = bf16r(bf16r(bf16r(1.f + fc.x) * n0) + fs.x);
+        m[t * 2 + 1] = bf16r(bf16r(bf16r(1.f + fc.y) * n1) + fs.y);
+      }
+      const int64_t col = static_cast<int64_t>(i * 32 + lane) * 8;
+      if (yb) {
+        uint4 o;
+        o.x = pack_bf16x2(m[0], m[1]);
+        o.y = pack_bf16x2(m[2], m[3]);
+        o.z = pack_bf16x2(m[4], m[5]);
+        o.w = pack_bf16x2(m[6], m[7]);
+        *reinterpret_cast<uint4*>(yb + static_cast<int64_t>(row) * ldyb + col) = o;
+      }
+      if (yq) {
+        uint2 o;
+        o.x = to_fp8x2<FMT>(quant_pre<FMT>(m[0], s), quant_pre<FMT>(m[1], s)) |
+              (static_cast<uint32_t>(to_fp8x2<FMT>(quant_pre<FMT>(m[2], s), quant_pre<FMT>(m[3], s))) << 16);
+        o.y = to_fp8x2<FMT>(quant_pre<FMT>(m[4], s), quant_pre<FMT>(m[5], s)) |
+              (static_cast<uint32_t>(to_fp8x2<FMT>(quant_pre<FMT>(m[6], s), quant_pre<FMT>(m[7], s))) << 16);
+        *reinterpret_cast<uint2*>(yq + static_cast<int64_t>(row) * ldy + col) = o;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone QKNorm + RoPE on [B,H,S,128]; one warp per row, lane owns 4 consecutive elements
+//   modules/flux_model.py:164 (RMSNorm), 60-65 (apply_rope)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qknorm_rope_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          __nv_bfloat16* __restrict__ y,
+                                                          const float* __restrict__ norm_w,
+                                                          const __nv_bfloat16* __restrict__ rcos,
+                                                          const __nv_bfloat16* __restrict__ rsin, int64_t rope_bstride,
+                                                          int64_t rows, int H, int S, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int64_t s = row % S;
+  const int64_t b = row / (static_cast<int64_t>(S) * H);
+  uint2 in = *reinterpret_cast<const uint2*>(x + row * 128 + lane * 4);
+  float2 a = unpack_bf16x2(in.x), c = unpack_bf16x2(in.y);
+  float v[4] = {a.x, a.y, c.x, c.y};
+  if (norm_w) {
+    float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rinv = rsqrtf(ss * (1.f / 128.f) + eps);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = bf16r(v[j] * rinv * __ldg(norm_w + lane * 4 + j));
+  }
+  if (rcos && rsin) {
+    const int64_t off = b * rope_bstride + s * 64 + lane * 2;
+    float2 cs = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(rcos + off));
+    float2 sn = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(rsin + off));
+    float o0 = bf16r(cs.x * v[0]) + bf16r(-sn.x * v[1]);
+    float o1 = bf16r(sn.x * v[0]) + bf16r(cs.x * v[1]);
+    float o2 = bf16r(cs.y * v[2]) + bf16r(-sn.y * v[3]);
+    float o3 = bf16r(sn.y * v[2]) + bf16r(cs.y * v[3]);
+    v[0] = o0, v[1] = o1, v[2] = o2, v[3] = o3;
+  }
+  uint2 out;
+  out.x = pack_bf16x2(v[0], v[1]);
+  out.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(y + row * 128 + lane * 4) = out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// skinny-M fp8 GEMV: out[m,n] = bf16(acc*s + bias).  Weight-streaming; A cached in smem as fp16
+// (exact for both fp8 formats); products and sums in fp32 (exact products, like the tensor core).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGemvColsPerWarp = 4;
+constexpr int kGemvWarps = 8;
+constexpr int kGemvMT = 4;  // rows of A handled per pass
+
+template <int FMT>
+__device__ __forceinline__ void fp8x16_to_float(const uint4& in, float (&f)[16]) {
+  const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>((w[t] >> (16 * h)) & 0xffff),
+                                                  FMT == 0 ? __NV_E4M3 : __NV_E5M2);
+      float2 ff = __half22float2(*reinterpret_cast<__half2*>(&hr));
+      f[t * 4 + h * 2 + 0] = ff.x;
+      f[t * 4 + h * 2 + 1] = ff.y;
+    }
+  }
+}
+
+template <int AFMT, int WFMT>
+__global__ void __launch_bounds__(kGemvWarps * 32) f8_gemv_kernel(const uint8_t* __restrict__ a,
+                                                                  const uint8_t* __restrict__ w,
+                                                                  const __nv_bfloat16* __restrict__ bias,
+                                                                  const float* __restrict__ sa,
+                                                                  const float* __restrict__ sw,
+                                                                  __nv_bfloat16* __restrict__ out, int M, int N, int K) {
+  extern __shared__ __half a_sm[];  // [kGemvMT][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float s = __ldg(sa) * __ldg(sw);
+  const int n0 = (blockIdx.x * kGemvWarps + warp) * kGemvColsPerWarp;
+  for (int m0 = 0; m0 < M; m0 += kGemvMT) {
+    const int mt = min(kGemvMT, M - m0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < mt * K / 2; i += blockDim.x) {
+      const int m = (i * 2) / K, k = (i * 2) % K;
+      uint16_t two = *reinterpret_cast<const uint16_t*>(a + static_cast<int64_t>(m0 + m) * K + k);
+      __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(two, AFMT == 0 ? __NV_E4M3 : __NV_E5M2);
+      *reinterpret_cast<__half2*>(a_sm + m * K + k) = *reinterpret_cast<__half2*>(&hr);
+    }
+    __syncthreads();
+    if (n0 < N) {
+      float acc[kGemvColsPerWarp][kGemvMT];
+#pragma unroll
+      for (int c = 0; c < kGemvColsPerWarp; ++c)
+#pragma unroll
+        for (int m = 0; m < kGemvMT; ++m) acc[c][m] = 0.f;
+      for (int k = lane * 16; k < K; k += 32 * 16) {
+        float af[kGemvMT][16];
+#pragma unroll
+        for (int m = 0; m < kGemvMT; ++m) {
+          if (m < mt) {
+            const uint4* ap = reinterpret_cast<const uint4*>(a_sm + m * K + k);
+            uint4 lo = ap[0], hi = ap[1];
+            const __half2* h = reinterpret_cast<const __half2*>(&lo);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float2 f0 = __half22float2(h[t]), f1 = __half22float2(h2[t]);
+              af[m][t * 2] = f0.x, af[m][t * 2 + 1] = f0.y;
+              af[m][8 + t * 2] = f1.x, af[m][8 + t * 2 + 1] = f1.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < kGemvColsPerWarp; ++c) {
+          if (n0 + c < N) {
+            uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + static_cast<int64_t>(n0 + c) * K + k));
+            float wf[16];
+            fp8x16_to_float<WFMT>(wv, wf);
+#pragma unroll
+            for (int m = 0; m < kGemvMT; ++m)
+              if (m < mt) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[c][m] = fmaf(wf[j], af[m][j], acc[c][m]);
+              }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kGemvColsPerWarp; ++c)
+#pragma unroll
+        for (int m = 0; m < kGemvMT; ++m) {
+          float v = acc[c][m];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && m < mt && n0 + c < N) {
+            float bb = bias ? __bfloat162float(bias[n0 + c]) : 0.f;
+            out[static_cast<int64_t>(m0 + m) * N + n0 + c] = __float2bfloat16_rn(fmaf(v, s, bb));
+          }
+        }
+    }
+  }
+}
+
+static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = static_cast<int64_t>(sm_count()) * max_blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" int fluxb200_quantize(const void* x, void* y, int64_t n, const float* scale, int fmt,
+                                 fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(x && y && scale && n >= 0, "fluxb200_quantize: null operand");
+  FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_quantize: bad fp8 format %d", fmt);
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+             "fluxb200_quantize: x must be 16B and y 8B aligned");
+  if (n == 0) return 0;
+  const int grid = grid_for(n / 8 + 1, 256);
+  if (fmt == 0)
+    quantize_kernel<0><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y), n, scale);
+  else
+    quantize_kernel<1><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y), n, scale);
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_amax(const void* x, int64_t n, float* amax, fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(x && amax && n >= 0, "fluxb200_amax: null operand");
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "fluxb200_amax: x must be 16B aligned");
+  if (n == 0) return 0;
+  amax_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), n, amax);
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_silu_quant(const void* x, void* y_fp8, void* y_bf16, int64_t n, const float* scale, int fmt,
+                                   fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(x && (y_fp8 || y_bf16), "fluxb200_silu_quant: null operand");
+  FB_REQUIRE(!y_fp8 || scale, "fluxb200_silu_quant: scale required for fp8 output");
+  FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_silu_quant: bad fp8 format %d", fmt);
+  if (n == 0) return 0;
+  const int grid = grid_for(n, 256);
+  if (fmt == 0)
+    silu_quant_kernel<0><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y_fp8),
+                                                   static_cast<__nv_bfloat16*>(y_bf16), n, scale);
+  else
+    silu_quant_kernel<1><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y_fp8),
+                                                   static_cast<__nv_bfloat16*>(y_bf16), n, scale);
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_ln_mod_quant(const void* x, int64_t ldx, const void* shift, const void* scale,
+                                     int64_t mod_batch_stride, void* y_fp8, int64_t ldy, void* y_bf16,
+                                     int64_t ldy_bf16, const float* in_scale, int fmt, int B, int L, int D, float eps,
+                                     fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(x && shift && scale && (y_fp8 || y_bf16), "fluxb200_ln_mod_quant: null operand");
+  FB_REQUIRE(!y_fp8 || in_scale, "fluxb200_ln_mod_quant: in_scale required for fp8 output");
+  FB_REQUIRE(B > 0 && L > 0 && D > 0 && D % 256 == 0 && D <= 256 * kLnMaxIter,
+             "fluxb200_ln_mod_quant: D=%d must be a multiple of 256 and <= %d", D, 256 * kLnMaxIter);
+  FB_REQUIRE(ldx % 8 == 0 && mod_batch_stride % 8 == 0 && (!y_fp8 || ldy % 8 == 0) && (!y_bf16 || ldy_bf16 % 8 == 0),
+             "fluxb200_ln_mod_quant: strides must keep 16-byte (bf16) / 8-byte (fp8) alignment");
+  FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_ln_mod_quant: bad fp8 format %d", fmt);
+  const int rows = B * L;
+  const int grid = (rows + 7) / 8;
+  if (fmt == 0)
+    ln_mod_quant_kernel<0><<<grid, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(shift),
+        static_cast<const __nv_bfloat16*>(scale), mod_batch_stride, static_cast<uint8_t*>(y_fp8), ldy,
+        static_cast<__nv_bfloat16*>(y_bf16), ldy_bf16, in_scale, rows, L, D, eps);
+  else
+    ln_mod_quant_kernel<1><<<grid, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(shift),
+        static_cast<const __nv_bfloat16*>(scale), mod_batch_stride, static_cast<uint8_t*>(y_fp8), ldy,
+        static_cast<__nv_bfloat16*>(y_bf16), ldy_bf16, in_scale, rows, L, D, eps);
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_qknorm_rope(const void* x, void* y, const float* norm_w, const void* rope_cos,
+                                    const void* rope_sin, int64_t rope_batch_stride, int B, int H, int S, float eps,
+                                    fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(x && y && B > 0 && H > 0 && S > 0, "fluxb200_qknorm_rope: bad operand");
+  FB_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "fluxb200_qknorm_rope: cos and sin go together");
+  const int64_t rows = static_cast<int64_t>(B) * H * S;
+  const int64_t grid = (rows + 7) / 8;
+  qknorm_rope_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), norm_w,
+      static_cast<const __nv_bfloat16*>(rope_cos), static_cast<const __nv_bfloat16*>(rope_sin), rope_batch_stride,
+      rows, H, S, eps);
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_f8_gemv(const void* a, int a_fmt, const void* w, int w_fmt, const void* bias,
+                                const float* sa, const float* sw, void* out, int M, int N, int K,
+                                fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(a && w && sa && sw && out, "fluxb200_f8_gemv: null operand");
+  FB_REQUIRE(M > 0 && M <= 16 && N > 0 && K > 0 && K % 16 == 0, "fluxb200_f8_gemv: need 0<M<=16, K %% 16 == 0");
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(a) & 1) == 0,
+             "fluxb200_f8_gemv: w must be 16B aligned");
+  FB_REQUIRE((a_fmt == 0 || a_fmt == 1) && (w_fmt == 0 || w_fmt == 1), "fluxb200_f8_gemv: bad fp8 format");
+  const size_t smem = static_cast<size_t>(kGemvMT) * K * sizeof(__half);
+  FB_REQUIRE(smem <= 200 * 1024, "fluxb200_f8_gemv: K=%d too large", K);
+  const int cols_per_block = kGemvWarps * kGemvColsPerWarp;
+  const int grid = (N + cols_per_block - 1) / cols_per_block;
+#define FB_GEMV(AF, WF)                                                                                         \
+  do {                                                                                                          \
+    auto kern = f8_gemv_kernel<AF, WF>;                                                                         \
+    if (smem > 48 * 1024) FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kGemvWarps * 32, smem, stream>>>(static_cast<const uint8_t*>(a), static_cast<const uint8_t*>(w), \
+                                                   static_cast<const __nv_bfloat16*>(bias), sa, sw,              \
+                                                   static_cast<__nv_bfloat16*>(out), M, N, K);                   \
+  } while (0)
+  if (a_fmt == 0 && w_fmt == 0) FB_GEMV(0, 0);
+  else if (a_fmt == 1 && w_fmt == 0) FB_GEMV(1, 0);
+  else if (a_fmt == 0 && w_fmt == 1) FB_GEMV(0, 1);
+  else FB_GEMV(1, 1);
+#undef FB_GEMV
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}

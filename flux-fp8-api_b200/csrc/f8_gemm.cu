@@ -1,0 +1,516 @@
+// FP8 GEMM for F8Linear.forward (reference: float8_quantize.py:272-296, torch._scaled_mm) with the
+// block-level eager ops that follow each linear fused into the epilogue
+// (modules/flux_model.py:353-400, 467-485).
+//
+// Persistent warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer: A[128 x 128B] and W[BN x 128B] tiles, SWIZZLE_128B, kStages-deep ring
+//   warp 1      MMA issuer:   tcgen05.mma.kind::f8f6f4 (M=128, N=BN, K=32), fp32 accumulators in TMEM,
+//               two accumulator buffers so tile i+1's MMAs overlap tile i's epilogue
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: tcgen05.ld (thread == output row), dequant scale + bias -> bf16 rounding ->
+//               fused op -> vectorised global stores.  Warps 4-7 own columns [0,BN/2), 8-11 the rest.
+#include <cuda.h>
+
+#include "flux_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace fb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 128;  // bytes == fp8 elements: one SWIZZLE_128B span
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kHeadDim = 128;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kA = kBM * kBK;
+  static constexpr int kB = BN * kBK;
+  static constexpr int kStage = kA + kB;
+  static constexpr int kBarOff = kStages * kStage;
+  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr, norm weights (2*128 fp32)
+  static constexpr int kNormOff = kBarOff + 256;
+  static constexpr int kTotal = kNormOff + 2 * kHeadDim * 4 + 1024 /*alignment slack*/;
+};
+
+struct GemmParams {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_w;
+  fluxb200_gemm_args g;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  uint32_t idesc;
+};
+
+struct RowInfo {
+  int row;    // global row
+  int b;      // sample
+  int pos;    // row within sample
+  bool valid;
+};
+
+// ---- epilogue bodies: one thread owns one output row and `32` consecutive columns per call ----------
+
+// y = bf16(acc*s + bias)
+__device__ __forceinline__ void dequant_bias(const uint32_t (&v)[32], float s, const __nv_bfloat16* bias, int col,
+                                             float (&y)[32]) {
+  if (bias != nullptr) {
+    const uint4* bp = reinterpret_cast<const uint4*>(bias + col);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 bb = __ldg(bp + q);
+      uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 bf = unpack_bf16x2(w[t]);
+        y[q * 8 + t * 2 + 0] = bf16r(fmaf(__uint_as_float(v[q * 8 + t * 2 + 0]), s, bf.x));
+        y[q * 8 + t * 2 + 1] = bf16r(fmaf(__uint_as_float(v[q * 8 + t * 2 + 1]), s, bf.y));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = bf16r(__uint_as_float(v[j]) * s);
+  }
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&y)[32]) {
+  uint4* op = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    o.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
+    o.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
+    o.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
+    o.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
+    op[q] = o;
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ void store_fp8x32(uint8_t* dst, const float (&p)[32]) {
+  uint4* op = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int j = q * 16 + t * 4;
+      w[t] = static_cast<uint32_t>(to_fp8x2<FMT>(p[j], p[j + 1])) |
+             (static_cast<uint32_t>(to_fp8x2<FMT>(p[j + 2], p[j + 3])) << 16);
+    }
+    op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__device__ __forceinline__ void epi_plain(const GemmParams& P, const RowInfo& ri, int col, const float (&y)[32]) {
+  const fluxb200_gemm_args& g = P.g;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col;
+  if (col + 32 <= g.N) {
+    store_bf16x32(dst, y);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col + j < g.N) dst[j] = __float2bfloat16_rn(y[j]);
+  }
+}
+
+__device__ __forceinline__ void epi_gate_residual(const GemmParams& P, const RowInfo& ri, int col,
+                                                  float (&y)[32]) {
+  const fluxb200_gemm_args& g = P.g;
+  const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.gate) +
+                                                   static_cast<int64_t>(ri.b) * g.gate_batch_stride + col);
+  const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.resid) +
+                                                   static_cast<int64_t>(ri.row) * g.ldr + col);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 gg = __ldg(gp + q);
+    uint4 rr = rp[q];
+    uint32_t gw[4] = {gg.x, gg.y, gg.z, gg.w};
+    uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 gf = unpack_bf16x2(gw[t]);
+      float2 rf = unpack_bf16x2(rw[t]);
+      int j = q * 8 + t * 2;
+      y[j] = rf.x + bf16r(gf.x * y[j]);  // rounded to bf16 by the store
+      y[j + 1] = rf.y + bf16r(gf.y * y[j + 1]);
+    }
+  }
+  store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, y);
+}
+
+__device__ __forceinline__ void epi_gelu_quant(const GemmParams& P, const RowInfo& ri, int out_col, float oscale,
+                                               float (&y)[32]) {
+  const fluxb200_gemm_args& g = P.g;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + out_col;
+  if (g.out_fmt == FLUXB200_E5M2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = quant_pre<1>(bf16r(gelu_tanh(y[j])), oscale);
+    store_fp8x32<1>(dst, y);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = quant_pre<0>(bf16r(gelu_tanh(y[j])), oscale);
+    store_fp8x32<0>(dst, y);
+  }
+}
+
+// One thread owns one (row, head): 128 accumulator columns starting at TMEM address `taddr`.
+// which: 0 = q, 1 = k (RMSNorm + RoPE), 2 = v (copy).
+__device__ __forceinline__ void epi_qkv_head(const GemmParams& P, const RowInfo& ri, uint32_t taddr, int col0,
+                                             float s, const float* norm_smem) {
+  const fluxb200_gemm_args& g = P.g;
+  const int hd = g.num_heads * kHeadDim;
+  const int which = col0 / hd;
+  const int head = (col0 - which * hd) / kHeadDim;
+  const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? g.q : (which == 1 ? g.k : g.v));
+  const int64_t spos = static_cast<int64_t>(g.seq_offset) + ri.pos;
+  __nv_bfloat16* dst =
+      base + ((static_cast<int64_t>(ri.b) * g.num_heads + head) * g.seq_total + spos) * kHeadDim;
+
+  uint32_t v[32];
+  float y[32];
+  float rinv = 1.f;
+  if (which < 2) {
+    // pass 1: fp32 sum of squares of the bf16-rounded linear output (F.rms_norm on x.float())
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      tmem_ld32(taddr + c * 32, v);
+      tmem_ld_wait();
+      dequant_bias(v, s, bias, col0 + c * 32, y);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ss = fmaf(y[j], y[j], ss);
+    }
+    rinv = rsqrtf(ss * (1.f / kHeadDim) + 1e-6f);
+  }
+  const float* nw = norm_smem + which * kHeadDim;  // only read when which < 2
+  const __nv_bfloat16* cosp = reinterpret_cast<const __nv_bfloat16*>(g.rope_cos) +
+                              static_cast<int64_t>(ri.b) * g.rope_batch_stride + spos * (kHeadDim / 2);
+  const __nv_bfloat16* sinp = reinterpret_cast<const __nv_bfloat16*>(g.rope_sin) +
+                              static_cast<int64_t>(ri.b) * g.rope_batch_stride + spos * (kHeadDim / 2);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld32(taddr + c * 32, v);
+    tmem_ld_wait();
+    dequant_bias(v, s, bias, col0 + c * 32, y);
+    if (which < 2 && ri.valid) {
+      // RMSNorm (fp32) -> bf16, then RoPE on interleaved pairs with bf16 products and sum
+      uint4 cw[2], sw[2];
+      const uint4* cp = reinterpret_cast<const uint4*>(cosp + c * 16);
+      const uint4* sp = reinterpret_cast<const uint4*>(sinp + c * 16);
+      cw[0] = __ldg(cp);
+      cw[1] = __ldg(cp + 1);
+      sw[0] = __ldg(sp);
+      sw[1] = __ldg(sp + 1);
+      const uint32_t* cu = reinterpret_cast<const uint32_t*>(cw);
+      const uint32_t* su = reinterpret_cast<const uint32_t*>(sw);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        float2 cf = unpack_bf16x2(cu[t]);
+        float2 sf = unpack_bf16x2(su[t]);
+        float cc[2] = {cf.x, cf.y};
+        float sn[2] = {sf.x, sf.y};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          int j = t * 4 + u * 2;
+          float x0 = bf16r(y[j] * rinv * nw[c * 32 + j]);
+          float x1 = bf16r(y[j + 1] * rinv * nw[c * 32 + j + 1]);
+          // out0 = cos*x0 + (-sin)*x1 ; out1 = sin*x0 + cos*x1   (modules/flux_model.py:60-65)
+          y[j] = bf16r(cc[u] * x0) + bf16r(-sn[u] * x1);
+          y[j + 1] = bf16r(sn[u] * x0) + bf16r(cc[u] * x1);
+        }
+      }
+    }
+    if (ri.valid) store_bf16x32(dst + c * 32, y);
+  }
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_constant__ GemmParams P) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tfull_bar = empty_bar + S::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* norm_smem = reinterpret_cast<float*>(smem + S::kNormOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const fluxb200_gemm_args& g = P.g;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmap_a);
+    tma_prefetch_desc(&P.tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 2 * BN);
+    tmem_relinquish();
+  }
+  if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
+    if (threadIdx.x < 2 * kHeadDim)
+      norm_smem[threadIdx.x] =
+          threadIdx.x < kHeadDim ? g.q_norm_w[threadIdx.x] : g.k_norm_w[threadIdx.x - kHeadDim];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = P.num_m_tiles * P.num_n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % P.num_m_tiles) * kBM;
+        const int n0 = (tile / P.num_m_tiles) * BN;
+        for (int kb = 0; kb < P.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStage);
+          uint8_t* sa = smem + stage * S::kStage;
+          tma_load_2d(sa, &P.tmap_a, &full_bar[stage], kb * kBK, m0);
+          tma_load_2d(sa + S::kA, &P.tmap_w, &full_bar[stage], kb * kBK, n0);
+          if (++stage == S::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < P.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::kStage);
+          const uint32_t b_addr = a_addr + S::kA;
+#pragma unroll
+          for (int k = 0; k < kBK / 32; ++k) {
+            uint64_t ad = make_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t bd = make_desc_sw128(b_addr + k * 32, 16, 1024);
+            mma_f8f6f4_ss(d_tmem, ad, bd, P.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (kb == P.num_k_blocks - 1) tc_commit(&tfull_bar[as]);
+          if (++stage == S::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    const int lg = warp & 3;                 // TMEM lane group of this warp
+    const int half = (warp - kEpiWarp0) >> 2;  // which half of the BN columns
+    constexpr int kHalfCols = BN / 2;
+    const float s = __ldg(g.a_scale_recip) * __ldg(g.w_scale_recip);
+    float oscale = 0.f;
+    if constexpr (EPI == FLUXB200_EPI_GELU_QUANT || EPI == FLUXB200_EPI_LINEAR1) oscale = __ldg(g.out_scale);
+    const int rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % P.num_m_tiles) * kBM;
+      const int n0 = (tile / P.num_m_tiles) * BN;
+      RowInfo ri;
+      ri.row = m0 + lg * 32 + lane;
+      ri.valid = ri.row < g.M;
+      ri.b = ri.row / rpb;
+      ri.pos = ri.row - ri.b * rpb;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN + half * kHalfCols;
+      const int col0 = n0 + half * kHalfCols;
+
+      bool qkv_path = (EPI == FLUXB200_EPI_QKV_ROPE);
+      if constexpr (EPI == FLUXB200_EPI_LINEAR1) qkv_path = col0 < 3 * g.num_heads * kHeadDim;
+      if (qkv_path) {
+        if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
+          static_assert(kHalfCols == kHeadDim || (EPI != FLUXB200_EPI_QKV_ROPE && EPI != FLUXB200_EPI_LINEAR1),
+                        "QKV epilogues need BN == 256");
+          epi_qkv_head(P, ri, taddr, col0, s, norm_smem);
+        }
+      } else {
+        const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols / 32; ++c) {
+          uint32_t v[32];
+          float y[32];
+          const int col = col0 + c * 32;
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (col >= g.N) continue;  // warp-uniform
+          const bool full_cols = col + 32 <= g.N;
+          dequant_bias(v, s, full_cols ? bias : nullptr, col, y);
+          if (!full_cols && bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < g.N) y[j] = bf16r(fmaf(__uint_as_float(v[j]), s, __bfloat162float(bias[col + j])));
+          }
+          if (!ri.valid) continue;
+          if constexpr (EPI == FLUXB200_EPI_PLAIN) {
+            epi_plain(P, ri, col, y);
+          } else if constexpr (EPI == FLUXB200_EPI_GATE_RESIDUAL) {
+            epi_gate_residual(P, ri, col, y);
+          } else if constexpr (EPI == FLUXB200_EPI_GELU_QUANT) {
+            epi_gelu_quant(P, ri, g.out_col_offset + col, oscale, y);
+          } else if constexpr (EPI == FLUXB200_EPI_LINEAR1) {
+            epi_gelu_quant(P, ri, g.out_col_offset + col - 3 * g.num_heads * kHeadDim, oscale, y);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+
+template <int BN, int EPI>
+static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool attr_set = false;
+  auto kern = f8_gemm_kernel<BN, EPI>;
+  if (!attr_set) {
+    FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  const int tiles = P.num_m_tiles * P.num_n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(P);
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fb
+
+extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_t stream_) {
+  using namespace fb;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(args != nullptr, "fluxb200_f8_gemm: args is NULL");
+  const fluxb200_gemm_args& g = *args;
+  FB_REQUIRE(g.a && g.w && g.a_scale_recip && g.w_scale_recip, "fluxb200_f8_gemm: null operand");
+  FB_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "fluxb200_f8_gemm: bad shape M=%d N=%d K=%d", g.M, g.N, g.K);
+  FB_REQUIRE(g.K % 16 == 0, "fluxb200_f8_gemm: K=%d must be a multiple of 16", g.K);
+  FB_REQUIRE((g.a_fmt == 0 || g.a_fmt == 1) && (g.w_fmt == 0 || g.w_fmt == 1), "fluxb200_f8_gemm: bad fp8 format");
+  FB_REQUIRE(g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0,
+             "fluxb200_f8_gemm: bias must be 16-byte aligned");
+
+  const int epi = g.epilogue;
+  const bool qkv = epi == FLUXB200_EPI_QKV_ROPE || epi == FLUXB200_EPI_LINEAR1;
+  int bn = 256;
+  switch (epi) {
+    case FLUXB200_EPI_PLAIN:
+      FB_REQUIRE(g.out && g.ldo >= g.N && g.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15) == 0,
+                 "fluxb200_f8_gemm(PLAIN): out must be 16B aligned with ldo %% 8 == 0");
+      break;
+    case FLUXB200_EPI_GATE_RESIDUAL:
+      FB_REQUIRE(g.out && g.resid && g.gate, "fluxb200_f8_gemm(GATE_RESIDUAL): null operand");
+      FB_REQUIRE(g.N % 32 == 0 && g.ldo % 8 == 0 && g.ldr % 8 == 0 && g.gate_batch_stride % 8 == 0,
+                 "fluxb200_f8_gemm(GATE_RESIDUAL): N %% 32, ldo/ldr/gate stride %% 8 required");
+      break;
+    case FLUXB200_EPI_GELU_QUANT:
+      FB_REQUIRE(g.out && g.out_scale, "fluxb200_f8_gemm(GELU_QUANT): null operand");
+      FB_REQUIRE(g.N % 32 == 0 && g.ldo % 16 == 0 && g.out_col_offset % 16 == 0,
+                 "fluxb200_f8_gemm(GELU_QUANT): N %% 32, ldo/offset %% 16 required");
+      break;
+    case FLUXB200_EPI_LINEAR1:
+      FB_REQUIRE(g.out && g.out_scale, "fluxb200_f8_gemm(LINEAR1): null operand");
+      FB_REQUIRE(g.ldo % 16 == 0 && g.out_col_offset % 16 == 0, "fluxb200_f8_gemm(LINEAR1): ldo/offset %% 16");
+      FB_REQUIRE(g.N > 3 * g.num_heads * kHeadDim && (g.N - 3 * g.num_heads * kHeadDim) % 128 == 0,
+                 "fluxb200_f8_gemm(LINEAR1): N must be 3*H*128 + k*128");
+      // fallthrough
+    case FLUXB200_EPI_QKV_ROPE:
+      FB_REQUIRE(g.q && g.k && g.v && g.q_norm_w && g.k_norm_w && g.rope_cos && g.rope_sin,
+                 "fluxb200_f8_gemm(QKV): null operand");
+      FB_REQUIRE(g.num_heads > 0 && (epi == FLUXB200_EPI_LINEAR1 || g.N == 3 * g.num_heads * kHeadDim),
+                 "fluxb200_f8_gemm(QKV_ROPE): N must equal 3*H*128");
+      FB_REQUIRE(g.seq_total > 0 && g.seq_offset >= 0, "fluxb200_f8_gemm(QKV): bad sequence geometry");
+      {
+        const int rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
+        FB_REQUIRE(g.seq_offset + rpb <= g.seq_total, "fluxb200_f8_gemm(QKV): seq_offset+rows_per_batch > seq_total");
+        FB_REQUIRE(g.M % rpb == 0, "fluxb200_f8_gemm(QKV): M must be a multiple of rows_per_batch");
+      }
+      break;
+    default:
+      return set_error(FLUXB200_ERR_INVALID, "fluxb200_f8_gemm: unknown epilogue %d", epi);
+  }
+  if (!qkv && (g.N <= 128 || (g.N % 256 != 0 && g.N % 128 == 0) ||
+               (static_cast<int64_t>((g.M + 127) / 128) * ((g.N + 255) / 256) < sm_count() / 2)))
+    bn = 128;
+
+  GemmParams P;
+  P.g = g;
+  P.num_m_tiles = (g.M + kBM - 1) / kBM;
+  P.num_n_tiles = (g.N + bn - 1) / bn;
+  P.num_k_blocks = (g.K + kBK - 1) / kBK;
+  P.idesc = make_idesc(g.a_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3, g.w_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3,
+                       kBM, bn);
+  int rc = make_tmap_2d(&P.tmap_a, g.a, 1, g.M, g.K, g.K, kBM, kBK);
+  if (rc) return rc;
+  rc = make_tmap_2d(&P.tmap_w, g.w, 1, g.N, g.K, g.K, bn, kBK);
+  if (rc) return rc;
+
+#define FB_LAUNCH(BN_, EPI_) return launch_gemm<BN_, EPI_>(P, stream)
+  if (bn == 256) {
+    switch (epi) {
+      case FLUXB200_EPI_PLAIN: FB_LAUNCH(256, FLUXB200_EPI_PLAIN);
+      case FLUXB200_EPI_GATE_RESIDUAL: FB_LAUNCH(256, FLUXB200_EPI_GATE_RESIDUAL);
+      case FLUXB200_EPI_GELU_QUANT: FB_LAUNCH(256, FLUXB200_EPI_GELU_QUANT);
+      case FLUXB200_EPI_QKV_ROPE: FB_LAUNCH(256, FLUXB200_EPI_QKV_ROPE);
+      case FLUXB200_EPI_LINEAR1: FB_LAUNCH(256, FLUXB200_EPI_LINEAR1);
+    }
+  } else {
+    switch (epi) {
+      case FLUXB200_EPI_PLAIN: FB_LAUNCH(128, FLUXB200_EPI_PLAIN);
+      case FLUXB200_EPI_GATE_RESIDUAL: FB_LAUNCH(128, FLUXB200_EPI_GATE_RESIDUAL);
+      case FLUXB200_EPI_GELU_QUANT: FB_LAUNCH(128, FLUXB200_EPI_GELU_QUANT);
+    }
+  }
+#undef FB_LAUNCH
+  return set_error(FLUXB200_ERR_INVALID, "fluxb200_f8_gemm: no kernel for epilogue %d / BN %d", epi, bn);
+}

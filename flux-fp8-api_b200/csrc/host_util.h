@@ -1,0 +1,42 @@
+// Host-side helpers shared by the C-ABI translation units: per-thread error string, CUDA error
+// checks that never throw, TMA tensor-map encoding through the driver entry point (the library
+// does not link libcuda, so it loads on machines without a driver).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "flux_b200.h"
+
+namespace fb {
+
+std::string& last_error_ref();
+int set_error(int code, const char* fmt, ...);
+int sm_count();
+
+#define FB_CUDA_OK(expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fb::set_error(FLUXB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define FB_REQUIRE(cond, ...)                                          \
+  do {                                                                 \
+    if (!(cond)) return fb::set_error(FLUXB200_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// 2-D row-major tensor [rows, cols] of `elem_bytes`-wide elements, row pitch `pitch_bytes`,
+// box = [box_rows, box_cols], SWIZZLE_128B (box_cols*elem_bytes must be 128).
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                 uint64_t pitch_bytes, uint32_t box_rows, uint32_t box_cols);
+// 3-D tensor [d2, d1, d0] (d0 innermost, contiguous), strides in bytes for d1 and d2.
+int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+
+}  // namespace fb

@@ -1,0 +1,180 @@
+/*
+ * flux_b200.h -- C ABI of libflux_b200.so: the B200 (sm_100a) FP8 Flux-DiT denoise hot path.
+ *
+ * The reference (aredden/flux-fp8-api) has no FFI layer: its boundary for this path is the
+ * nn.Module surface.  Each entry point below names the reference code
+ * (file:line under /root/reference) whose device work it replaces; the Python classes in
+ * flux-fp8-api_b200/ keep the reference's signatures and call these through ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a CUDA device pointer unless stated otherwise
+ *   - bf16 tensors are passed as `const void*` to 2-byte elements, fp8 as 1-byte elements
+ *   - fp8 formats: FLUXB200_E4M3 (float8_e4m3fn) / FLUXB200_E5M2 (float8_e5m2)
+ *   - per-tensor scales are 0-dim fp32 tensors in device memory (as in F8Linear's buffers)
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); calls are stream-ordered,
+ *     allocate nothing, keep no global mutable state besides a per-thread error string
+ *   - return value: 0 on success, a negative FLUXB200_ERR_* otherwise; never throws
+ */
+#ifndef FLUX_B200_H_
+#define FLUX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLUXB200_VERSION 100 /* 0.1.0 */
+
+enum { FLUXB200_E4M3 = 0, FLUXB200_E5M2 = 1 };
+
+enum {
+  FLUXB200_OK = 0,
+  FLUXB200_ERR_INVALID = -1,     /* bad argument (shape / alignment / null pointer)        */
+  FLUXB200_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                    */
+  FLUXB200_ERR_UNSUPPORTED = -3, /* device is not sm_100 or shape outside the kernel's domain */
+};
+
+typedef void* fluxb200_stream_t;
+
+/* Library version (FLUXB200_VERSION). */
+int fluxb200_version(void);
+/* Message of the last failing call on this thread ("" if none). Pointer valid until the next call. */
+const char* fluxb200_last_error(void);
+/* 0 when the current CUDA device can run the kernels (compute capability 10.x); fills *sm_count. */
+int fluxb200_device_check(int* sm_count);
+
+/* ---------------------------------------------------------------------------------------------
+ * F8Linear.quantize_input / to_fp8_saturated   (float8_quantize.py:217-218, 220-246, 274-276)
+ *   y = fp8( clamp( bf16(x * scale), -max, max ) )      -- the double rounding is reproduced
+ * ------------------------------------------------------------------------------------------- */
+int fluxb200_quantize(const void* x_bf16, void* y_fp8, int64_t n, const float* scale, int fmt,
+                      fluxb200_stream_t stream);
+/* torch.max(torch.abs(x)) (float8_quantize.py:197, 227): *amax = max(*amax, max|x|); caller zeroes. */
+int fluxb200_amax(const void* x_bf16, int64_t n, float* amax, fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * F8Linear.forward GEMM  (float8_quantize.py:284-292  torch._scaled_mm)
+ *   acc[M,N] = A_fp8[M,K] . W_fp8[N,K]^T   (tcgen05 kind::f8f6f4, fp32 accumulate in TMEM)
+ *   y = bf16( acc * (*a_scale_recip) * (*w_scale_recip) + bias )
+ * followed by one of the fused epilogues, which reproduce the eager ops that follow the linear
+ * in the reference block code (every intermediate rounded to bf16 as eager PyTorch does).
+ * ------------------------------------------------------------------------------------------- */
+enum {
+  /* out[M,ldo] bf16 = y */
+  FLUXB200_EPI_PLAIN = 0,
+  /* out = bf16( resid + bf16( gate[b] * y ) )        modules/flux_model.py:387-396, 482-484 */
+  FLUXB200_EPI_GATE_RESIDUAL = 1,
+  /* out fp8 = quantize( gelu_tanh(y), *out_scale )   modules/flux_model.py:301,335,455 + next
+     F8Linear's input quantisation (float8_quantize.py:274-276) */
+  FLUXB200_EPI_GELU_QUANT = 2,
+  /* N = 3*H*128: per-head QK-RMSNorm (fp32, eps 1e-6) + RoPE on q,k; q,k,v written as
+     [B,H,seq_total,128] at sequence offset seq_offset.  modules/flux_model.py:353,164,60-65,380-382 */
+  FLUXB200_EPI_QKV_ROPE = 3,
+  /* SingleStreamBlock.linear1: columns [0,3*H*128) as QKV_ROPE, the remaining mlp columns as
+     GELU_QUANT written to out at column out_col_offset.  modules/flux_model.py:471-480 */
+  FLUXB200_EPI_LINEAR1 = 4,
+};
+
+typedef struct fluxb200_gemm_args {
+  const void* a;              /* fp8 [M,K] row-major, 16-byte aligned, K % 16 == 0            */
+  const void* w;              /* fp8 [N,K] row-major (F8Linear.float8_data)                    */
+  const void* bias;           /* bf16 [N] or NULL                                              */
+  const float* a_scale_recip; /* F8Linear.input_scale_reciprocal                               */
+  const float* w_scale_recip; /* F8Linear.scale_reciprocal                                     */
+  int32_t M, N, K;
+  int32_t a_fmt, w_fmt;   /* FLUXB200_E4M3 / FLUXB200_E5M2                                     */
+  int32_t epilogue;       /* FLUXB200_EPI_*                                                    */
+  int32_t rows_per_batch; /* row r belongs to sample r / rows_per_batch (0: one sample)        */
+  /* PLAIN, GATE_RESIDUAL (bf16) and GELU_QUANT / LINEAR1 (fp8) output */
+  void* out;
+  int64_t ldo; /* elements */
+  /* GATE_RESIDUAL */
+  const void* resid; /* bf16 [M,ldr]; may alias out */
+  int64_t ldr;
+  const void* gate; /* bf16, gate[b*gate_batch_stride + n] */
+  int64_t gate_batch_stride;
+  /* GELU_QUANT / LINEAR1 */
+  const float* out_scale; /* next F8Linear.input_scale */
+  int32_t out_fmt;
+  int32_t out_col_offset;
+  /* QKV_ROPE / LINEAR1 */
+  void* q; /* bf16 [B,H,seq_total,128] */
+  void* k;
+  void* v;
+  int32_t num_heads;
+  int32_t seq_total;
+  int32_t seq_offset;
+  int32_t _pad0;
+  const float* q_norm_w; /* fp32 [128]  QKNorm.query_norm.scale */
+  const float* k_norm_w; /* fp32 [128]  QKNorm.key_norm.scale   */
+  const void* rope_cos;  /* bf16 [*, seq_total, 64]  pe[...,0,0] (EmbedND output, bf16-rounded) */
+  const void* rope_sin;  /* bf16 [*, seq_total, 64]  pe[...,1,0]                               */
+  int64_t rope_batch_stride; /* elements between samples (0: shared)                           */
+} fluxb200_gemm_args;
+
+int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_t stream);
+
+/* Skinny-M variant for Modulation.lin / MLPEmbedder (M = batch <= 16): weight-streaming GEMV.
+ *   out[m, n] = bf16( (sum_k A[m,k]*W[n,k]) * sa * sw + bias[n] )   modules/flux_model.py:252 */
+int fluxb200_f8_gemv(const void* a_fp8, int a_fmt, const void* w_fp8, int w_fmt, const void* bias_bf16,
+                     const float* a_scale_recip, const float* w_scale_recip, void* out_bf16, int M, int N,
+                     int K, fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Modulation prologue: y = quantize( bf16(silu(x)), scale )   (modules/flux_model.py:249,252 +
+ * float8_quantize.py:274-276).  y_bf16 (optional) receives bf16(silu(x)) for unquantised lins.
+ * ------------------------------------------------------------------------------------------- */
+int fluxb200_silu_quant(const void* x_bf16, void* y_fp8, void* y_bf16, int64_t n, const float* scale, int fmt,
+                        fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm(eps, no affine) -> (1+scale)*x + shift -> next F8Linear's input quantisation
+ *   modules/flux_model.py:367-368, 374-375, 389, 395, 469-470 + float8_quantize.py:274-276
+ * x bf16 [B*L, D] (row stride ldx); shift/scale bf16 [B][D] (sample stride mod_batch_stride).
+ * y_fp8 [B*L, ldy] and/or y_bf16 [B*L, ldy_bf16] (either may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int fluxb200_ln_mod_quant(const void* x, int64_t ldx, const void* shift, const void* scale,
+                          int64_t mod_batch_stride, void* y_fp8, int64_t ldy, void* y_bf16, int64_t ldy_bf16,
+                          const float* in_scale, int fmt, int B, int L, int D, float eps,
+                          fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone QKNorm + apply_rope on [B,H,S,128] tensors (modules/flux_model.py:164, 60-65).
+ * norm_w may be NULL (skip RMSNorm); cos/sin may be NULL (skip RoPE).  In-place allowed.
+ * ------------------------------------------------------------------------------------------- */
+int fluxb200_qknorm_rope(const void* x, void* y, const float* norm_w, const void* rope_cos,
+                         const void* rope_sin, int64_t rope_batch_stride, int B, int H, int S, float eps,
+                         fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * attention(): F.scaled_dot_product_attention(q,k,v) + transpose/reshape to [B,S,H*128]
+ *   modules/flux_model.py:41-45 (RoPE is applied by the producer of q,k).
+ * q,k,v bf16 [B,H,S,128] contiguous.  out[b, s, h*128 + d]: row stride ldo elements.
+ * out_kind 0: bf16.  out_kind 1: fp8 = quantize(bf16(o), scale) where rows s < split_row use
+ * *out_scale0 and the others *out_scale1 (txt / img proj input scales; equal for single blocks).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fluxb200_attention_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int64_t ldo;
+  int64_t out_batch_stride; /* elements between samples of out */
+  int32_t B, H, S;
+  float softmax_scale; /* 1/sqrt(128) */
+  int32_t out_kind;
+  int32_t out_fmt;
+  int32_t split_row;
+  int32_t variant; /* 0 = default; other values select experimental tilings */
+  const float* out_scale0;
+  const float* out_scale1;
+} fluxb200_attention_args;
+
+int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUX_B200_H_ */
