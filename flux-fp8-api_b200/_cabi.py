@@ -96,6 +96,9 @@ class AttentionArgs(C.Structure):
         ("variant", C.c_int32),
         ("out_scale0", C.c_void_p),
         ("out_scale1", C.c_void_p),
+        ("out1", C.c_void_p),
+        ("ldo1", C.c_int64),
+        ("out1_batch_stride", C.c_int64),
     ]
 
 
@@ -144,10 +147,17 @@ def load() -> C.CDLL:
     return lib
 
 
+#: number of kernels launched through the C ABI by this process (every successful entry-point call except
+#: version / last_error / device_check is exactly one kernel launch)
+LAUNCHES = 0
+
+
 def check(rc: int, what: str) -> None:
     """Translate a negative return code into the exception class the reference would raise
     (ValueError for bad shapes, RuntimeError otherwise; SURVEY.md section 8b 'Error conventions')."""
     if rc == 0:
+        global LAUNCHES
+        LAUNCHES += 1
         return
     msg = load().fluxb200_last_error().decode("utf-8", "replace")
     if rc == ERR_INVALID:

@@ -344,7 +344,11 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
     tc_fence_after();
     const float inv_l = 1.f / l;
     const bool valid = qrow < a.S;
-    const int64_t obase = static_cast<int64_t>(b) * a.out_batch_stride + static_cast<int64_t>(qrow) * a.ldo + h * kD;
+    const bool second = a.out1 != nullptr && qrow >= a.split_row;
+    void* const outp = second ? a.out1 : a.out;
+    const int64_t obase = second ? static_cast<int64_t>(b) * a.out1_batch_stride +
+                                       static_cast<int64_t>(qrow - a.split_row) * a.ldo1 + h * kD
+                                 : static_cast<int64_t>(b) * a.out_batch_stride + static_cast<int64_t>(qrow) * a.ldo + h * kD;
     float oscale = 1.f;
     if (a.out_kind == 1) oscale = __ldg(qrow < a.split_row ? a.out_scale0 : a.out_scale1);
 #pragma unroll 1
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       tmem_ld_wait();
       if (!valid) continue;
       if (a.out_kind == 0) {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + obase + c * 32);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + obase + c * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 o;
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
           dst[q] = o;
         }
       } else {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + obase + c * 32);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(outp) + obase + c * 32);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint32_t w[4];
@@ -431,6 +435,10 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
                    a.out_scale0 && a.out_scale1 && (a.out_fmt == 0 || a.out_fmt == 1),
                "fluxb200_attention: fp8 out needs 16-byte aligned rows and both scales");
   FB_REQUIRE(a.ldo >= static_cast<int64_t>(a.H) * kD, "fluxb200_attention: ldo < H*128");
+  if (a.out1 != nullptr)
+    FB_REQUIRE(a.ldo1 >= static_cast<int64_t>(a.H) * kD && a.ldo1 % 16 == 0 && a.out1_batch_stride % 16 == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.out1) & 15) == 0 && a.split_row >= 0,
+               "fluxb200_attention: bad second destination");
 
   AttnParams P;
   P.a = a;

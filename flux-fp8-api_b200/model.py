@@ -1,0 +1,205 @@
+"""Flux container: the caller of the hot path (reference: modules/flux_model.py:24-36, 95-155, 488-734;
+SURVEY.md row a11 / N1).  Same constructor, attribute names and forward signature as the reference's
+`Flux`, so reference checkpoints (BFL key layout, optionally prequantised) load with load_state_dict.
+
+The embedders and the final layer are < 0.03 % of the step's FLOPs and stay bf16 torch (cuBLAS) modules
+unless quantize_flow_embedder_layers is set (then they are F8Linear and run on our kernels).  What this
+container adds over the reference's per-step recomputation:
+
+`txt_in(txt)`, `vector_in(y)`, `guidance_in(...)` and the RoPE table are step-invariant: they are computed
+once per request and reused for every denoise step (the reference recomputes them each step,
+modules/flux_model.py:694-702).
+"""
+from __future__ import annotations
+
+import math
+import weakref
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _cabi as cabi
+from .blocks import DoubleStreamBlock, EmbedND, SingleStreamBlock, tensor_version
+from .f8linear import F8Linear
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class FluxParams:
+    in_channels: int = 64
+    vec_in_dim: int = 768
+    context_in_dim: int = 4096
+    hidden_size: int = 3072
+    mlp_ratio: float = 4.0
+    num_heads: int = 24
+    depth: int = 19
+    depth_single_blocks: int = 38
+    axes_dim: List[int] = field(default_factory=lambda: [16, 56, 56])
+    theta: int = 10_000
+    qkv_bias: bool = True
+    guidance_embed: bool = True
+
+
+@dataclass
+class FluxSpec:
+    """The subset of the reference's ModelSpec (util.py:38-79) that Flux.__init__ reads."""
+
+    params: FluxParams = field(default_factory=FluxParams)
+    prequantized_flow: bool = False
+    quantize_modulation: bool = True
+    quantize_flow_embedder_layers: bool = False
+
+
+def flux_dev_spec(**kw) -> FluxSpec:
+    """Flux.1-dev hyper-parameters (reference util.py:163-176)."""
+    return FluxSpec(params=FluxParams(guidance_embed=True), **kw)
+
+
+def flux_schnell_spec(**kw) -> FluxSpec:
+    return FluxSpec(params=FluxParams(guidance_embed=False), **kw)
+
+
+def timestep_embedding(t: Tensor, dim, max_period=10000, time_factor: float = 1000.0):
+    """Sinusoidal embedding, fp32 (reference modules/flux_model.py:95-116).  `t` keeps its own dtype for
+    the `time_factor * t` product (bf16 in the pipeline), as in the reference."""
+    t = time_factor * t
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=t.device) / half)
+    args = t[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+def _linear(in_f: int, out_f: int, f8: bool) -> nn.Module:
+    return F8Linear(in_features=in_f, out_features=out_f, bias=True) if f8 else nn.Linear(in_f, out_f, bias=True)
+
+
+class MLPEmbedder(nn.Module):
+    def __init__(self, in_dim: int, hidden_dim: int, prequantized: bool = False, quantized=False):
+        super().__init__()
+        f8 = prequantized and quantized
+        self.in_layer = _linear(in_dim, hidden_dim, f8)
+        self.silu = nn.SiLU()
+        self.out_layer = _linear(hidden_dim, hidden_dim, f8)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.out_layer(self.silu(self.in_layer(x)))
+
+
+class LastLayer(nn.Module):
+    def __init__(self, hidden_size: int, patch_size: int, out_channels: int):
+        super().__init__()
+        self.norm_final = nn.LayerNorm(hidden_size, elementwise_affine=False, eps=1e-6)
+        self.linear = nn.Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 2 * hidden_size, bias=True))
+
+    def forward(self, x: Tensor, vec: Tensor) -> Tensor:
+        shift, scale = self.adaLN_modulation(vec).chunk(2, dim=1)
+        x = (1 + scale[:, None, :]) * self.norm_final(x) + shift[:, None, :]
+        return self.linear(x)
+
+
+class _StepInvariantCache:
+    """Results that depend only on per-request inputs.  A hit needs the very same tensor objects (held by
+    weak reference, so a recycled address can never alias) with unchanged in-place version counters."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, name: str, tensors, compute):
+        hit = self._store.get(name)
+        if hit is not None:
+            refs, versions, val = hit
+            if all(r() is t for r, t in zip(refs, tensors)) and versions == tuple(tensor_version(t) for t in tensors):
+                return val
+        val = compute()
+        self._store[name] = (tuple(weakref.ref(t) for t in tensors), tuple(tensor_version(t) for t in tensors), val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+class Flux(nn.Module):
+    """Transformer model for flow matching on sequences (B200 hot path inside)."""
+
+    def __init__(self, config, dtype: torch.dtype = torch.float16):
+        super().__init__()
+        p = config.params
+        self.dtype = dtype
+        self.params = p
+        self.in_channels = self.out_channels = p.in_channels
+        self.loras: list = []
+        preq = config.prequantized_flow
+        q_embed = config.quantize_flow_embedder_layers and preq
+        q_mod = config.quantize_modulation and preq
+        if p.hidden_size % p.num_heads != 0:
+            raise ValueError(f"Hidden size {p.hidden_size} must be divisible by num_heads {p.num_heads}")
+        pe_dim = p.hidden_size // p.num_heads
+        if sum(p.axes_dim) != pe_dim:
+            raise ValueError(f"Got {p.axes_dim} but expected positional dim {pe_dim}")
+        self.hidden_size, self.num_heads = p.hidden_size, p.num_heads
+        self.pe_embedder = EmbedND(dim=pe_dim, theta=p.theta, axes_dim=p.axes_dim, dtype=self.dtype)
+        self.img_in = _linear(self.in_channels, self.hidden_size, q_embed)
+        self.time_in = MLPEmbedder(256, self.hidden_size, prequantized=preq, quantized=q_embed)
+        self.vector_in = MLPEmbedder(p.vec_in_dim, self.hidden_size, prequantized=preq, quantized=q_embed)
+        self.guidance_in = (MLPEmbedder(256, self.hidden_size, prequantized=preq, quantized=q_embed)
+                            if p.guidance_embed else nn.Identity())
+        self.txt_in = _linear(p.context_in_dim, self.hidden_size, q_embed)
+        self.double_blocks = nn.ModuleList([
+            DoubleStreamBlock(self.hidden_size, self.num_heads, mlp_ratio=p.mlp_ratio, qkv_bias=p.qkv_bias,
+                              dtype=self.dtype, quantized_modulation=q_mod, prequantized=preq)
+            for _ in range(p.depth)])
+        self.single_blocks = nn.ModuleList([
+            SingleStreamBlock(self.hidden_size, self.num_heads, mlp_ratio=p.mlp_ratio, dtype=self.dtype,
+                              quantized_modulation=q_mod, prequantized=preq)
+            for _ in range(p.depth_single_blocks)])
+        self.final_layer = LastLayer(self.hidden_size, 1, self.out_channels)
+        self._cache = _StepInvariantCache()
+        #: set False to recompute txt_in / vector_in / pe every step exactly as the reference does
+        self.cache_step_invariants = True
+
+    def reset_request_cache(self) -> None:
+        self._cache.clear()
+
+    def _invariants_cacheable(self) -> bool:
+        """While an embedder F8Linear is still calibrating it must see one call per step, like the reference."""
+        if not self.cache_step_invariants:
+            return False
+        for mod in (self.txt_in, self.vector_in, self.guidance_in):
+            for m in mod.modules():
+                if isinstance(m, F8Linear) and not m.frozen:
+                    return False
+        return True
+
+    def forward(self, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, timesteps: Tensor, y: Tensor,
+                guidance: Optional[Tensor] = None) -> Tensor:
+        if img.ndim != 3 or txt.ndim != 3:
+            raise ValueError("Input img and txt tensors must have 3 dimensions.")
+        cabi.require_cuda(img, txt)
+        cache = self._cache if self._invariants_cacheable() else _StepInvariantCache()
+
+        img = self.img_in(img)
+        vec = self.time_in(timestep_embedding(timesteps, 256).type(self.dtype))
+        if self.params.guidance_embed:
+            if guidance is None:
+                raise ValueError("Didn't get guidance strength for guidance distilled model.")
+            vec = vec + cache.get("guidance", (guidance,),
+                                  lambda: self.guidance_in(timestep_embedding(guidance, 256).type(self.dtype)))
+        vec = vec + cache.get("vector", (y,), lambda: self.vector_in(y))
+        txt = cache.get("txt", (txt,), lambda: self.txt_in(txt))
+        pe = cache.get("pe", (txt_ids, img_ids), lambda: self.pe_embedder(torch.cat((txt_ids, img_ids), dim=1)))
+
+        T = txt.shape[1]
+        for block in self.double_blocks:
+            img, txt = block(img=img, txt=txt, vec=vec, pe=pe)
+        x = torch.cat((txt, img), 1)
+        for block in self.single_blocks:
+            x = block(x, vec=vec, pe=pe)
+        x = x[:, T:, ...]
+        return self.final_layer(x, vec)

@@ -1,0 +1,250 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/flux_b200.h).
+
+These take torch CUDA tensors, allocate outputs with torch, and pass raw pointers plus the current
+stream to libflux_b200.so.  They do no arithmetic themselves.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi as cabi
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+
+
+def _contig(t: Tensor, what: str) -> Tensor:
+    if not t.is_contiguous():
+        raise ValueError(f"{what} must be contiguous")
+    return t
+
+
+def device_check() -> int:
+    n = C.c_int(0)
+    cabi.check(cabi.load().fluxb200_device_check(C.byref(n)), "fluxb200_device_check")
+    return n.value
+
+
+def quantize(x: Tensor, scale: Tensor, dtype: torch.dtype, out: Optional[Tensor] = None) -> Tensor:
+    """F8Linear.to_fp8_saturated(...).to(fp8)  (reference float8_quantize.py:217-218, 274-276)."""
+    cabi.require_cuda(x, scale)
+    if x.dtype != BF16:
+        raise ValueError(f"quantize expects bfloat16 activations, got {x.dtype}")
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    cabi.check(cabi.load().fluxb200_quantize(x.data_ptr(), out.data_ptr(), x.numel(), scale.data_ptr(),
+                                             cabi.fp8_fmt(dtype), cabi.stream_ptr()), "fluxb200_quantize")
+    return out
+
+
+def amax(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """torch.max(torch.abs(x)).float()  (reference float8_quantize.py:197, 227)."""
+    cabi.require_cuda(x)
+    if x.dtype != BF16:
+        raise ValueError(f"amax expects bfloat16, got {x.dtype}")
+    x = x.contiguous()
+    if out is None:
+        out = torch.zeros((), dtype=torch.float32, device=x.device)
+    cabi.check(cabi.load().fluxb200_amax(x.data_ptr(), x.numel(), out.data_ptr(), cabi.stream_ptr()), "fluxb200_amax")
+    return out
+
+
+def silu_quant(x: Tensor, scale: Optional[Tensor], dtype: Optional[torch.dtype], want_bf16: bool = False):
+    """Modulation prologue: (fp8 quantised silu(x), bf16 silu(x))."""
+    cabi.require_cuda(x)
+    x = x.contiguous()
+    yq = torch.empty(x.shape, dtype=dtype, device=x.device) if dtype is not None else None
+    yb = torch.empty_like(x) if want_bf16 else None
+    cabi.check(cabi.load().fluxb200_silu_quant(x.data_ptr(), cabi.ptr(yq), cabi.ptr(yb), x.numel(), cabi.ptr(scale),
+                                               cabi.fp8_fmt(dtype) if dtype is not None else 0, cabi.stream_ptr()),
+               "fluxb200_silu_quant")
+    return yq, yb
+
+
+def ln_mod_quant(x: Tensor, shift: Tensor, scale: Tensor, in_scale: Optional[Tensor], dtype: Optional[torch.dtype],
+                 out_fp8: Optional[Tensor] = None, want_bf16: bool = False, eps: float = 1e-6):
+    """LayerNorm(no affine) -> (1+scale)*x+shift -> quantise.  x [B,L,D]; shift/scale [B,1,D] or [B,D]
+    (possibly strided views into the modulation output)."""
+    cabi.require_cuda(x, shift, scale)
+    B, L, D = x.shape
+    if x.stride(-1) != 1 or x.stride(0) != L * x.stride(1):
+        x = x.contiguous()
+    sh = shift.reshape(B, D) if shift.dim() == 3 else shift
+    sc = scale.reshape(B, D) if scale.dim() == 3 else scale
+    if sh.stride(-1) != 1 or sc.stride(-1) != 1 or sh.stride(0) != sc.stride(0):
+        sh, sc = sh.contiguous(), sc.contiguous()
+    yq = out_fp8
+    if yq is None and dtype is not None:
+        yq = torch.empty((B, L, D), dtype=dtype, device=x.device)
+    yb = torch.empty((B, L, D), dtype=BF16, device=x.device) if want_bf16 else None
+    cabi.check(cabi.load().fluxb200_ln_mod_quant(
+        x.data_ptr(), x.stride(1), sh.data_ptr(), sc.data_ptr(), sh.stride(0) if B > 1 else D,
+        cabi.ptr(yq), yq.stride(-2) if yq is not None else 0, cabi.ptr(yb), D, cabi.ptr(in_scale),
+        cabi.fp8_fmt(dtype) if dtype is not None else 0, B, L, D, eps, cabi.stream_ptr()), "fluxb200_ln_mod_quant")
+    return yq, yb
+
+
+def qknorm_rope(x: Tensor, norm_w: Optional[Tensor], cos: Optional[Tensor], sin: Optional[Tensor]) -> Tensor:
+    """Stand-alone QKNorm + RoPE on [B,H,S,128] (cos/sin: bf16 [Bp,S,64], Bp in {1,B})."""
+    cabi.require_cuda(x)
+    B, H, S, D = x.shape
+    if D != 128:
+        raise ValueError("head_dim must be 128")
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    bstride = 0
+    if cos is not None:
+        cos, sin = cos.contiguous(), sin.contiguous()
+        bstride = cos.stride(0) if cos.shape[0] > 1 else 0
+    cabi.check(cabi.load().fluxb200_qknorm_rope(x.data_ptr(), y.data_ptr(), cabi.ptr(norm_w), cabi.ptr(cos),
+                                                cabi.ptr(sin), bstride, B, H, S, 1e-6, cabi.stream_ptr()),
+               "fluxb200_qknorm_rope")
+    return y
+
+
+def f8_gemv(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tensor, w_scale_recip: Tensor) -> Tensor:
+    cabi.require_cuda(a, w)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=BF16, device=a.device)
+    cabi.check(cabi.load().fluxb200_f8_gemv(a.data_ptr(), cabi.fp8_fmt(a.dtype), w.data_ptr(), cabi.fp8_fmt(w.dtype),
+                                            cabi.ptr(bias), a_scale_recip.data_ptr(), w_scale_recip.data_ptr(),
+                                            out.data_ptr(), M, N, K, cabi.stream_ptr()), "fluxb200_f8_gemv")
+    return out
+
+
+def gemm_args(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tensor, w_scale_recip: Tensor,
+              epilogue: int) -> cabi.GemmArgs:
+    cabi.require_cuda(a, w, bias, a_scale_recip, w_scale_recip)
+    if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1]:
+        raise ValueError(f"f8_gemm: incompatible shapes {tuple(a.shape)} x {tuple(w.shape)}^T")
+    _contig(a, "A"), _contig(w, "W")
+    g = cabi.GemmArgs()
+    g.a, g.w, g.bias = a.data_ptr(), w.data_ptr(), cabi.ptr(bias)
+    g.a_scale_recip, g.w_scale_recip = a_scale_recip.data_ptr(), w_scale_recip.data_ptr()
+    g.M, g.K = a.shape
+    g.N = w.shape[0]
+    g.a_fmt, g.w_fmt = cabi.fp8_fmt(a.dtype), cabi.fp8_fmt(w.dtype)
+    g.epilogue = epilogue
+    return g
+
+
+#: when set to a list, run_gemm / attention append (kind, flops, start_event, end_event) per launch: CUDA-event
+#: timing of individual kernels on the launching stream (bench.py's roofline pass)
+KERNEL_TIMELINE = None
+
+
+def _timed(kind: str, flops: float, launch) -> None:
+    if KERNEL_TIMELINE is None:
+        launch()
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    launch()
+    e.record()
+    KERNEL_TIMELINE.append((kind, flops, s, e))
+
+
+def run_gemm(g: cabi.GemmArgs) -> None:
+    _timed("f8_gemm", 2.0 * g.M * g.N * g.K,
+           lambda: cabi.check(cabi.load().fluxb200_f8_gemm(C.byref(g), cabi.stream_ptr()), "fluxb200_f8_gemm"))
+
+
+def f8_gemm(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tensor, w_scale_recip: Tensor,
+            out: Optional[Tensor] = None) -> Tensor:
+    """bf16( (A.W^T) * sa * sw + bias ): the torch._scaled_mm call of F8Linear.forward."""
+    g = gemm_args(a, w, bias, a_scale_recip, w_scale_recip, cabi.EPI_PLAIN)
+    if g.M <= 16 and g.K % 16 == 0 and g.K * 8 <= 200 * 1024:
+        return f8_gemv(a, w, bias, a_scale_recip, w_scale_recip)
+    if out is None:
+        out = torch.empty((g.M, g.N), dtype=BF16, device=a.device)
+    g.out, g.ldo = out.data_ptr(), out.stride(0)
+    run_gemm(g)
+    return out
+
+
+def f8_gemm_gate_residual(a, w, bias, sa, sw, resid: Tensor, gate: Tensor, rows_per_batch: int,
+                          out: Optional[Tensor] = None) -> Tensor:
+    """out = resid + gate[b] * linear(a)   (resid [M,N] bf16 view, gate [B,N] view)."""
+    g = gemm_args(a, w, bias, sa, sw, cabi.EPI_GATE_RESIDUAL)
+    if out is None:
+        out = torch.empty((g.M, g.N), dtype=BF16, device=a.device)
+    g.out, g.ldo = out.data_ptr(), out.stride(0)
+    g.resid, g.ldr = resid.data_ptr(), resid.stride(0)
+    g.gate, g.gate_batch_stride = gate.data_ptr(), gate.stride(0)
+    g.rows_per_batch = rows_per_batch
+    run_gemm(g)
+    return out
+
+
+def f8_gemm_gelu_quant(a, w, bias, sa, sw, out_scale: Tensor, out_dtype: torch.dtype, out: Optional[Tensor] = None,
+                       out_col_offset: int = 0) -> Tensor:
+    g = gemm_args(a, w, bias, sa, sw, cabi.EPI_GELU_QUANT)
+    if out is None:
+        out = torch.empty((g.M, g.N), dtype=out_dtype, device=a.device)
+    g.out, g.ldo = out.data_ptr(), out.stride(0)
+    g.out_scale, g.out_fmt, g.out_col_offset = out_scale.data_ptr(), cabi.fp8_fmt(out_dtype), out_col_offset
+    run_gemm(g)
+    return out
+
+
+def f8_gemm_qkv_rope(a, w, bias, sa, sw, q: Tensor, k: Tensor, v: Tensor, q_norm_w: Tensor, k_norm_w: Tensor,
+                     cos: Tensor, sin: Tensor, rows_per_batch: int, seq_offset: int,
+                     mlp_out: Optional[Tensor] = None, mlp_scale: Optional[Tensor] = None,
+                     mlp_col_offset: int = 0) -> None:
+    """QKV (or SingleStreamBlock.linear1 when mlp_out is given) GEMM writing normalised+rotated q,k and v
+    straight into the joint [B,H,S,128] buffers."""
+    epi = cabi.EPI_LINEAR1 if mlp_out is not None else cabi.EPI_QKV_ROPE
+    g = gemm_args(a, w, bias, sa, sw, epi)
+    B, H, S, D = q.shape
+    g.q, g.k, g.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    g.num_heads, g.seq_total, g.seq_offset = H, S, seq_offset
+    g.rows_per_batch = rows_per_batch
+    g.q_norm_w, g.k_norm_w = q_norm_w.data_ptr(), k_norm_w.data_ptr()
+    g.rope_cos, g.rope_sin = cos.data_ptr(), sin.data_ptr()
+    g.rope_batch_stride = cos.stride(0) if cos.shape[0] > 1 else 0
+    if mlp_out is not None:
+        g.out, g.ldo = mlp_out.data_ptr(), mlp_out.stride(0)
+        g.out_scale, g.out_fmt, g.out_col_offset = mlp_scale.data_ptr(), cabi.fp8_fmt(mlp_out.dtype), mlp_col_offset
+    run_gemm(g)
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, out: Optional[Tensor] = None, out_scale0: Optional[Tensor] = None,
+              out_scale1: Optional[Tensor] = None, split_row: int = 0, variant: int = 0,
+              out1: Optional[Tensor] = None) -> Tensor:
+    """softmax(q k^T / sqrt(d)) v on [B,H,S,128] -> [B,S,H*128] (bf16, or fp8 when `out` is an fp8 tensor
+    and scales are given; `out` may be a column-slice view of a wider buffer).  With `out1`, rows
+    [0, split_row) go to `out` and rows [split_row, S) to `out1` (txt / img streams of a double block)."""
+    cabi.require_cuda(q, k, v)
+    B, H, S, D = q.shape
+    if D != 128:
+        raise ValueError("head_dim must be 128")
+    _contig(q, "q"), _contig(k, "k"), _contig(v, "v")
+    if out is None:
+        out = torch.empty((B, S, H * D), dtype=BF16, device=q.device)
+    a = cabi.AttentionArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.ldo, a.out_batch_stride = out.stride(1), out.stride(0)
+    a.B, a.H, a.S = B, H, S
+    a.softmax_scale = 1.0 / math.sqrt(D)
+    a.variant = variant
+    if out.dtype == BF16:
+        a.out_kind = 0
+    else:
+        a.out_kind, a.out_fmt = 1, cabi.fp8_fmt(out.dtype)
+        a.out_scale0 = out_scale0.data_ptr()
+        a.out_scale1 = (out_scale1 if out_scale1 is not None else out_scale0).data_ptr()
+    a.split_row = split_row
+    if out1 is not None:
+        # rows >= split_row go to out1 ([B, S - split_row, H*128], same dtype as out)
+        if out1.dtype != out.dtype:
+            raise ValueError("attention: out and out1 must share a dtype")
+        a.out1, a.ldo1, a.out1_batch_stride = out1.data_ptr(), out1.stride(1), out1.stride(0)
+    _timed("attention", 4.0 * B * H * S * S * D,
+           lambda: cabi.check(cabi.load().fluxb200_attention(C.byref(a), cabi.stream_ptr()), "fluxb200_attention"))
+    return out

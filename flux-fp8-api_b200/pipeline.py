@@ -1,0 +1,264 @@
+"""Denoise-loop orchestration around Flux.forward (reference: flux_pipeline.py:234-344, 347-371, 627-651).
+
+The reference's FluxPipeline.generate keeps the loop in Python and this stays so (BASELINE.json:
+"flux_pipeline.denoise stays as orchestrator"); text encoders, VAE and JPEG encoding are out of scope
+(SURVEY.md section 2).  What lives here:
+
+* the pieces of `prepare` / `get_noise` / `get_schedule` that shape the transformer's inputs
+* `denoise()`: the Euler loop of generate() (flux_pipeline.py:627-651)
+* `GraphedStep`: one whole Flux.forward + Euler update captured in a CUDA graph (static shapes, static
+  buffers), replayed once per step -- the B200 replacement for the reference's per-block torch.compile
+* synthetic weights / inputs of the published Flux shapes (there is no checkpoint or network here)
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional
+
+import torch
+from torch import Tensor, nn
+
+from .f8linear import F8Linear, quantize_flow_transformer_and_dispatch_float8
+from .model import Flux, FluxSpec
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------
+# schedule / input shaping
+# ------------------------------------------------------------------------------------------------
+def time_shift(mu: float, sigma: float, t: Tensor) -> Tensor:
+    return math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** sigma)
+
+
+def get_schedule(num_steps: int, image_seq_len: int, base_shift: float = 0.5, max_shift: float = 1.15,
+                 shift: bool = True) -> List[float]:
+    """num_steps+1 timesteps from 1 to 0, shifted towards high noise for large images (dev only)."""
+    ts = torch.linspace(1, 0, num_steps + 1)
+    if shift:
+        slope = (max_shift - base_shift) / (4096 - 256)
+        mu = slope * image_seq_len + (base_shift - slope * 256)
+        ts = time_shift(mu, 1.0, ts)
+    return ts.tolist()
+
+
+def patchify(latent: Tensor) -> Tensor:
+    """[B,16,h,w] latent -> [B,(h/2)(w/2),64] tokens of 2x2 patches (flux_pipeline.py:270-271)."""
+    x = latent.unfold(2, 2, 2).unfold(3, 2, 2).permute(0, 2, 3, 1, 4, 5)
+    return x.reshape(x.shape[0], -1, x.shape[3] * x.shape[4] * x.shape[5])
+
+
+def make_img_ids(batch: int, h2: int, w2: int, device, dtype=BF16) -> Tensor:
+    """Position ids (0, row, col) of the token grid (flux_pipeline.py:280-292)."""
+    ids = torch.zeros(h2, w2, 3, device=device, dtype=dtype)
+    ids[..., 1] = ids[..., 1] + torch.arange(h2, device=device, dtype=dtype)[:, None]
+    ids[..., 2] = ids[..., 2] + torch.arange(w2, device=device, dtype=dtype)[None, :]
+    return ids[None].repeat(batch, 1, 1, 1).flatten(1, 2)
+
+
+def synthetic_request(params, height: int, width: int, batch: int, text_len: int, device, seed: int = 0,
+                      guidance: float = 3.5, sample_offset: int = 0) -> Dict[str, Tensor]:
+    """Latents and text embeddings of the shapes generate() feeds the transformer, from per-sample seeds
+    (sample i uses seed + sample_offset + i, so a batch shard reproduces the same samples)."""
+    h8, w8 = 2 * math.ceil(height / 16), 2 * math.ceil(width / 16)
+    lat, txt, y = [], [], []
+    for i in range(batch):
+        g = torch.Generator(device=device).manual_seed(seed + sample_offset + i)
+        lat.append(torch.randn(1, 16, h8, w8, device=device, dtype=BF16, generator=g))
+        txt.append(0.15 * torch.randn(1, text_len, params.context_in_dim, device=device, dtype=torch.float32, generator=g))
+        y.append(torch.randn(1, params.vec_in_dim, device=device, dtype=torch.float32, generator=g))
+    img = patchify(torch.cat(lat))
+    return dict(
+        img=img.contiguous(),
+        img_ids=make_img_ids(batch, h8 // 2, w8 // 2, device),
+        txt=torch.cat(txt).to(BF16),
+        txt_ids=torch.zeros(batch, text_len, 3, device=device, dtype=BF16),
+        y=torch.cat(y).to(BF16),
+        guidance=torch.full((batch,), guidance, device=device, dtype=BF16),
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic model
+# ------------------------------------------------------------------------------------------------
+@torch.inference_mode()
+def init_synthetic_weights(model: nn.Module, seed: int = 1234) -> None:
+    """Seeded stand-in for the BFL checkpoint: Linear W ~ N(0, 0.02^2), bias
+    ~ N(0, 0.02^2), modulation W ~ N(0, 0.01^2) / bias 0, QK-norm scale = 1 + N(0, 0.05^2).
+    Generated layer by layer on the model's device in fp32, stored bf16."""
+    from .blocks import Modulation, RMSNorm
+
+    mod_lins = {id(m.lin) for m in model.modules() if isinstance(m, Modulation)}
+    dev = next(model.parameters()).device
+    g = torch.Generator(device=dev).manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, nn.Linear):
+            is_mod = id(m) in mod_lins
+            m.weight.copy_(torch.randn(m.weight.shape, device=dev, generator=g) * (0.01 if is_mod else 0.02))
+            if m.bias is not None:
+                if is_mod:
+                    m.bias.zero_()
+                else:
+                    m.bias.copy_(torch.randn(m.bias.shape, device=dev, generator=g) * 0.02)
+        elif isinstance(m, RMSNorm):
+            m.scale.copy_(1 + 0.05 * torch.randn(m.scale.shape, device=dev, generator=g))
+
+
+@torch.inference_mode()
+def build_synthetic_flux(spec: FluxSpec, device, seed: int = 1234, quantize: bool = True) -> Flux:
+    """bf16 Flux with synthetic weights on `device`, then the reference flow: swap linears to F8Linear and
+    quantise (quantize_flow_transformer_and_dispatch_float8).  Input scales still need calibrate()."""
+    spec_build = FluxSpec(params=spec.params, prequantized_flow=False, quantize_modulation=spec.quantize_modulation,
+                          quantize_flow_embedder_layers=spec.quantize_flow_embedder_layers)
+    with torch.device(device):
+        model = Flux(spec_build, dtype=BF16).to(BF16)
+    init_synthetic_weights(model, seed)
+    model.eval()
+    if quantize:
+        quantize_flow_transformer_and_dispatch_float8(
+            model, torch.device(device), offload_flow=False, swap_linears_with_cublaslinear=False, flow_dtype=BF16,
+            quantize_modulation=spec.quantize_modulation,
+            quantize_flow_embedder_layers=spec.quantize_flow_embedder_layers)
+    return model
+
+
+def all_frozen(model: nn.Module) -> bool:
+    return all(m.frozen for m in model.modules() if isinstance(m, F8Linear))
+
+
+@torch.inference_mode()
+def calibrate(model: Flux, request: Dict[str, Tensor], num_steps: int = 13, shift: bool = True) -> None:
+    """Freeze every F8Linear input scale the way the reference's warm-up generate does
+    (flux_pipeline.py:197-212): run `num_steps` >= 13 denoise steps in eager mode."""
+    denoise(model, dict(request), get_schedule(num_steps, request["img"].shape[1], shift=shift))
+    if not all_frozen(model):
+        raise RuntimeError("calibration did not freeze every F8Linear input scale (need > num_scale_trials calls)")
+
+
+# ------------------------------------------------------------------------------------------------
+# denoise loop
+# ------------------------------------------------------------------------------------------------
+@torch.inference_mode()
+def denoise(model: Callable, request: Dict[str, Tensor], timesteps: List[float],
+            step_fn: Optional[Callable] = None) -> Tensor:
+    """Euler integration of the flow (flux_pipeline.py:627-651): per step t_vec.fill_(t_curr);
+    pred = model(...); img = img + (t_prev - t_curr) * pred."""
+    img = request["img"]
+    t_vec = None
+    for t_curr, t_prev in zip(timesteps[:-1], timesteps[1:]):
+        if t_vec is None:
+            t_vec = torch.full((img.shape[0],), t_curr, dtype=img.dtype, device=img.device)
+        else:
+            t_vec = t_vec.reshape((img.shape[0],)).fill_(t_curr)
+        if step_fn is not None:
+            img = step_fn(img, t_vec, t_prev - t_curr)
+            continue
+        pred = model(img=img, img_ids=request["img_ids"], txt=request["txt"], txt_ids=request["txt_ids"],
+                     y=request["y"], timesteps=t_vec, guidance=request.get("guidance"))
+        img = img + (t_prev - t_curr) * pred
+    return img
+
+
+class GraphedStep:
+    """One denoise step (Flux.forward + Euler update) as a CUDA graph over static buffers.
+
+    Every kernel of the step -- ours through the C ABI and the few torch ops of the embedders -- is
+    captured once for a fixed (batch, L, T) and replayed per step; TMA descriptors are encoded at capture
+    time and baked into the kernel parameters.  Per step the host only copies the latent and the two
+    scalars (t, dt) into the static inputs."""
+
+    def __init__(self, model: Flux, request: Dict[str, Tensor], warmup: int = 2):
+        if not all_frozen(model):
+            raise RuntimeError("GraphedStep needs frozen input scales: run calibrate() first")
+        self.model = model
+        self.req = request
+        dev = request["img"].device
+        self.img = request["img"].clone()
+        self.t_vec = torch.zeros((self.img.shape[0],), dtype=self.img.dtype, device=dev)
+        self.dt = torch.zeros((), dtype=torch.float32, device=dev)
+        self.out = torch.empty_like(self.img)
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream), torch.inference_mode():
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.inference_mode(), torch.cuda.graph(self.graph, stream=stream):
+            self._step()
+
+    def _step(self):
+        r = self.req
+        pred = self.model(img=self.img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
+                          timesteps=self.t_vec, guidance=r.get("guidance"))
+        # img + (t_prev - t_curr) * pred: eager torch multiplies in fp32 by the python scalar, rounds the product
+        # to bf16, then adds in bf16 -- reproduced with the fp32 0-dim `dt`
+        self.out.copy_(self.img + (self.dt * pred.float()).to(pred.dtype))
+
+    def __call__(self, img: Tensor, t_vec: Tensor, dt: float) -> Tensor:
+        self.img.copy_(img)
+        self.t_vec.copy_(t_vec)
+        self.dt.fill_(dt)
+        self.graph.replay()
+        return self.out.clone()
+
+
+class DenoiseSession:
+    """Public per-request API: owns the (graph-captured) step for one request shape and moves latents
+    between pinned host memory and the device.
+
+        sess = DenoiseSession(model, request)              # captures the CUDA graph
+        latent = sess.run(timesteps)                        # whole loop, latents stay in HBM
+        host_out = sess.step_host(host_in, t_curr, t_prev)  # one step, host -> device -> host
+    """
+
+    def __init__(self, model: Flux, request: Dict[str, Tensor], use_graph: bool = True):
+        self.model, self.request = model, request
+        self.step = GraphedStep(model, request) if use_graph else None
+        img = request["img"]
+        self._host_in = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+        self._host_out = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+        self._dev_in = torch.empty_like(img)
+        self._t_vec = torch.zeros((img.shape[0],), dtype=img.dtype, device=img.device)
+        self._t_host = torch.zeros((img.shape[0],), dtype=img.dtype, pin_memory=True)
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self._host_in.numel() * self._host_in.element_size() + self._t_host.numel() * self._t_host.element_size()
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return self._host_out.numel() * self._host_out.element_size()
+
+    @torch.inference_mode()
+    def run(self, timesteps: List[float]) -> Tensor:
+        return denoise(self.model, self.request, timesteps, step_fn=self.step)
+
+    @torch.inference_mode()
+    def step_device(self, img: Tensor, t_curr: float, t_prev: float) -> Tensor:
+        self._t_vec.fill_(t_curr)
+        if self.step is not None:
+            return self.step(img, self._t_vec, t_prev - t_curr)
+        r = self.request
+        pred = self.model(img=img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
+                          timesteps=self._t_vec, guidance=r.get("guidance"))
+        return img + (t_prev - t_curr) * pred
+
+    @torch.inference_mode()
+    def step_host(self, img_host: Tensor, t_curr: float, t_prev: float) -> Tensor:
+        """One denoise step with HOST buffers: pinned H2D copy of the latent and timestep, the step on the
+        device, D2H copy of the updated latent (synchronises before returning)."""
+        self._host_in.copy_(img_host)
+        self._t_host.fill_(t_curr)
+        self._dev_in.copy_(self._host_in, non_blocking=True)
+        self._t_vec.copy_(self._t_host, non_blocking=True)
+        if self.step is not None:
+            out = self.step(self._dev_in, self._t_vec, t_prev - t_curr)
+        else:
+            r = self.request
+            pred = self.model(img=self._dev_in, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
+                              timesteps=self._t_vec, guidance=r.get("guidance"))
+            out = self._dev_in + (t_prev - t_curr) * pred
+        self._host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._host_out

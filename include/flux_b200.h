@@ -170,6 +170,12 @@ typedef struct fluxb200_attention_args {
   int32_t variant; /* 0 = default; other values select experimental tilings */
   const float* out_scale0;
   const float* out_scale1;
+  /* Optional second destination: when out1 != NULL, rows s >= split_row are written to
+     out1[b*out1_batch_stride + (s - split_row)*ldo1 + h*128 + d] instead of `out`
+     (DoubleStreamBlock: txt rows feed txt_attn.proj, img rows img_attn.proj). */
+  void* out1;
+  int64_t ldo1;
+  int64_t out1_batch_stride;
 } fluxb200_attention_args;
 
 int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_stream_t stream);

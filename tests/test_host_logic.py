@@ -1,0 +1,133 @@
+"""CPU: host-side mirror of the reference interface -- state-dict format, error conventions, schedule and
+input shaping, request cache, batch sharding arithmetic (no kernels are launched)."""
+import os
+
+import pytest
+import torch
+from torch import nn
+
+from flux_fp8_api_b200 import model as M
+from flux_fp8_api_b200 import parallel as PAR
+from flux_fp8_api_b200 import pipeline as PL
+from flux_fp8_api_b200.f8linear import F8Linear, mul_scale
+from oracle import flux_oracle as O
+
+BF16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def tiny(golden_dir):
+    return torch.load(os.path.join(golden_dir, "flux_tiny.pt"))
+
+
+def tiny_spec(tiny, **kw):
+    return M.FluxSpec(params=M.FluxParams(**tiny["tiny"]), **kw)
+
+
+def test_state_dict_keys_match_the_reference(tiny):
+    net = M.Flux(tiny_spec(tiny, prequantized_flow=True), dtype=BF16)
+    missing, unexpected = net.load_state_dict(tiny["state"], strict=True)
+    assert not missing and not unexpected
+    assert set(net.state_dict().keys()) == set(tiny["state"].keys())
+    assert PL.all_frozen(net)
+    lin = net.double_blocks[0].img_attn.qkv
+    assert isinstance(lin, F8Linear) and lin.float8_data.dtype == torch.float8_e4m3fn
+    assert lin.weight.shape == (1,) and lin.weight.dtype == BF16  # placeholder defines the output dtype
+    assert lin.input_scale.dtype == torch.float32 and lin.input_scale.dim() == 0
+    assert lin.trial_index == lin.num_scale_trials
+
+
+def test_unquantised_layout_has_plain_linears(tiny):
+    net = M.Flux(tiny_spec(tiny, prequantized_flow=False), dtype=BF16)
+    assert not any(isinstance(m, F8Linear) for m in net.modules())
+    assert isinstance(net.double_blocks[0].img_mod.lin, nn.Linear)
+    net2 = M.Flux(tiny_spec(tiny, prequantized_flow=True, quantize_modulation=False), dtype=BF16)
+    assert isinstance(net2.double_blocks[0].img_mod.lin, nn.Linear)
+    assert isinstance(net2.double_blocks[0].img_attn.qkv, F8Linear)
+    assert isinstance(net2.img_in, nn.Linear)
+    net3 = M.Flux(tiny_spec(tiny, prequantized_flow=True, quantize_flow_embedder_layers=True), dtype=BF16)
+    assert isinstance(net3.img_in, F8Linear) and isinstance(net3.time_in.in_layer, F8Linear)
+    assert isinstance(net3.final_layer.linear, nn.Linear)
+
+
+def test_f8linear_load_cases(tiny):
+    sd = {k[len("double_blocks.0.img_attn.proj."):]: v for k, v in tiny["state"].items()
+          if k.startswith("double_blocks.0.img_attn.proj.")}
+    full = F8Linear(256, 256, dtype=BF16)
+    full.load_state_dict(sd)
+    assert full.frozen
+    # weight scales only -> input scale must be re-calibrated (reference float8_quantize.py:154-178)
+    partial = {k: v for k, v in sd.items() if not k.startswith("input_scale")}
+    lin = F8Linear(256, 256, dtype=BF16)
+    lin.load_state_dict(partial, strict=False)
+    assert lin.weight_initialized and not lin.input_scale_initialized and lin.trial_index == 0
+    # malformed
+    with pytest.raises(RuntimeError):
+        F8Linear(256, 256, dtype=BF16).load_state_dict({"bias": sd["bias"]}, strict=False)
+    bad = dict(sd)
+    bad["float8_data"] = sd["float8_data"][:128]
+    with pytest.raises(RuntimeError):
+        F8Linear(256, 256, dtype=BF16).load_state_dict(bad)
+
+
+def test_flux_constructor_errors():
+    with pytest.raises(ValueError):
+        M.Flux(M.FluxSpec(params=M.FluxParams(hidden_size=250, num_heads=4)))
+    with pytest.raises(ValueError):
+        M.Flux(M.FluxSpec(params=M.FluxParams(hidden_size=256, num_heads=2, axes_dim=[16, 56, 40], depth=0,
+                                              depth_single_blocks=0)))
+
+
+def test_scale_semantics_switch():
+    import flux_fp8_api_b200.f8linear as f8
+
+    s = torch.tensor(57344.0 / 5.0)
+    assert f8.SCALE_SEMANTICS == "cuda"
+    assert mul_scale(s).item() == s.to(BF16).float().item() != s.item()
+    f8.SCALE_SEMANTICS = "cpu"
+    try:
+        assert mul_scale(s) is s
+    finally:
+        f8.SCALE_SEMANTICS = "cuda"
+    assert mul_scale(torch.tensor(448.0)).item() == 448.0  # weight scale of real checkpoints is bf16-exact
+
+
+def test_schedule_and_input_shaping_match_the_oracle():
+    for steps, L, shift in [(28, 4096, True), (4, 4096, False), (50, 9216, True), (13, 64, True)]:
+        assert PL.get_schedule(steps, L, shift=shift) == O.get_schedule(steps, L, shift=shift)
+    ids = PL.make_img_ids(2, 6, 10, "cpu")
+    assert torch.equal(ids, O.make_img_ids(2, 6, 10, BF16))
+    lat = torch.arange(2 * 16 * 4 * 6, dtype=torch.float32).reshape(2, 16, 4, 6)
+    tok = PL.patchify(lat)
+    assert tok.shape == (2, 6, 64)
+    assert torch.equal(tok[0, 0].reshape(16, 2, 2), lat[0, :, 0:2, 0:2])
+    params = M.FluxParams()
+    req = PL.synthetic_request(params, 64, 48, 3, 32, "cpu", seed=5)
+    assert req["img"].shape == (3, 12, 64) and req["txt"].shape == (3, 32, 4096) and req["y"].shape == (3, 768)
+    shard = PL.synthetic_request(params, 64, 48, 1, 32, "cpu", seed=5, sample_offset=2)
+    assert torch.equal(shard["img"][0], req["img"][2]) and torch.equal(shard["txt"][0], req["txt"][2])
+
+
+def test_step_invariant_cache_never_aliases():
+    c = M._StepInvariantCache()
+    calls = []
+    a = torch.zeros(3)
+    f = lambda: calls.append(1) or len(calls)
+    assert c.get("k", (a,), f) == 1 and c.get("k", (a,), f) == 1
+    a.add_(1)  # in-place change -> recompute
+    assert c.get("k", (a,), f) == 2
+    b = torch.zeros(3)  # a different tensor object -> recompute even if it had the same address/shape
+    assert c.get("k", (b,), f) == 3
+
+
+def test_shard_ranges_partition_the_batch():
+    for total in range(0, 20):
+        for world in (1, 2, 3, 4, 8):
+            spans = [PAR.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    req = {"img": torch.arange(8)[:, None], "txt": torch.arange(8)[:, None] * 10, "note": 3}
+    got = torch.cat([PAR.shard_request(req, r, 4)["img"] for r in range(4)])
+    assert torch.equal(got, req["img"]) and PAR.shard_request(req, 1, 4)["note"] == 3

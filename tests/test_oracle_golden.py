@@ -1,0 +1,124 @@
+"""CPU: the oracle (oracle/flux_oracle.py) against the committed reference outputs in tests/golden/
+(minted from the unmodified reference by oracle/make_golden.py).  No /root/reference needed."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import flux_oracle as O
+
+BF16 = torch.bfloat16
+
+
+def load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name))
+
+
+def dt_of(s):
+    return torch.float8_e5m2 if "e5m2" in s else torch.float8_e4m3fn
+
+
+def maxdiff(a, b):
+    return (a.float() - b.float()).abs().max().item()
+
+
+def test_quantize_is_bit_exact(golden_dir):
+    g = load(golden_dir, "quantize.pt")
+    assert len(g["cases"]) == 12
+    for c in g["cases"]:
+        dt = dt_of(c["dtype"])
+        scale = O.amax_to_scale(torch.tensor(c["amax"], dtype=torch.float32), torch.finfo(dt).max)
+        assert torch.equal(scale, c["scale"]), c
+        assert torch.equal(O.quantize(g["x"], c["scale"], dt).view(torch.uint8), c["y"]), c
+
+
+def test_scale_is_clamped_to_fp8_max():
+    # tensors with amax < 1 get the constant scale 448 / 57344, not "full range"
+    assert O.amax_to_scale(torch.tensor(0.05), 448.0).item() == 448.0
+    assert O.amax_to_scale(torch.tensor(0.0), 57344.0).item() == 57344.0
+    assert O.amax_to_scale(torch.tensor(4.0), 448.0).item() == 112.0
+
+
+def test_quantize_double_rounding_differs_from_single():
+    # fp8(bf16(x*s)) != fp8(x*s) for some inputs; the oracle must do the former
+    x = torch.linspace(-3, 3, 20001).to(BF16)
+    s = torch.tensor(57344.0 / 5.0)
+    double = O.quantize(x, s, torch.float8_e5m2).float()
+    single = (x.float() * s).clamp(-57344, 57344).to(torch.float8_e5m2).float()
+    assert (double != single).any()
+
+
+def test_f8linear_and_calibration(golden_dir):
+    for c in load(golden_dir, "f8linear.pt"):
+        in_dt = dt_of(c["in_dtype"])
+        sd = c["state"]
+        wq, ws, wsr = O.quantize_weight(c["weight_bf16"])
+        assert torch.equal(wq.view(torch.uint8), sd["float8_data"].view(torch.uint8))
+        assert torch.equal(ws, sd["scale"]) and torch.equal(wsr, sd["scale_reciprocal"])
+        # calibration: frozen scale = amax_to_scale(max of the first 12 call amaxes)
+        amax12 = torch.tensor(max(c["x_all_amax"][:12]), dtype=torch.float32)
+        assert torch.equal(O.amax_to_scale(amax12, torch.finfo(in_dt).max), sd["input_scale"])
+        y = O.f8linear(c["x_last"], sd, "", in_dt)
+        tol = 2.0 ** -7 * max(1.0, c["y_last"].abs().max().item())
+        assert maxdiff(y, c["y_last"]) <= tol
+        assert ((y.float() - c["y_last"].float()) != 0).float().mean().item() < 0.005
+
+
+def test_calibrating_linear_trace():
+    cal = O.CalibratingLinear(12)
+    g = torch.Generator().manual_seed(0)
+    amaxes = []
+    for i in range(14):
+        x = (torch.randn(64, 32, generator=g) * (1 + i % 5)).to(BF16)
+        amaxes.append(x.abs().max().float())
+        cal.quantize_input(x)
+        if i < 12:
+            assert not cal.initialized
+            assert torch.equal(cal.input_scale, O.amax_to_scale(torch.stack(amaxes).max(), 57344.0))
+    assert cal.initialized and cal.index == 12
+    assert torch.equal(cal.input_scale, O.amax_to_scale(torch.stack(amaxes[:12]).max(), 57344.0))
+
+
+def test_ops_against_reference(golden_dir):
+    g = load(golden_dir, "ops.pt")
+    pe = O.embed_nd(g["ids"], [16, 56, 56], 10_000, BF16)
+    assert torch.equal(pe, g["pe"])
+    q, k = O.apply_rope(g["q"], g["k"], g["pe"])
+    assert torch.equal(q, g["q_rope"]) and torch.equal(k, g["k_rope"])
+    assert maxdiff(O.rms_norm(g["q"], g["qnorm_w"]), g["q_norm"]) <= 2.0 ** -7
+    assert maxdiff(O.rms_norm(g["k"], g["knorm_w"]), g["k_norm"]) <= 2.0 ** -7
+    assert maxdiff(O.attention(g["q"], g["k"], g["v"], g["pe"]), g["attention"]) <= 2.0 ** -6
+    assert maxdiff(O.layernorm_modulate(g["x"], g["shift"], g["scale"]), g["ln_mod"]) <= 2.0 ** -5
+    assert torch.equal(O.timestep_embedding(g["t"], 256), g["t_emb"])
+    assert torch.equal(F.gelu(g["x"], approximate="tanh"), g["gelu"]) and torch.equal(F.silu(g["x"]), g["silu"])
+
+
+def test_rope_is_identity_for_text_positions(golden_dir):
+    g = load(golden_dir, "ops.pt")
+    q, _ = O.apply_rope(g["q"], g["k"], g["pe"])
+    assert torch.equal(q[:, :, :32], g["q"][:, :, :32])  # ids == 0 -> cos 1, sin 0
+
+
+def test_blocks_and_forward_against_reference(golden_dir):
+    g = load(golden_dir, "flux_tiny.pt")
+    sd, cfg, bi = g["state"], g["cfg"], g["block_in"]
+    heads = g["tiny"]["num_heads"]
+    img, txt = O.double_block(bi["img"], bi["txt"], bi["vec"], bi["pe"], sd, "double_blocks.0.", heads)
+    assert maxdiff(img, g["double_img"]) <= 2.0 ** -4 and maxdiff(txt, g["double_txt"]) <= 2.0 ** -4
+    xs = torch.cat((bi["txt"], bi["img"]), 1)
+    assert maxdiff(O.single_block(xs, bi["vec"], bi["pe"], sd, "single_blocks.0.", heads), g["single"]) <= 2.0 ** -4
+    (sh, sc, ga), _ = O.modulation(bi["vec"], sd, "double_blocks.0.img_mod.", True)
+    for ours, ref in zip((sh, sc, ga), g["mod1"]):
+        assert maxdiff(ours, ref) <= 2.0 ** -8
+    y = O.flux_forward(sd, cfg, **g["inputs"])
+    assert maxdiff(y, g["y_fp8"]) <= 2.0 ** -4
+    assert maxdiff(g["y_fp8"], g["y_bf16"]) < 0.1  # the fp8 path tracks the bf16 path
+
+
+def test_schedule_matches_reference_formula():
+    ts = O.get_schedule(28, 4096)
+    assert len(ts) == 29 and ts[0] == 1.0 and ts[-1] == 0.0
+    assert all(a > b for a, b in zip(ts[:-1], ts[1:]))
+    lin = O.get_schedule(4, 4096, shift=False)
+    assert lin == pytest.approx([1.0, 0.75, 0.5, 0.25, 0.0])
