@@ -54,6 +54,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// volatile: stays between the ping-pong barriers that bracket the exp phase
+__device__ __forceinline__ float fast_exp2_pinned(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int REGS>
 __device__ __forceinline__ void reg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
@@ -244,6 +251,12 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
     const float sl2 = P.scale_log2;
     float m_used = -INFINITY;
     float l = 0.f;
+    // Ping-pong token between the two softmax warpgroups (named barriers 1 and 2): only one of them is in its
+    // MUFU-bound exp phase at a time, so while one exponentiates the tensor pipe works on the other's tiles.
+    // Without it both run in lock-step and the exp phases and the MMAs serialise (profiles/r1_attention.md).
+    if constexpr (NQ == 2) {
+      if (g == 1) named_bar_arrive(1, 256);  // hand the first turn to warpgroup 0
+    }
 
     for (int j = 0; j < n; ++j) {
       const int slot = NQ == 2 ? g : (j & 1);
@@ -281,12 +294,14 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       }
       float rs = 0.f;
       const float neg_m = -m_used;
+      if constexpr (NQ == 2) named_bar_sync(1 + g, 256);  // wait for our turn
 #pragma unroll
       for (int i = 0; i < 128; ++i) {
-        float p = fast_exp2(fmaf(__uint_as_float(sv[i]), sl2, neg_m));
+        float p = fast_exp2_pinned(fmaf(__uint_as_float(sv[i]), sl2, neg_m));
         rs += p;
         sv[i] = __float_as_uint(p);
       }
+      if constexpr (NQ == 2) named_bar_arrive(1 + (g ^ 1), 256);  // pass the turn
       l += rs;
 
       if (j > 0) {

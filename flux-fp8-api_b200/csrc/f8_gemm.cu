@@ -2,7 +2,13 @@
 // block-level eager ops that follow each linear fused into the epilogue
 // (modules/flux_model.py:353-400, 467-485).
 //
-// Persistent warp-specialised kernel, one CTA per SM:
+// Two tilings of the same persistent warp-specialised kernel:
+//   CG = 1  one CTA per SM, tile 128 x BN (BN = 256 or 128), tcgen05.mma.cta_group::1
+//   CG = 2  one CTA *pair* (cluster of 2 SMs) per 256 x 256 tile, tcgen05.mma.cta_group::2: each CTA stages its
+//           128 rows of A and its 128-row half of W, the leader CTA issues M=256 MMAs that read both CTAs' shared
+//           memory, each CTA's TMEM receives its 128 accumulator rows.  Halves the shared-memory operand traffic
+//           per MMA, which is what caps the single-CTA form at ~55 % tensor-pipe utilisation (profiles/).
+// Roles per CTA:
 //   warp 0      TMA producer: A[128 x 128B] and W[BN x 128B] tiles, SWIZZLE_128B, kStages-deep ring
 //   warp 1      MMA issuer:   tcgen05.mma.kind::f8f6f4 (M=128, N=BN, K=32), fp32 accumulators in TMEM,
 //               two accumulator buffers so tile i+1's MMAs overlap tile i's epilogue
@@ -10,6 +16,8 @@
 //   warps 4-11  epilogue: tcgen05.ld (thread == output row), dequant scale + bias -> bf16 rounding ->
 //               fused op -> vectorised global stores.  Warps 4-7 own columns [0,BN/2), 8-11 the rest.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "flux_b200.h"
 #include "host_util.h"
@@ -23,11 +31,12 @@ constexpr int kGemmThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kHeadDim = 128;
 
-template <int BN>
+template <int BN, int CG>
 struct GemmSmem {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kBRows = BN / CG;  // rows of W staged by one CTA
+  static constexpr int kStages = kBRows == 256 ? 4 : 6;
   static constexpr int kA = kBM * kBK;
-  static constexpr int kB = BN * kBK;
+  static constexpr int kB = kBRows * kBK;
   static constexpr int kStage = kA + kB;
   static constexpr int kBarOff = kStages * kStage;
   // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr, norm weights (2*128 fp32)
@@ -229,9 +238,10 @@ __device__ __forceinline__ void epi_qkv_head(const GemmParams& P, const RowInfo&
 
 // ---- the kernel -------------------------------------------------------------------------------------
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_constant__ GemmParams P) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
+  static_assert(CG == 1 || BN == 256, "the 2-CTA tiling is 256 x 256");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
@@ -244,6 +254,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const fluxb200_gemm_args& g = P.g;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;  // 0 = leader of the pair
+  const int tile0 = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
+  const int tile_stride = CG == 2 ? gridDim.x >> 1 : gridDim.x;
+  constexpr int kTileM = kBM * CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmap_a);
@@ -256,13 +270,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8 * CG);  // one arrive per epilogue warp (of both CTAs for CG == 2)
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, 2 * BN);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_2sm(tmem_ptr, 2 * BN);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr, 2 * BN);
+      tmem_relinquish();
+    }
   }
   if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
     if (threadIdx.x < 2 * kHeadDim)
@@ -270,7 +289,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
           threadIdx.x < kHeadDim ? g.q_norm_w[threadIdx.x] : g.k_norm_w[threadIdx.x - kHeadDim];
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -278,17 +297,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
+      // ---- TMA producer (both CTAs of a pair: each loads its own A rows and its half of the W rows) ----
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % P.num_m_tiles) * kBM;
-        const int n0 = (tile / P.num_m_tiles) * BN;
+      for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+        const int m0 = (tile % P.num_m_tiles) * kTileM + cta_rank * kBM;
+        const int n0 = (tile / P.num_m_tiles) * BN + cta_rank * S::kBRows;
         for (int kb = 0; kb < P.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], S::kStage);
           uint8_t* sa = smem + stage * S::kStage;
-          tma_load_2d(sa, &P.tmap_a, &full_bar[stage], kb * kBK, m0);
-          tma_load_2d(sa + S::kA, &P.tmap_w, &full_bar[stage], kb * kBK, n0);
+          if constexpr (CG == 2) {
+            // all bytes of the pair are accounted on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStage);
+            tma_load_2d_2sm(sa, &P.tmap_a, &full_bar[stage], kb * kBK, m0);
+            tma_load_2d_2sm(sa + S::kA, &P.tmap_w, &full_bar[stage], kb * kBK, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], S::kStage);
+            tma_load_2d(sa, &P.tmap_a, &full_bar[stage], kb * kBK, m0);
+            tma_load_2d(sa + S::kA, &P.tmap_w, &full_bar[stage], kb * kBK, n0);
+          }
           if (++stage == S::kStages) {
             stage = 0;
             phase ^= 1;
@@ -296,13 +323,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
+      // ---- MMA issuer (leader CTA only) ----
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -315,10 +344,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
           for (int k = 0; k < kBK / 32; ++k) {
             uint64_t ad = make_desc_sw128(a_addr + k * 32, 16, 1024);
             uint64_t bd = make_desc_sw128(b_addr + k * 32, 16, 1024);
-            mma_f8f6f4_ss(d_tmem, ad, bd, P.idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2)
+              mma_f8f6f4_ss_2sm(d_tmem, ad, bd, P.idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              mma_f8f6f4_ss(d_tmem, ad, bd, P.idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
-          if (kb == P.num_k_blocks - 1) tc_commit(&tfull_bar[as]);
+          // smem slot reusable (in both CTAs) once these MMAs have read it
+          if constexpr (CG == 2) tc_commit_2sm(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
+          if (kb == P.num_k_blocks - 1) {
+            if constexpr (CG == 2) tc_commit_2sm(&tfull_bar[as], 3); else tc_commit(&tfull_bar[as]);
+          }
           if (++stage == S::kStages) {
             stage = 0;
             phase ^= 1;
@@ -330,6 +365,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
         }
       }
     }
+    __syncwarp();
   } else if (warp >= kEpiWarp0) {
     const int lg = warp & 3;                 // TMEM lane group of this warp
     const int half = (warp - kEpiWarp0) >> 2;  // which half of the BN columns
@@ -340,8 +376,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
     const int rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % P.num_m_tiles) * kBM;
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+      const int m0 = (tile % P.num_m_tiles) * kTileM + cta_rank * kBM;
       const int n0 = (tile / P.num_m_tiles) * BN;
       RowInfo ri;
       ri.row = m0 + lg * 32 + lane;
@@ -392,7 +428,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_remote(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -401,28 +439,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
   static bool attr_set = false;
-  auto kern = f8_gemm_kernel<BN, EPI>;
+  auto kern = f8_gemm_kernel<BN, EPI, CG>;
   if (!attr_set) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
   const int tiles = P.num_m_tiles * P.num_n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(P);
-  FB_CUDA_OK(cudaGetLastError());
+  const int units = sm_count() / CG;  // CTAs (CG == 1) or CTA pairs (CG == 2) that fit on the device
+  const int grid = (tiles < units ? tiles : units) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P));
   return 0;
 }
 
@@ -482,21 +532,40 @@ extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_
   if (!qkv && (g.N <= 128 || (g.N % 256 != 0 && g.N % 128 == 0) ||
                (static_cast<int64_t>((g.M + 127) / 128) * ((g.N + 255) / 256) < sm_count() / 2)))
     bn = 128;
+  // 2-CTA tiling (256 x 256 per SM pair) when it fills most of the machine; FLUXB200_GEMM_CG=1|2 forces a form.
+  int cg = 1;
+  const int64_t tiles2 = static_cast<int64_t>((g.M + 255) / 256) * ((g.N + 255) / 256);
+  if (bn == 256 && g.N >= 256 && tiles2 >= (sm_count() / 2) * 3 / 4) cg = 2;
+  static const int forced_cg = [] {
+    const char* e = getenv("FLUXB200_GEMM_CG");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced_cg == 1) cg = 1;
+  if (forced_cg == 2 && g.N >= 256 && (qkv || g.N % 256 == 0 || epi == FLUXB200_EPI_PLAIN)) { cg = 2; bn = 256; }
 
   GemmParams P;
   P.g = g;
-  P.num_m_tiles = (g.M + kBM - 1) / kBM;
+  P.num_m_tiles = (g.M + kBM * cg - 1) / (kBM * cg);
   P.num_n_tiles = (g.N + bn - 1) / bn;
   P.num_k_blocks = (g.K + kBK - 1) / kBK;
   P.idesc = make_idesc(g.a_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3, g.w_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3,
-                       kBM, bn);
+                       kBM * cg, bn);
   int rc = make_tmap_2d(&P.tmap_a, g.a, 1, g.M, g.K, g.K, kBM, kBK);
   if (rc) return rc;
-  rc = make_tmap_2d(&P.tmap_w, g.w, 1, g.N, g.K, g.K, bn, kBK);
+  rc = make_tmap_2d(&P.tmap_w, g.w, 1, g.N, g.K, g.K, bn / cg, kBK);
   if (rc) return rc;
 
-#define FB_LAUNCH(BN_, EPI_) return launch_gemm<BN_, EPI_>(P, stream)
-  if (bn == 256) {
+#define FB_LAUNCH(BN_, EPI_) return launch_gemm<BN_, EPI_, 1>(P, stream)
+#define FB_LAUNCH2(EPI_) return launch_gemm<256, EPI_, 2>(P, stream)
+  if (cg == 2) {
+    switch (epi) {
+      case FLUXB200_EPI_PLAIN: FB_LAUNCH2(FLUXB200_EPI_PLAIN);
+      case FLUXB200_EPI_GATE_RESIDUAL: FB_LAUNCH2(FLUXB200_EPI_GATE_RESIDUAL);
+      case FLUXB200_EPI_GELU_QUANT: FB_LAUNCH2(FLUXB200_EPI_GELU_QUANT);
+      case FLUXB200_EPI_QKV_ROPE: FB_LAUNCH2(FLUXB200_EPI_QKV_ROPE);
+      case FLUXB200_EPI_LINEAR1: FB_LAUNCH2(FLUXB200_EPI_LINEAR1);
+    }
+  } else if (bn == 256) {
     switch (epi) {
       case FLUXB200_EPI_PLAIN: FB_LAUNCH(256, FLUXB200_EPI_PLAIN);
       case FLUXB200_EPI_GATE_RESIDUAL: FB_LAUNCH(256, FLUXB200_EPI_GATE_RESIDUAL);
@@ -512,5 +581,6 @@ extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_
     }
   }
 #undef FB_LAUNCH
+#undef FB_LAUNCH2
   return set_error(FLUXB200_ERR_INVALID, "fluxb200_f8_gemm: no kernel for epilogue %d / BN %d", epi, bn);
 }

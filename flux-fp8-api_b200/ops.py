@@ -37,6 +37,8 @@ def quantize(x: Tensor, scale: Tensor, dtype: torch.dtype, out: Optional[Tensor]
     x = x.contiguous()
     if out is None:
         out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    if x.numel() == 0:
+        return out
     cabi.check(cabi.load().fluxb200_quantize(x.data_ptr(), out.data_ptr(), x.numel(), scale.data_ptr(),
                                              cabi.fp8_fmt(dtype), cabi.stream_ptr()), "fluxb200_quantize")
     return out
@@ -50,6 +52,8 @@ def amax(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     x = x.contiguous()
     if out is None:
         out = torch.zeros((), dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return out
     cabi.check(cabi.load().fluxb200_amax(x.data_ptr(), x.numel(), out.data_ptr(), cabi.stream_ptr()), "fluxb200_amax")
     return out
 

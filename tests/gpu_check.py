@@ -396,11 +396,15 @@ def main():
         print(f"== {name}: {'OK' if not FAILS else 'FAILED: ' + ', '.join(FAILS)}")
         sys.exit(1 if FAILS else 0)
     rc = 0
-    for name in ["elementwise", "gemm", "epilogue", "attention1", "model", "flux"]:
+    base_env = dict(os.environ)
+    for name in ["gemm", "epilogue", "gemm_cg2", "epilogue_cg2", "attention1", "attention4", "model", "flux"]:
         print(f"===== {name} =====", flush=True)
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=420)
+            env = dict(base_env)
+            if name.endswith("_cg2"):
+                env["FLUXB200_GEMM_CG"] = "2"
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), name.replace("_cg2", "")], timeout=420, env=env)
             rc |= p.returncode
         except subprocess.TimeoutExpired:
             print(f"== {name}: TIMEOUT")

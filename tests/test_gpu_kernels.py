@@ -1,0 +1,248 @@
+"""GPU (-m gpu): every CUDA kernel, called through the C ABI, against the oracle on the same seeded inputs.
+
+Tolerances (stated per test): integer/byte outputs of the quantisers are bit-exact; GEMM-family outputs
+may differ from the oracle's fp32 matmul only by fp32 summation order, i.e. at most 1 bf16 ulp on a small
+fraction of elements; attention rounds P to bf16 (as fused GPU kernels do) so it is compared at 1 bf16 ulp
+of the output range."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+E4M3, E5M2 = torch.float8_e4m3fn, torch.float8_e5m2
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops(lib):
+    from flux_fp8_api_b200 import ops as _ops
+
+    assert _ops.device_check() >= 100
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import flux_oracle
+
+    return flux_oracle
+
+
+def gen(seed):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+def rand_fp8(shape, dtype, std, seed):
+    return (torch.randn(shape, device=DEV, generator=gen(seed)) * std).to(BF16).to(dtype)
+
+
+def scalar(v):
+    return torch.tensor(v, dtype=torch.float32, device=DEV)
+
+
+def ulp_check(got, ref, ulps=1, frac=0.01):
+    """|got-ref| <= ulps bf16 ulps at the reference magnitude range, on at most `frac` of the elements."""
+    g, r = got.float(), ref.float()
+    assert torch.isfinite(g).all()
+    tol = ulps * 2.0 ** -7 * max(1.0, r.abs().max().item())
+    d = (g - r).abs()
+    assert d.max().item() <= tol, f"max|d| {d.max().item()} > {tol}"
+    assert (d > 0).float().mean().item() <= frac, f"mismatch fraction {(d > 0).float().mean().item()}"
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [E5M2, E4M3])
+@pytest.mark.parametrize("amax", [0.003, 0.7, 5.0, 300.0])
+def test_quantize_bit_exact(ops, O, golden_dir, dt, amax):
+    from flux_fp8_api_b200.f8linear import mul_scale
+
+    gold = torch.load(os.path.join(golden_dir, "quantize.pt"))
+    xs = gold["x"].to(DEV)
+    x = (torch.randn(1 << 18, device=DEV, generator=gen(1)) * 3).to(BF16)
+    s = O.amax_to_scale(scalar(amax), torch.finfo(dt).max)
+    # GPU reference semantics: torch on CUDA multiplies by bf16(scale)
+    for t in (x, xs, x[:12345]):
+        assert torch.equal(ops.quantize(t, mul_scale(s), dt).view(torch.uint8), O.quantize(t, s, dt).view(torch.uint8))
+    # CPU reference semantics == the committed golden bytes
+    case = [c for c in gold["cases"] if c["amax"] == amax and str(dt) == c["dtype"]][0]
+    assert torch.equal(ops.quantize(xs, case["scale"].to(DEV), dt).view(torch.uint8).cpu(), case["y"])
+
+
+def test_amax_and_empty(ops):
+    x = (torch.randn(777_777, device=DEV, generator=gen(2)) * 5).to(BF16)
+    assert ops.amax(x).item() == x.abs().max().float().item()
+    x[123_456] = -1000.0
+    assert ops.amax(x).item() == 1000.0
+    assert ops.amax(x[:0]).item() == 0.0
+    assert ops.quantize(x[:0], scalar(1.0), E5M2).numel() == 0
+
+
+@pytest.mark.parametrize("B,L,D", [(1, 512, 3072), (2, 384, 3072), (2, 100, 256), (1, 77, 4096)])
+def test_ln_modulate_quantise(ops, O, B, L, D):
+    from flux_fp8_api_b200.f8linear import mul_scale
+
+    g = gen(3)
+    x = (torch.randn(B, L, D, device=DEV, generator=g) * 2 + 0.3).to(BF16)
+    mod = (torch.randn(B, 1, 6 * D, device=DEV, generator=g) * 0.3).to(BF16)
+    shift, scale = mod[..., :D], mod[..., D:2 * D]
+    ref = O.layernorm_modulate(x, shift, scale)
+    s = O.amax_to_scale(ref.abs().max().float(), 57344.0)
+    yq, yb = ops.ln_mod_quant(x, shift, scale, mul_scale(s), E5M2, want_bf16=True)
+    ulp_check(yb, ref, ulps=2, frac=0.001)
+    mism = (yq.float() != O.quantize(ref, s, E5M2).float()).float().mean().item()
+    assert mism < 0.001
+
+
+def test_silu_qknorm_rope_against_reference_golden(ops, O, golden_dir):
+    g = torch.load(os.path.join(golden_dir, "ops.pt"))
+    pe = g["pe"].to(DEV)
+    cos, sin = pe[:, 0, :, :, 0, 0].contiguous(), pe[:, 0, :, :, 1, 0].contiguous()
+    q = g["q"].to(DEV)
+    assert torch.equal(ops.qknorm_rope(q, None, cos, sin).cpu(), g["q_rope"])  # RoPE: bit-exact
+    ulp_check(ops.qknorm_rope(q, g["qnorm_w"].float().to(DEV), None, None).cpu(), g["q_norm"], frac=0.001)
+    x = g["x"].to(DEV)
+    _, sb = ops.silu_quant(x, None, None, want_bf16=True)
+    ulp_check(sb.cpu(), g["silu"], frac=0.001)
+
+
+@pytest.mark.parametrize("M,N,K,adt", [(128, 256, 128, E5M2), (128, 128, 128, E5M2), (256, 512, 384, E4M3),
+                                       (200, 384, 320, E5M2), (100, 72, 64, E5M2), (1, 18432, 3072, E5M2),
+                                       (4, 9216, 3072, E5M2), (512, 9216, 3072, E5M2), (4608, 3072, 3072, E5M2),
+                                       (4096, 3072, 12288, E5M2)])
+def test_f8_gemm_plain(ops, O, M, N, K, adt):
+    a, w = rand_fp8((M, K), adt, 4.0, 5), rand_fp8((N, K), E4M3, 1.0, 6)
+    bias = (torch.randn(N, device=DEV, generator=gen(7)) * 0.5).to(BF16)
+    sa, sw = scalar(1 / 64.0), scalar(1 / 32.0)
+    ulp_check(ops.f8_gemm(a, w, bias, sa, sw), O.scaled_mm(a, w, sa, sw, bias))
+    ulp_check(ops.f8_gemm(a, w, None, sa, sw), O.scaled_mm(a, w, sa, sw, None))
+
+
+def test_f8_gemm_linearity_full_size(ops):
+    """Size-independent property at the BASELINE shape (M=4608, N=21504, K=3072): doubling the de-quant scale
+    doubles every output exactly (power-of-two scaling commutes with every rounding on the path)."""
+    a, w = rand_fp8((4608, 3072), E5M2, 4.0, 8), rand_fp8((21504, 3072), E4M3, 1.0, 9)
+    y1 = ops.f8_gemm(a, w, None, scalar(1 / 64.0), scalar(1 / 32.0))
+    y2 = ops.f8_gemm(a, w, None, scalar(1 / 32.0), scalar(1 / 32.0))
+    assert torch.equal(y2.float(), 2 * y1.float())
+    # and rows are independent: a row block computed alone equals the same rows of the full product
+    y3 = ops.f8_gemm(a[1024:1536].contiguous(), w, None, scalar(1 / 64.0), scalar(1 / 32.0))
+    assert torch.equal(y3, y1[1024:1536])
+
+
+@pytest.mark.parametrize("B,L,N,K", [(2, 256, 512, 256), (3, 100, 256, 512), (1, 4608, 3072, 3072)])
+def test_epilogue_gate_residual(ops, O, B, L, N, K):
+    M = B * L
+    a, w = rand_fp8((M, K), E5M2, 4.0, 10), rand_fp8((N, K), E4M3, 1.0, 11)
+    g = gen(12)
+    bias = (torch.randn(N, device=DEV, generator=g) * 0.5).to(BF16)
+    resid = torch.randn(M, N, device=DEV, generator=g).to(BF16)
+    gate = torch.randn(B, 3 * N, device=DEV, generator=g).to(BF16)[:, N:2 * N]
+    sa, sw = scalar(1 / 64.0), scalar(1 / 32.0)
+    y = O.scaled_mm(a, w, sa, sw, bias)
+    ref = (resid.view(B, L, N) + gate[:, None, :] * y.view(B, L, N)).view(M, N)
+    ulp_check(ops.f8_gemm_gate_residual(a, w, bias, sa, sw, resid, gate, L), ref, ulps=2)
+    inplace = resid.clone()
+    ops.f8_gemm_gate_residual(a, w, bias, sa, sw, inplace, gate, L, out=inplace)
+    ulp_check(inplace, ref, ulps=2)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 256), (4608, 12288, 3072)])
+def test_epilogue_gelu_quant(ops, O, M, N, K):
+    from flux_fp8_api_b200.f8linear import mul_scale
+
+    a, w = rand_fp8((M, K), E5M2, 4.0, 13), rand_fp8((N, K), E4M3, 1.0, 14)
+    bias = (torch.randn(N, device=DEV, generator=gen(15)) * 0.5).to(BF16)
+    sa, sw = scalar(1 / 64.0), scalar(1 / 32.0)
+    ge = F.gelu(O.scaled_mm(a, w, sa, sw, bias), approximate="tanh")
+    so = O.amax_to_scale(ge.abs().max().float(), 57344.0)
+    out = ops.f8_gemm_gelu_quant(a, w, bias, sa, sw, mul_scale(so), E5M2)
+    ref = O.quantize(ge, so, E5M2)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() != ref.float()).float().mean().item() < 0.002  # rare 1-ulp GELU / accumulation flips
+    assert ((out.float() - ref.float()).abs() / so).max().item() <= 0.05
+
+
+@pytest.mark.parametrize("B,L,T,H,K,mlp", [(2, 128, 64, 2, 256, 0), (1, 256, 128, 2, 256, 512), (1, 200, 56, 2, 256, 256),
+                                           (1, 4096, 512, 24, 3072, 12288)])
+def test_epilogue_qkv_rope_and_linear1(ops, O, B, L, T, H, K, mlp):
+    from flux_fp8_api_b200.f8linear import mul_scale
+
+    S, D = L + T, H * 128
+    N, M = 3 * D + mlp, B * L
+    a, w = rand_fp8((M, K), E5M2, 4.0, 16), rand_fp8((N, K), E4M3, 0.5, 17)
+    g = gen(18)
+    bias = (torch.randn(N, device=DEV, generator=g) * 0.5).to(BF16)
+    qw = (1 + 0.05 * torch.randn(128, device=DEV, generator=g)).to(BF16)
+    kw = (1 + 0.05 * torch.randn(128, device=DEV, generator=g)).to(BF16)
+    hh = next(h for h in range(int(math.isqrt(L)), 0, -1) if L % h == 0)
+    ids = torch.cat((torch.zeros(1, T, 3), O.make_img_ids(1, hh, L // hh, torch.float32)), 1).to(BF16).to(DEV)
+    pe = O.embed_nd(ids, [16, 56, 56], 10000, BF16)
+    cos, sin = pe[:, 0, :, :, 0, 0].contiguous(), pe[:, 0, :, :, 1, 0].contiguous()
+    sa, sw = scalar(1 / 64.0), scalar(1 / 32.0)
+    y = O.scaled_mm(a, w, sa, sw, bias).view(B, L, N)
+    rq, rk, rv = O.split_heads(y[..., :3 * D], H)
+    rq, rk = O.apply_rope(O.rms_norm(rq, qw), O.rms_norm(rk, kw), pe[:, :, T:])
+    q = torch.zeros(B, H, S, 128, dtype=BF16, device=DEV)
+    k, v = torch.zeros_like(q), torch.zeros_like(q)
+    mlp_out = so = None
+    if mlp:
+        ge = F.gelu(y[..., 3 * D:], approximate="tanh")
+        so = O.amax_to_scale(ge.abs().max().float(), 57344.0)
+        mlp_out = torch.zeros(M, D + mlp, dtype=E5M2, device=DEV)
+    ops.f8_gemm_qkv_rope(a, w, bias, sa, sw, q, k, v, qw.float(), kw.float(), cos, sin, L, T, mlp_out=mlp_out,
+                         mlp_scale=mul_scale(so) if mlp else None, mlp_col_offset=D)
+    ulp_check(q[:, :, T:], rq, ulps=4, frac=0.02)  # 1-ulp flips before RMSNorm/RoPE are amplified by the rotation
+    ulp_check(k[:, :, T:], rk, ulps=4, frac=0.02)
+    ulp_check(v[:, :, T:], rv, ulps=1, frac=0.01)
+    assert (q[:, :, :T] == 0).all() and (v[:, :, :T] == 0).all()  # other stream's rows untouched
+    if mlp:
+        ref = O.quantize(ge, so, E5M2).view(M, mlp)
+        assert (mlp_out[:, D:].float() != ref.float()).float().mean().item() < 0.002
+        assert (mlp_out[:, :D].float() == 0).all()
+
+
+def attn_ref(O, q, k, v):
+    outs = [O.sdpa(q[:, h:h + 4], k[:, h:h + 4], v[:, h:h + 4]) for h in range(0, q.shape[1], 4)]
+    x = torch.cat(outs, 1).transpose(1, 2)
+    return x.reshape(q.shape[0], q.shape[2], -1)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("B,H,S,std", [(1, 1, 128, 1.0), (2, 2, 384, 2.0), (1, 2, 320, 1.0), (1, 3, 1000, 1.5)])
+def test_attention_small(ops, O, variant, B, H, S, std):
+    g = gen(19)
+    q = (torch.randn(B, H, S, 128, device=DEV, generator=g) * std).to(BF16)
+    k = (torch.randn(B, H, S, 128, device=DEV, generator=g) * std).to(BF16)
+    v = torch.randn(B, H, S, 128, device=DEV, generator=g).to(BF16)
+    ulp_check(ops.attention(q, k, v, variant=variant), attn_ref(O, q, k, v), ulps=2, frac=1.0)
+
+
+def test_attention_full_size_and_fp8_split_output(ops, O):
+    from flux_fp8_api_b200.f8linear import mul_scale
+
+    B, H, S, T = 1, 24, 4608, 512
+    g = gen(20)
+    q = torch.randn(B, H, S, 128, device=DEV, generator=g).to(BF16)
+    k = torch.randn(B, H, S, 128, device=DEV, generator=g).to(BF16)
+    v = torch.randn(B, H, S, 128, device=DEV, generator=g).to(BF16)
+    ref = attn_ref(O, q, k, v)
+    out = ops.attention(q, k, v)
+    ulp_check(out, ref, ulps=2, frac=1.0)
+    # property: softmax rows sum to one -> attention of constant V is that constant (exactly representable)
+    ones = torch.full_like(v, 0.5)
+    assert torch.equal(ops.attention(q, k, ones), torch.full_like(out, 0.5))
+    # fp8 outputs routed to two destinations with two scales (double-block layout)
+    s0, s1 = O.amax_to_scale(scalar(1.0), 57344.0), O.amax_to_scale(scalar(3.0), 57344.0)
+    o_txt = torch.zeros(B, T, H * 128, dtype=E5M2, device=DEV)
+    o_img = torch.zeros(B, S - T, H * 128, dtype=E5M2, device=DEV)
+    ops.attention(q, k, v, out=o_txt, out_scale0=mul_scale(s0), out_scale1=mul_scale(s1), split_row=T, out1=o_img)
+    r_txt, r_img = O.quantize(ref[:, :T], s0, E5M2), O.quantize(ref[:, T:], s1, E5M2)
+    assert (o_txt.float() != r_txt.float()).float().mean().item() < 0.06  # 1-ulp bf16 differences before the e5m2 cast
+    assert (o_img.float() != r_img.float()).float().mean().item() < 0.06
+    assert ((o_img.float() - r_img.float()).abs() / s1).max().item() <= 2.0 ** -4
