@@ -29,10 +29,12 @@ EXPORTS = (
     "fluxb200_amax",
     "fluxb200_f8_gemm",
     "fluxb200_f8_gemv",
+    "fluxb200_modulation_batched",
     "fluxb200_silu_quant",
     "fluxb200_ln_mod_quant",
     "fluxb200_qknorm_rope",
     "fluxb200_attention",
+    "fluxb200_debug_counters",
 )
 
 
@@ -102,6 +104,22 @@ class AttentionArgs(C.Structure):
     ]
 
 
+class GemvLayer(C.Structure):
+    """struct fluxb200_gemv_layer"""
+
+    _fields_ = [
+        ("w", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("in_qscale", C.c_void_p),
+        ("a_scale_recip", C.c_void_p),
+        ("w_scale_recip", C.c_void_p),
+        ("N", C.c_int32),
+        ("out_offset", C.c_int32),
+        ("block_start", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
 class FluxB200Error(RuntimeError):
     pass
 
@@ -130,6 +148,10 @@ def load() -> C.CDLL:
         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_int, C.c_int, C.c_int, C.c_void_p,
     ]
+    lib.fluxb200_modulation_batched.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+        C.c_int, C.c_void_p,
+    ]
     lib.fluxb200_silu_quant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     lib.fluxb200_ln_mod_quant.argtypes = [
         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
@@ -140,6 +162,7 @@ def load() -> C.CDLL:
         C.c_float, C.c_void_p,
     ]
     lib.fluxb200_attention.argtypes = [C.POINTER(AttentionArgs), C.c_void_p]
+    lib.fluxb200_debug_counters.argtypes = [C.POINTER(C.c_ulonglong)]
     for name in EXPORTS:
         if name != "fluxb200_last_error":
             getattr(lib, name).restype = C.c_int

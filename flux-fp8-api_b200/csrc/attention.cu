@@ -15,6 +15,8 @@
 // TMEM columns: S slot i at i*128 (fp32), O accumulator of query tile g at 256 + g*128.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "flux_b200.h"
 #include "host_util.h"
 #include "ptx.cuh"
@@ -46,7 +48,13 @@ struct AttnParams {
   fluxb200_attention_args a;
   int num_kv_tiles;
   float scale_log2;
+  int debug;  // timing experiments only (env FLUXB200_ATTN_DEBUG): 1 = MMA/TMA pipeline alone, softmax skipped
 };
+
+// Phase timing (cycles) of CTA (0,0,0): [0..7] softmax warpgroup 0 / warp 4 lane 0, [8..15] MMA issuer.
+// Read back with fluxb200_debug_counters(); negligible cost (one predicated thread per role).
+__device__ unsigned long long g_attn_dbg[16];
+__device__ __forceinline__ unsigned long long clk() { return clock64(); }
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -125,32 +133,42 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // q, k, v come from the preceding QKV GEMMs
 
   if (warp < 4) {
     if constexpr (NQ == 2) reg_dec<56>();
-    if (warp == 0 && lane == 0) {
-      // ---------------- TMA producer ----------------
-      mbar_arrive_expect_tx(q_full, NQ * kTileBytes);
-      for (int g = 0; g < NQ; ++g) {
-        uint8_t* dst = smem + C::kQOff + g * kTileBytes;
-        tma_load_3d(dst, &P.tmap_q, q_full, 0, q0 + g * kBQ, bh, kEvictFirst);
-        tma_load_3d(dst + kChunkBytes, &P.tmap_q, q_full, 64, q0 + g * kBQ, bh, kEvictFirst);
+    if (warp == 0) {
+      // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, NQ * kTileBytes);
+        for (int g = 0; g < NQ; ++g) {
+          uint8_t* dst = smem + C::kQOff + g * kTileBytes;
+          tma_load_3d(dst, &P.tmap_q, q_full, 0, q0 + g * kBQ, bh, kEvictFirst);
+          tma_load_3d(dst + kChunkBytes, &P.tmap_q, q_full, 64, q0 + g * kBQ, bh, kEvictFirst);
+        }
       }
+      __syncwarp();
       for (int j = 0; j < n; ++j) {
         const int st = j % KS;
         const uint32_t ph = (j / KS) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], kTileBytes);
         uint8_t* kd = smem + C::kKOff + st * kTileBytes;
-        tma_load_3d(kd, &P.tmap_k, &k_full[st], 0, j * kBKV, bh, kEvictLast);
-        tma_load_3d(kd + kChunkBytes, &P.tmap_k, &k_full[st], 64, j * kBKV, bh, kEvictLast);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], kTileBytes);
         uint8_t* vd = smem + C::kVOff + st * kTileBytes;
-        tma_load_3d(vd, &P.tmap_v, &v_full[st], 0, j * kBKV, bh, kEvictLast);
-        tma_load_3d(vd + kChunkBytes, &P.tmap_v, &v_full[st], 64, j * kBKV, bh, kEvictLast);
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+          tma_load_3d(kd, &P.tmap_k, &k_full[st], 0, j * kBKV, bh, kEvictLast);
+          tma_load_3d(kd + kChunkBytes, &P.tmap_k, &k_full[st], 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+          tma_load_3d(vd, &P.tmap_v, &v_full[st], 0, j * kBKV, bh, kEvictLast);
+          tma_load_3d(vd + kChunkBytes, &P.tmap_v, &v_full[st], 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kFmtBF16, kBQ, kBKV, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kFmtBF16, kBQ, kD, 0, 1);  // V is MN-major
@@ -159,31 +177,46 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       const uint32_t v_addr = smem_u32(smem + C::kVOff);
       const uint32_t p_addr = smem_u32(smem + C::kPOff);
 
+      uint64_t q_desc[NQ], k_desc[KS], v_desc[KS], p_desc[2];
+      for (int g = 0; g < NQ; ++g) q_desc[g] = make_desc_sw128(q_addr + g * kTileBytes, 16, 1024);
+      for (int i = 0; i < KS; ++i) {
+        k_desc[i] = make_desc_sw128(k_addr + i * kTileBytes, 16, 1024);
+        v_desc[i] = make_desc_sw128(v_addr + i * kTileBytes, kChunkBytes, 1024);
+      }
+      for (int i = 0; i < 2; ++i) p_desc[i] = make_desc_sw128(p_addr + i * kTileBytes, 16, 1024);
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) tc_commit(bar);
+        __syncwarp();
+      };
       auto issue_qk = [&](int g, int slot, int st) {
         const uint32_t d = tmem_base + slot * 128;
+        const uint64_t ad0 = q_desc[g], bd0 = k_desc[st];
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kD / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
-          uint64_t ad = make_desc_sw128(q_addr + g * kTileBytes + off, 16, 1024);
-          uint64_t bd = make_desc_sw128(k_addr + st * kTileBytes + off, 16, 1024);
-          mma_f16_ss(d, ad, bd, idesc_qk, kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
+            mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+          }
         }
+        __syncwarp();
       };
       auto issue_pv = [&](int g, int pslot, int st, bool first) {
         const uint32_t d = tmem_base + 256 + g * 128;
+        const uint64_t bd0 = v_desc[st];
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kBKV / 16; ++kk) {
-          // V tile: [2 d-chunks][kv rows][128 B]; 16 kv rows per MMA = 2048 B; next d-chunk at kChunkBytes
-          uint64_t bd = make_desc_sw128(v_addr + st * kTileBytes + kk * 2048, kChunkBytes, 1024);
-          const uint32_t acc = (!first || kk != 0) ? 1u : 0u;
-          if constexpr (TS) {
-            mma_f16_ts(d, tmem_base + pslot * 128 + kk * 8, bd, idesc_pv, acc);
-          } else {
-            const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
-            uint64_t ad = make_desc_sw128(p_addr + pslot * kTileBytes + off, 16, 1024);
-            mma_f16_ss(d, ad, bd, idesc_pv, acc);
+          for (int kk = 0; kk < kBKV / 16; ++kk) {
+            // V tile: [2 d-chunks][kv rows][128 B]; 16 kv rows per MMA = 2048 B; next d-chunk at kChunkBytes
+            const uint32_t acc = (!first || kk != 0) ? 1u : 0u;
+            if constexpr (TS) {
+              mma_f16_ts(d, tmem_base + pslot * 128 + kk * 8, desc_advance(bd0, kk * 2048), idesc_pv, acc);
+            } else {
+              const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
+              mma_f16_ss(d, desc_advance(p_desc[pslot], off), desc_advance(bd0, kk * 2048), idesc_pv, acc);
+            }
           }
         }
+        __syncwarp();
       };
 
       mbar_wait(q_full, 0);
@@ -192,9 +225,9 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       if constexpr (NQ == 2) {
         for (int g = 0; g < 2; ++g) {
           issue_qk(g, g, 0);
-          tc_commit(&s_ready[g]);
+          commit(&s_ready[g]);
         }
-        tc_commit(&k_empty[0]);
+        commit(&k_empty[0]);
         for (int j = 0; j < n; ++j) {
           const int st = j % KS;
           mbar_wait(&v_full[st], (j / KS) & 1);
@@ -202,8 +235,8 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
             mbar_wait(&p_ready[g], j & 1);
             tc_fence_after();
             issue_pv(g, g, st, j == 0);
-            tc_commit(&o_done[g]);
-            if (g == 1) tc_commit(&v_empty[st]);
+            commit(&o_done[g]);
+            if (g == 1) commit(&v_empty[st]);
             if (j + 1 < n) {
               const int st1 = (j + 1) % KS;
               if (g == 0) {
@@ -211,15 +244,15 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
                 tc_fence_after();
               }
               issue_qk(g, g, st1);
-              tc_commit(&s_ready[g]);
-              if (g == 1) tc_commit(&k_empty[st1]);
+              commit(&s_ready[g]);
+              if (g == 1) commit(&k_empty[st1]);
             }
           }
         }
       } else {
         issue_qk(0, 0, 0);
-        tc_commit(&s_ready[0]);
-        tc_commit(&k_empty[0]);
+        commit(&s_ready[0]);
+        commit(&k_empty[0]);
         for (int j = 0; j < n; ++j) {
           const int st = j % KS;
           if (j + 1 < n) {
@@ -227,15 +260,15 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
             mbar_wait(&k_full[st1], ((j + 1) / KS) & 1);
             tc_fence_after();
             issue_qk(0, (j + 1) & 1, st1);
-            tc_commit(&s_ready[(j + 1) & 1]);
-            tc_commit(&k_empty[st1]);
+            commit(&s_ready[(j + 1) & 1]);
+            commit(&k_empty[st1]);
           }
           mbar_wait(&v_full[st], (j / KS) & 1);
           mbar_wait(&p_ready[0], j & 1);
           tc_fence_after();
           issue_pv(0, j & 1, st, j == 0);
-          tc_commit(&o_done[0]);
-          tc_commit(&v_empty[st]);
+          commit(&o_done[0]);
+          commit(&v_empty[st]);
         }
       }
     }
@@ -258,11 +291,15 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       if (g == 1) named_bar_arrive(1, 256);  // hand the first turn to warpgroup 0
     }
 
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    unsigned long long d_wait_s = 0, d_ld = 0, d_max = 0, d_exp = 0, d_wait_o = 0, d_st = 0, tA = 0, tB = 0;
     for (int j = 0; j < n; ++j) {
       const int slot = NQ == 2 ? g : (j & 1);
       const uint32_t sph = NQ == 2 ? (j & 1) : ((j >> 1) & 1);
+      if (dbg) tA = clk();
       mbar_wait(&s_ready[slot], sph);
       tc_fence_after();
+      if (dbg) { tB = clk(); d_wait_s += tB - tA; tA = tB; }
       uint32_t sv[128];
       {
         uint32_t(*sv4)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
@@ -272,6 +309,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
         tmem_ld32(lane_base + slot * 128 + 96, sv4[3]);
         tmem_ld_wait();
       }
+      if (dbg) { tB = clk(); d_ld += tB - tA; tA = tB; }
       const int kv_left = a.S - j * kBKV;  // columns >= kv_left are out of range (last tile only)
       if (kv_left < kBKV) {
 #pragma unroll
@@ -294,6 +332,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       }
       float rs = 0.f;
       const float neg_m = -m_used;
+      if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
       if constexpr (NQ == 2) named_bar_sync(1 + g, 256);  // wait for our turn
 #pragma unroll
       for (int i = 0; i < 128; ++i) {
@@ -303,10 +342,12 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       }
       if constexpr (NQ == 2) named_bar_arrive(1 + (g ^ 1), 256);  // pass the turn
       l += rs;
+      if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
 
       if (j > 0) {
         mbar_wait(&o_done[g], (j - 1) & 1);  // PV(j-1) finished: O stable, P buffer reusable
         tc_fence_after();
+        if (dbg) { tB = clk(); d_wait_o += tB - tA; tA = tB; }
         if (warp_grow) {
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
@@ -352,6 +393,12 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[g]);
+      if (dbg) { tB = clk(); d_st += tB - tA; tA = tB; }
+    }
+    if (dbg) {
+      g_attn_dbg[0] = d_wait_s, g_attn_dbg[1] = d_ld, g_attn_dbg[2] = d_max, g_attn_dbg[3] = d_exp;
+      g_attn_dbg[4] = d_wait_o, g_attn_dbg[5] = d_st, g_attn_dbg[6] = n;
+      g_attn_dbg[8] = g_attn_dbg[9] = g_attn_dbg[10] = 0;
     }
 
     // ---------------- epilogue: O / l -> bf16 -> (optional) fp8 ----------------
@@ -407,12 +454,393 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
     }
   }
 
+  pdl_launch_dependents();  // multi-wave grid: let the next kernel in only when this CTA is done
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+
+// =====================================================================================================
+// Half-tile pipelined variant (default).  Same roles and TMEM budget as attention_kernel<2, true>, but every
+// 128-row KV tile is processed as two independent 64-column halves: S_g[h] (64 fp32 columns) -> softmax ->
+// P_g[h] (32 bf16-pair columns over the same TMEM) -> PV_g(h), and QK for half h of the NEXT tile is issued
+// right after PV of half h of this one.  While a softmax warpgroup exponentiates one half, the tensor pipe is
+// already producing the other half of its next scores, so each query tile has two dependency chains in flight
+// (four per SM) instead of one: the MMA round trip (commit -> mbarrier -> tcgen05.ld -> max) that left both
+// MUFU and tensor pipes ~50 % idle in the whole-tile version (profiles/r1_attention_lockstep_ncu_full.txt) is
+// hidden behind the other half's exp phase.
+//   TMEM: S_g[h] at g*128 + h*64, O_g at 256 + g*128.  smem: Q 64 KB + 2 stages x (K 32 KB + V 32 KB).
+// =====================================================================================================
+struct AttnHCfg {
+  static constexpr int kStages = 2;
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = 2 * kTileBytes;
+  static constexpr int kVOff = kKOff + kStages * kTileBytes;
+  static constexpr int kBarOff = kVOff + kStages * kTileBytes;
+  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr int kThreads = 384;
+};
+
+__global__ void __launch_bounds__(AttnHCfg::kThreads, 1) attention_kernel_halves(const __grid_constant__ AttnParams P) {
+  using C = AttnHCfg;
+  constexpr int KS = C::kStages;
+  constexpr int kHalf = kBKV / 2;  // 64 kv rows
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = q_full + 1;      // KS
+  uint64_t* k_empty = k_full + KS;    // KS
+  uint64_t* v_full = k_empty + KS;    // KS
+  uint64_t* v_empty = v_full + KS;    // KS
+  uint64_t* s_ready = v_empty + KS;   // [g][h] = 4
+  uint64_t* p_ready = s_ready + 4;    // [g][h] = 4
+  uint64_t* o_done = p_ready + 4;     // [g] = 2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const fluxb200_attention_args& a = P.a;
+  const int q0 = blockIdx.x * (2 * kBQ);
+  const int h_idx = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * a.H + h_idx;
+  const int n = P.num_kv_tiles;
+  const int nt = 2 * n;  // half-steps
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmap_q);
+    tma_prefetch_desc(&P.tmap_k);
+    tma_prefetch_desc(&P.tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 4);  // one arrive per softmax warp
+    }
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // q, k, v come from the preceding QKV GEMMs
+
+  if (warp < 4) {
+    // The producer and issuer warps run their loops warp-uniformly and predicate only the TMA / MMA / commit
+    // instructions on one elected lane: operands then live in uniform registers.  (Running the whole loop under
+    // `lane == 0` makes ptxas wrap every UTCHMMA in a vector->uniform "waterfall" loop, ~80 cycles per MMA.)
+    if (warp == 0) {
+      // ---------------- TMA producer ----------------
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        for (int g = 0; g < 2; ++g) {
+          uint8_t* dst = smem + C::kQOff + g * kTileBytes;
+          tma_load_3d(dst, &P.tmap_q, q_full, 0, q0 + g * kBQ, bh, kEvictFirst);
+          tma_load_3d(dst + kChunkBytes, &P.tmap_q, q_full, 64, q0 + g * kBQ, bh, kEvictFirst);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < n; ++j) {
+        const int st = j % KS;
+        const uint32_t ph = (j / KS) & 1;
+        uint8_t* kd = smem + C::kKOff + st * kTileBytes;
+        uint8_t* vd = smem + C::kVOff + st * kTileBytes;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+          tma_load_3d(kd, &P.tmap_k, &k_full[st], 0, j * kBKV, bh, kEvictLast);
+          tma_load_3d(kd + kChunkBytes, &P.tmap_k, &k_full[st], 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+          tma_load_3d(vd, &P.tmap_v, &v_full[st], 0, j * kBKV, bh, kEvictLast);
+          tma_load_3d(vd + kChunkBytes, &P.tmap_v, &v_full[st], 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kFmtBF16, kBQ, kHalf, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kFmtBF16, kBQ, kD, 0, 1);  // V is MN-major
+      const uint32_t q_addr = smem_u32(smem + C::kQOff);
+      const uint32_t k_addr = smem_u32(smem + C::kKOff);
+      const uint32_t v_addr = smem_u32(smem + C::kVOff);
+
+      // Descriptors are built once; every MMA then costs one 64-bit add per operand (a single thread issues
+      // ~50 MMAs per KV tile, so the issue stream itself is on the critical path).
+      uint64_t q_desc[2], k_desc[KS], v_desc[KS];
+      for (int g = 0; g < 2; ++g) q_desc[g] = make_desc_sw128(q_addr + g * kTileBytes, 16, 1024);
+      for (int i = 0; i < KS; ++i) {
+        k_desc[i] = make_desc_sw128(k_addr + i * kTileBytes, 16, 1024);
+        v_desc[i] = make_desc_sw128(v_addr + i * kTileBytes, kChunkBytes, 1024);
+      }
+      // S_g[h] = Q_g . K[tile t>>1, rows (t&1)*64 .. +64]^T
+      auto issue_qk = [&](int g, int t) {
+        const int hh = t & 1, st = (t >> 1) % KS;
+        const uint32_t d = tmem_base + g * 128 + hh * kHalf;
+        const uint64_t ad0 = q_desc[g];
+        const uint64_t bd0 = desc_advance(k_desc[st], hh * (kHalf * 128));
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
+            mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+          }
+          tc_commit(&s_ready[g * 2 + hh]);
+        }
+        __syncwarp();
+      };
+      // O_g += P_g[h] . V[tile t>>1, rows (t&1)*64 .. +64]
+      auto issue_pv = [&](int g, int t) {
+        const int hh = t & 1, st = (t >> 1) % KS;
+        const uint32_t d = tmem_base + 256 + g * 128;
+        const uint64_t bd0 = desc_advance(v_desc[st], hh * kHalf * 128);
+        const uint32_t a0 = tmem_base + g * 128 + hh * kHalf;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kHalf / 16; ++kk)
+            mma_f16_ts(d, a0 + kk * 8, desc_advance(bd0, kk * 16 * 128), idesc_pv, (t != 0 || kk != 0) ? 1u : 0u);
+          tc_commit(&o_done[g]);
+          if (hh == 1 && g == 1) tc_commit(&v_empty[st]);
+        }
+        __syncwarp();
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < 2; ++t)
+        for (int g = 0; g < 2; ++g) issue_qk(g, t);
+      if (elect_one()) tc_commit(&k_empty[0]);
+      __syncwarp();
+      const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+      unsigned long long d_wp = 0, d_wkv = 0, d_iss = 0, tA = clk(), tB = 0;
+      for (int t = 0; t < nt; ++t) {
+        const int j = t >> 1, hh = t & 1, st = j % KS;
+        if (hh == 0) mbar_wait(&v_full[st], (j / KS) & 1);
+        if (dbg) { tB = clk(); d_wkv += tB - tA; tA = tB; }
+        for (int g = 0; g < 2; ++g) {
+          if (P.debug != 1) mbar_wait(&p_ready[g * 2 + hh], j & 1);
+          tc_fence_after();
+          if (dbg) { tB = clk(); d_wp += tB - tA; tA = tB; }
+          issue_pv(g, t);
+          if (t + 2 < nt) {
+            const int j1 = (t + 2) >> 1, st1 = j1 % KS;
+            if (hh == 0 && g == 0) {
+              mbar_wait(&k_full[st1], (j1 / KS) & 1);
+              tc_fence_after();
+            }
+            issue_qk(g, t + 2);
+            if (hh == 1 && g == 1) {
+              if (elect_one()) tc_commit(&k_empty[st1]);
+              __syncwarp();
+            }
+          }
+          if (dbg) { tB = clk(); d_iss += tB - tA; tA = tB; }
+        }
+      }
+      if (dbg) g_attn_dbg[8] = d_wp, g_attn_dbg[9] = d_wkv, g_attn_dbg[10] = d_iss;
+      if (P.debug == 1) {  // drain the tensor pipe before the CTA tears down
+        if (elect_one()) tc_commit(q_full);
+        __syncwarp();
+        mbar_wait(q_full, 1);
+      }
+    }
+  } else {
+    // ---------------- softmax warpgroups ----------------
+    const int g = (warp - 4) >> 2;
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    const uint32_t o_taddr = lane_base + 256 + g * 128;
+    const float sl2 = P.scale_log2;
+    float m_used = -INFINITY;
+    float l = 0.f;
+
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    unsigned long long d_wait_s = 0, d_ld = 0, d_max = 0, d_exp = 0, d_wait_o = 0, d_st = 0, tA = 0, tB = 0;
+    for (int t = 0; t < (P.debug == 1 ? 0 : nt); ++t) {
+      const int j = t >> 1, hh = t & 1;
+      const uint32_t s_taddr = lane_base + g * 128 + hh * kHalf;
+      if (dbg) tA = clk();
+      mbar_wait(&s_ready[g * 2 + hh], j & 1);
+      tc_fence_after();
+      if (dbg) { tB = clk(); d_wait_s += tB - tA; tA = tB; }
+      uint32_t sv[kHalf];
+      {
+        uint32_t(*sv2)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+        tmem_ld32(s_taddr, sv2[0]);
+        tmem_ld32(s_taddr + 32, sv2[1]);
+        tmem_ld_wait();
+      }
+      if (dbg) { tB = clk(); d_ld += tB - tA; tA = tB; }
+      const int kv_left = a.S - j * kBKV - hh * kHalf;  // columns >= kv_left are out of range (last tile only)
+      if (kv_left < kHalf) {
+#pragma unroll
+        for (int i = 0; i < kHalf; ++i)
+          if (i >= kv_left) sv[i] = __float_as_uint(-INFINITY);
+      }
+      float mx0 = __uint_as_float(sv[0]), mx1 = __uint_as_float(sv[1]);
+      float mx2 = __uint_as_float(sv[2]), mx3 = __uint_as_float(sv[3]);
+#pragma unroll
+      for (int i = 4; i < kHalf; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
+      }
+      const float m_cand = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      // Lazy rescale: keep the stale max unless it is more than 2^8 below the new one.  A fully masked half
+      // (kv_left <= 0 on the last tile) has m_cand = -inf and contributes zeros.
+      const bool grow = m_cand > m_used + kRescaleThreshold;
+      const bool warp_grow = __any_sync(0xffffffffu, grow);
+      float alpha = 1.f;
+      if (warp_grow) {
+        const float m_new = fmaxf(m_used, m_cand);
+        alpha = (m_new == -INFINITY) ? 1.f : fast_exp2(m_used - m_new);
+        m_used = m_new;
+        l *= alpha;
+      }
+      float rs0 = 0.f, rs1 = 0.f;
+      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+      if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
+#pragma unroll
+      for (int i = 0; i < kHalf; i += 2) {
+        float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), sl2, neg_m));
+        float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), sl2, neg_m));
+        rs0 += p0;
+        rs1 += p1;
+        sv[i >> 1] = pack_bf16x2(p0, p1);  // P as bf16 pairs, in place
+      }
+      l += rs0 + rs1;
+      if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
+
+      if (t > 0) {
+        mbar_wait(&o_done[g], (t - 1) & 1);  // previous PV of this query tile finished: O stable
+        tc_fence_after();
+        if (dbg) { tB = clk(); d_wait_o += tB - tA; tA = tB; }
+        if (warp_grow) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(o_taddr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(o_taddr + c * 32, ov);
+          }
+        }
+      }
+      {
+        uint32_t(*pk)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+        tmem_st32(s_taddr, pk[0]);  // 32 columns of bf16 pairs = 64 kv
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g * 2 + hh]);
+      if (dbg) { tB = clk(); d_st += tB - tA; tA = tB; }
+    }
+    if (dbg) {
+      g_attn_dbg[0] = d_wait_s, g_attn_dbg[1] = d_ld, g_attn_dbg[2] = d_max, g_attn_dbg[3] = d_exp;
+      g_attn_dbg[4] = d_wait_o, g_attn_dbg[5] = d_st, g_attn_dbg[6] = nt;
+    }
+
+    // ---------------- epilogue: O / l -> bf16 -> (optional) fp8 ----------------
+    if (P.debug != 1) mbar_wait(&o_done[g], (nt - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const bool valid = qrow < a.S && P.debug != 1;
+    const bool second = a.out1 != nullptr && qrow >= a.split_row;
+    void* const outp = second ? a.out1 : a.out;
+    const int64_t obase = second ? static_cast<int64_t>(b) * a.out1_batch_stride +
+                                       static_cast<int64_t>(qrow - a.split_row) * a.ldo1 + h_idx * kD
+                                 : static_cast<int64_t>(b) * a.out_batch_stride + static_cast<int64_t>(qrow) * a.ldo + h_idx * kD;
+    float oscale = 1.f;
+    if (a.out_kind == 1) oscale = __ldg(qrow < a.split_row ? a.out_scale0 : a.out_scale1);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t ov[32];
+      tmem_ld32(o_taddr + c * 32, ov);
+      tmem_ld_wait();
+      if (!valid) continue;
+      if (a.out_kind == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + obase + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(ov[q * 8 + 0]) * inv_l, __uint_as_float(ov[q * 8 + 1]) * inv_l);
+          o.y = pack_bf16x2(__uint_as_float(ov[q * 8 + 2]) * inv_l, __uint_as_float(ov[q * 8 + 3]) * inv_l);
+          o.z = pack_bf16x2(__uint_as_float(ov[q * 8 + 4]) * inv_l, __uint_as_float(ov[q * 8 + 5]) * inv_l);
+          o.w = pack_bf16x2(__uint_as_float(ov[q * 8 + 6]) * inv_l, __uint_as_float(ov[q * 8 + 7]) * inv_l);
+          dst[q] = o;
+        }
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(outp) + obase + c * 32);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float o = bf16r(__uint_as_float(ov[q * 16 + tt * 4 + e]) * inv_l);
+              f[e] = a.out_fmt == FLUXB200_E5M2 ? quant_pre<1>(o, oscale) : quant_pre<0>(o, oscale);
+            }
+            if (a.out_fmt == FLUXB200_E5M2)
+              w[tt] = to_fp8x2<1>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<1>(f[2], f[3])) << 16);
+            else
+              w[tt] = to_fp8x2<0>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<0>(f[2], f[3])) << 16);
+          }
+          dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  pdl_launch_dependents();  // multi-wave grid: let the next kernel in only when this CTA is done
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_attention_halves(const AttnParams& P, cudaStream_t stream) {
+  using C = AttnHCfg;
+  static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
+  static bool attr_set = false;
+  if (!attr_set) {
+    FB_CUDA_OK(cudaFuncSetAttribute(attention_kernel_halves, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+    attr_set = true;
+  }
+  const fluxb200_attention_args& a = P.a;
+  dim3 grid((a.S + 2 * kBQ - 1) / (2 * kBQ), a.H, a.B);
+  FB_CUDA_OK(launch_kernel(attention_kernel_halves, grid, dim3(C::kThreads), C::kTotal, stream, 1, P));
+  return 0;
 }
 
 template <int NQ, bool TS>
@@ -427,8 +855,7 @@ static int launch_attention(const AttnParams& P, cudaStream_t stream) {
   }
   const fluxb200_attention_args& a = P.a;
   dim3 grid((a.S + NQ * kBQ - 1) / (NQ * kBQ), a.H, a.B);
-  kern<<<grid, C::kThreads, C::kTotal, stream>>>(P);
-  FB_CUDA_OK(cudaGetLastError());
+  FB_CUDA_OK(launch_kernel(kern, grid, dim3(C::kThreads), C::kTotal, stream, 1, P));
   return 0;
 }
 
@@ -459,6 +886,11 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
   P.a = a;
   P.num_kv_tiles = (a.S + kBKV - 1) / kBKV;
   P.scale_log2 = a.softmax_scale * 1.4426950408889634f;
+  static const int dbg = [] {
+    const char* e = getenv("FLUXB200_ATTN_DEBUG");
+    return e ? atoi(e) : 0;
+  }();
+  P.debug = dbg;
   const uint64_t bhn = static_cast<uint64_t>(a.B) * a.H;
   const uint64_t row_bytes = kD * 2;
   int rc;
@@ -467,11 +899,18 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
   if ((rc = make_tmap_3d(&P.tmap_v, a.v, 2, kD, a.S, bhn, row_bytes, row_bytes * a.S, 64, kBKV, 1))) return rc;
 
   switch (a.variant) {
-    case 0:
+    case 0: return launch_attention_halves(P, stream);      // 2 query tiles x 2 KV halves in flight (default)
     case 1: return launch_attention<2, true>(P, stream);   // 2 query tiles, P through TMEM
     case 2: return launch_attention<1, false>(P, stream);  // 1 query tile, P through smem (SS MMA)
     case 3: return launch_attention<1, true>(P, stream);   // 1 query tile, P through TMEM
     case 4: return launch_attention<2, false>(P, stream);  // 2 query tiles, P through smem
     default: return set_error(FLUXB200_ERR_INVALID, "fluxb200_attention: unknown variant %d", a.variant);
   }
+}
+
+// Diagnostics: copies the 16 phase counters of the last attention launch (CTA 0) to host memory.
+extern "C" int fluxb200_debug_counters(unsigned long long* host_out16) {
+  FB_CUDA_OK(cudaDeviceSynchronize());
+  FB_CUDA_OK(cudaMemcpyFromSymbol(host_out16, fb::g_attn_dbg, sizeof(unsigned long long) * 16));
+  return 0;
 }

@@ -13,6 +13,7 @@ namespace fb {
 template <int FMT>
 __global__ void __launch_bounds__(256) quantize_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y,
                                                        int64_t n, const float* __restrict__ scale) {
+  pdl_wait();
   const float s = __ldg(scale);
   const int64_t nvec = n / 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(256) quantize_kernel(const __nv_bfloat16* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) amax_kernel(const __nv_bfloat16* __restrict__ x, int64_t n,
                                                    float* __restrict__ amax) {
+  pdl_wait();
   float m = 0.f;
   const int64_t nvec = n / 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -76,6 +78,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256) silu_quant_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y,
                                                          __nv_bfloat16* __restrict__ yb, int64_t n,
                                                          const float* __restrict__ scale) {
+  pdl_wait();
   const float s = scale ? __ldg(scale) : 1.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -100,6 +103,7 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ yb, int64_t ldyb,
                                                            const float* __restrict__ in_scale, int rows, int L, int D,
                                                            float eps) {
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(const __nv_bfloat16* _
                                                           const __nv_bfloat16* __restrict__ rcos,
                                                           const __nv_bfloat16* __restrict__ rsin, int64_t rope_bstride,
                                                           int64_t rows, int H, int S, float eps) {
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -257,6 +262,7 @@ __global__ void __launch_bounds__(kGemvWarps * 32) f8_gemv_kernel(const uint8_t*
                                                                   const float* __restrict__ sa,
                                                                   const float* __restrict__ sw,
                                                                   __nv_bfloat16* __restrict__ out, int M, int N, int K) {
+  pdl_wait();
   extern __shared__ __half a_sm[];  // [kGemvMT][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float s = __ldg(sa) * __ldg(sw);
@@ -325,6 +331,122 @@ __global__ void __launch_bounds__(kGemvWarps * 32) f8_gemv_kernel(const uint8_t*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// batched modulation: (1) per-layer silu + quantise of the shared `vec`, (2) one weight-streaming GEMV over
+// every layer's rows.  Each warp owns 4 weight rows at a time and issues all of a row group's 16-byte loads
+// before consuming them (K = 3072: 24 loads in flight per lane).
+// ---------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) silu_quant_layers_kernel(const __nv_bfloat16* __restrict__ vec,
+                                                                const fluxb200_gemv_layer* __restrict__ layers,
+                                                                uint8_t* __restrict__ aq, int BK) {
+  pdl_wait();
+  const float s = __ldg(layers[blockIdx.x].in_qscale);
+  uint8_t* dst = aq + static_cast<int64_t>(blockIdx.x) * BK;
+  for (int i = threadIdx.x; i < BK; i += blockDim.x) {
+    float v = __bfloat162float(vec[i]);
+    float a = bf16r(v / (1.f + expf(-v)));
+    dst[i] = to_fp8<FMT>(quant_pre<FMT>(a, s));
+  }
+}
+
+constexpr int kModColsPerBlock = 64;
+constexpr int kModMT = 2;    // rows of the (tiny) batch handled per pass
+constexpr int kModCols = 2;  // weight rows a warp streams at a time
+
+template <int AFMT, int WFMT, int NK>  // NK = ceil(K / 512): 16-byte chunks per lane per weight row
+__global__ void __launch_bounds__(256, 2) gemv_layers_kernel(const fluxb200_gemv_layer* __restrict__ layers,
+                                                             int num_layers, const uint8_t* __restrict__ aq,
+                                                             __nv_bfloat16* __restrict__ out, int64_t ld_out, int B,
+                                                             int K) {
+  pdl_wait();
+  __shared__ __align__(16) __half a_sm[kModMT * NK * 512];
+  __shared__ int s_layer;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    int l = 0;
+    while (l + 1 < num_layers && layers[l + 1].block_start <= static_cast<int>(blockIdx.x)) ++l;
+    s_layer = l;
+  }
+  __syncthreads();
+  const int l = s_layer;
+  const fluxb200_gemv_layer L = layers[l];
+  const float s = __ldg(L.a_scale_recip) * __ldg(L.w_scale_recip);
+  const uint8_t* w = static_cast<const uint8_t*>(L.w);
+  const __nv_bfloat16* bias = static_cast<const __nv_bfloat16*>(L.bias);
+  const int nblk = (static_cast<int>(blockIdx.x) - L.block_start) * kModColsPerBlock;
+
+  for (int m0 = 0; m0 < B; m0 += kModMT) {
+    const int mt = min(kModMT, B - m0);
+    __syncthreads();
+    const uint8_t* asrc = aq + (static_cast<int64_t>(l) * B + m0) * K;
+    for (int i = threadIdx.x; i < mt * K / 2; i += blockDim.x) {
+      uint16_t two = *reinterpret_cast<const uint16_t*>(asrc + i * 2);
+      __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(two, AFMT == 0 ? __NV_E4M3 : __NV_E5M2);
+      *reinterpret_cast<__half2*>(a_sm + i * 2) = *reinterpret_cast<__half2*>(&hr);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int grp = 0; grp < kModColsPerBlock / (8 * kModCols); ++grp) {
+      const int n0 = nblk + (grp * 8 + warp) * kModCols;
+      if (n0 >= L.N) continue;
+      uint4 wv[kModCols][NK];
+#pragma unroll
+      for (int c = 0; c < kModCols; ++c)
+#pragma unroll
+        for (int i = 0; i < NK; ++i)
+          wv[c][i] = (n0 + c < L.N && (i * 32 + lane) * 16 < K)
+                         ? __ldg(reinterpret_cast<const uint4*>(w + static_cast<int64_t>(n0 + c) * K + (i * 32 + lane) * 16))
+                         : make_uint4(0, 0, 0, 0);
+      float acc[kModCols][kModMT];
+#pragma unroll
+      for (int c = 0; c < kModCols; ++c)
+#pragma unroll
+        for (int m = 0; m < kModMT; ++m) acc[c][m] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NK; ++i) {
+        const int k = (i * 32 + lane) * 16;
+        if (k >= K) continue;  // zero weights were loaded; skip the smem read beyond K
+        float wf[kModCols][16];
+#pragma unroll
+        for (int c = 0; c < kModCols; ++c) fp8x16_to_float<WFMT>(wv[c][i], wf[c]);
+#pragma unroll
+        for (int m = 0; m < kModMT; ++m) {
+          if (m < mt) {
+            const uint4* ap = reinterpret_cast<const uint4*>(a_sm + m * K + k);
+            uint4 lo = ap[0], hi = ap[1];
+            const __half2* h = reinterpret_cast<const __half2*>(&lo);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float2 f0 = __half22float2(h[t]), f1 = __half22float2(h2[t]);
+#pragma unroll
+              for (int c = 0; c < kModCols; ++c) {
+                acc[c][m] = fmaf(wf[c][t * 2], f0.x, acc[c][m]);
+                acc[c][m] = fmaf(wf[c][t * 2 + 1], f0.y, acc[c][m]);
+                acc[c][m] = fmaf(wf[c][8 + t * 2], f1.x, acc[c][m]);
+                acc[c][m] = fmaf(wf[c][8 + t * 2 + 1], f1.y, acc[c][m]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kModCols; ++c)
+#pragma unroll
+        for (int m = 0; m < kModMT; ++m) {
+          float v = acc[c][m];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && m < mt && n0 + c < L.N) {
+            float bb = bias ? __bfloat162float(bias[n0 + c]) : 0.f;
+            out[static_cast<int64_t>(m0 + m) * ld_out + L.out_offset + n0 + c] = __float2bfloat16_rn(fmaf(v, s, bb));
+          }
+        }
+    }
+  }
+}
+
 static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
   int64_t blocks = (work_items + threads - 1) / threads;
   int64_t cap = static_cast<int64_t>(sm_count()) * max_blocks_per_sm;
@@ -346,11 +468,8 @@ extern "C" int fluxb200_quantize(const void* x, void* y, int64_t n, const float*
              "fluxb200_quantize: x must be 16B and y 8B aligned");
   if (n == 0) return 0;
   const int grid = grid_for(n / 8 + 1, 256);
-  if (fmt == 0)
-    quantize_kernel<0><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y), n, scale);
-  else
-    quantize_kernel<1><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y), n, scale);
-  FB_CUDA_OK(cudaGetLastError());
+  FB_CUDA_OK(launch_kernel(fmt == 0 ? quantize_kernel<0> : quantize_kernel<1>, dim3(grid), dim3(256), 0, stream, 1,
+                           static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y), n, scale));
   return 0;
 }
 
@@ -359,8 +478,8 @@ extern "C" int fluxb200_amax(const void* x, int64_t n, float* amax, fluxb200_str
   FB_REQUIRE(x && amax && n >= 0, "fluxb200_amax: null operand");
   FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "fluxb200_amax: x must be 16B aligned");
   if (n == 0) return 0;
-  amax_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), n, amax);
-  FB_CUDA_OK(cudaGetLastError());
+  FB_CUDA_OK(launch_kernel(amax_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, stream, 1,
+                           static_cast<const __nv_bfloat16*>(x), n, amax));
   return 0;
 }
 
@@ -372,13 +491,9 @@ extern "C" int fluxb200_silu_quant(const void* x, void* y_fp8, void* y_bf16, int
   FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_silu_quant: bad fp8 format %d", fmt);
   if (n == 0) return 0;
   const int grid = grid_for(n, 256);
-  if (fmt == 0)
-    silu_quant_kernel<0><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y_fp8),
-                                                   static_cast<__nv_bfloat16*>(y_bf16), n, scale);
-  else
-    silu_quant_kernel<1><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y_fp8),
-                                                   static_cast<__nv_bfloat16*>(y_bf16), n, scale);
-  FB_CUDA_OK(cudaGetLastError());
+  FB_CUDA_OK(launch_kernel(fmt == 0 ? silu_quant_kernel<0> : silu_quant_kernel<1>, dim3(grid), dim3(256), 0, stream, 1,
+                           static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(y_fp8),
+                           static_cast<__nv_bfloat16*>(y_bf16), n, scale));
   return 0;
 }
 
@@ -396,17 +511,10 @@ extern "C" int fluxb200_ln_mod_quant(const void* x, int64_t ldx, const void* shi
   FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_ln_mod_quant: bad fp8 format %d", fmt);
   const int rows = B * L;
   const int grid = (rows + 7) / 8;
-  if (fmt == 0)
-    ln_mod_quant_kernel<0><<<grid, 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(shift),
-        static_cast<const __nv_bfloat16*>(scale), mod_batch_stride, static_cast<uint8_t*>(y_fp8), ldy,
-        static_cast<__nv_bfloat16*>(y_bf16), ldy_bf16, in_scale, rows, L, D, eps);
-  else
-    ln_mod_quant_kernel<1><<<grid, 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(shift),
-        static_cast<const __nv_bfloat16*>(scale), mod_batch_stride, static_cast<uint8_t*>(y_fp8), ldy,
-        static_cast<__nv_bfloat16*>(y_bf16), ldy_bf16, in_scale, rows, L, D, eps);
-  FB_CUDA_OK(cudaGetLastError());
+  FB_CUDA_OK(launch_kernel(fmt == 0 ? ln_mod_quant_kernel<0> : ln_mod_quant_kernel<1>, dim3(grid), dim3(256), 0, stream, 1,
+                           static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(shift),
+                           static_cast<const __nv_bfloat16*>(scale), mod_batch_stride, static_cast<uint8_t*>(y_fp8), ldy,
+                           static_cast<__nv_bfloat16*>(y_bf16), ldy_bf16, in_scale, rows, L, D, eps));
   return 0;
 }
 
@@ -418,11 +526,10 @@ extern "C" int fluxb200_qknorm_rope(const void* x, void* y, const float* norm_w,
   FB_REQUIRE((rope_cos == nullptr) == (rope_sin == nullptr), "fluxb200_qknorm_rope: cos and sin go together");
   const int64_t rows = static_cast<int64_t>(B) * H * S;
   const int64_t grid = (rows + 7) / 8;
-  qknorm_rope_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), norm_w,
-      static_cast<const __nv_bfloat16*>(rope_cos), static_cast<const __nv_bfloat16*>(rope_sin), rope_batch_stride,
-      rows, H, S, eps);
-  FB_CUDA_OK(cudaGetLastError());
+  FB_CUDA_OK(launch_kernel(qknorm_rope_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0, stream, 1,
+                           static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), norm_w,
+                           static_cast<const __nv_bfloat16*>(rope_cos), static_cast<const __nv_bfloat16*>(rope_sin),
+                           rope_batch_stride, rows, H, S, eps));
   return 0;
 }
 
@@ -443,15 +550,44 @@ extern "C" int fluxb200_f8_gemv(const void* a, int a_fmt, const void* w, int w_f
   do {                                                                                                          \
     auto kern = f8_gemv_kernel<AF, WF>;                                                                         \
     if (smem > 48 * 1024) FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, kGemvWarps * 32, smem, stream>>>(static_cast<const uint8_t*>(a), static_cast<const uint8_t*>(w), \
-                                                   static_cast<const __nv_bfloat16*>(bias), sa, sw,              \
-                                                   static_cast<__nv_bfloat16*>(out), M, N, K);                   \
+    FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kGemvWarps * 32), smem, stream, 1, static_cast<const uint8_t*>(a), \
+                             static_cast<const uint8_t*>(w), static_cast<const __nv_bfloat16*>(bias), sa, sw,        \
+                             static_cast<__nv_bfloat16*>(out), M, N, K));                                            \
   } while (0)
   if (a_fmt == 0 && w_fmt == 0) FB_GEMV(0, 0);
   else if (a_fmt == 1 && w_fmt == 0) FB_GEMV(1, 0);
   else if (a_fmt == 0 && w_fmt == 1) FB_GEMV(0, 1);
   else FB_GEMV(1, 1);
 #undef FB_GEMV
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_modulation_batched(const void* vec, const fluxb200_gemv_layer* layers, int num_layers,
+                                           int total_blocks, void* aq, void* out, int64_t ld_out, int B, int K,
+                                           int a_fmt, int w_fmt, fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(vec && layers && aq && out, "fluxb200_modulation_batched: null operand");
+  FB_REQUIRE(num_layers > 0 && total_blocks > 0 && B > 0 && B <= 16, "fluxb200_modulation_batched: bad sizes");
+  FB_REQUIRE(K % 16 == 0 && K <= 4096, "fluxb200_modulation_batched: K=%d must be a multiple of 16 and <= 4096", K);
+  FB_REQUIRE((a_fmt == 0 || a_fmt == 1) && w_fmt == 0, "fluxb200_modulation_batched: e4m3 weights, e4m3/e5m2 inputs");
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(aq) & 15) == 0, "fluxb200_modulation_batched: workspace must be 16B aligned");
+  const __nv_bfloat16* v = static_cast<const __nv_bfloat16*>(vec);
+  uint8_t* a8 = static_cast<uint8_t*>(aq);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+#define FB_MOD(AF, NK_)                                                                                   \
+  do {                                                                                                    \
+    FB_CUDA_OK(launch_kernel(silu_quant_layers_kernel<AF>, dim3(num_layers), dim3(256), 0, stream, 1, v, layers, a8, B * K)); \
+    FB_CUDA_OK(launch_kernel(gemv_layers_kernel<AF, 0, NK_>, dim3(total_blocks), dim3(256), 0, stream, 1, layers, num_layers, \
+                             static_cast<const uint8_t*>(a8), o, ld_out, B, K));                                          \
+  } while (0)
+  const int nk = (K + 511) / 512;
+  if (a_fmt == 0) {
+    if (nk <= 1) FB_MOD(0, 1); else if (nk <= 2) FB_MOD(0, 2); else if (nk <= 6) FB_MOD(0, 6); else FB_MOD(0, 8);
+  } else {
+    if (nk <= 1) FB_MOD(1, 1); else if (nk <= 2) FB_MOD(1, 2); else if (nk <= 6) FB_MOD(1, 6); else FB_MOD(1, 8);
+  }
+#undef FB_MOD
   FB_CUDA_OK(cudaGetLastError());
   return 0;
 }

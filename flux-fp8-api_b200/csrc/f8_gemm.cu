@@ -50,6 +50,9 @@ struct GemmParams {
   fluxb200_gemm_args g;
   int num_m_tiles, num_n_tiles, num_k_blocks;
   uint32_t idesc;
+  // Timing experiments only (env FLUXB200_GEMM_DEBUG; results are garbage): 1 = no TMA traffic after the ring is
+  // first filled (pure MMA issue rate), 2 = no MMAs (pure TMA pipeline rate).
+  int debug;
 };
 
 struct RowInfo {
@@ -284,6 +287,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
     }
   }
   if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
+    // (norm weights are parameters, never written by a preceding kernel: safe before griddepcontrol.wait)
     if (threadIdx.x < 2 * kHeadDim)
       norm_smem[threadIdx.x] =
           threadIdx.x < kHeadDim ? g.q_norm_w[threadIdx.x] : g.k_norm_w[threadIdx.x - kHeadDim];
@@ -292,21 +296,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs.  This grid is
+  // one persistent wave, so the next kernel may be scheduled as soon as our CTAs start retiring.
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int num_tiles = P.num_m_tiles * P.num_n_tiles;
 
+  // Producer and issuer run their loops warp-uniformly; only the TMA / MMA / commit instructions are predicated on
+  // one elected lane, so descriptors and addresses stay in uniform registers (a `lane == 0` loop makes ptxas wrap
+  // every UTMALDG / UTCQMMA in a vector->uniform waterfall loop).
   if (warp == 0) {
-    if (lane == 0) {
-      // ---- TMA producer (both CTAs of a pair: each loads its own A rows and its half of the W rows) ----
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-        const int m0 = (tile % P.num_m_tiles) * kTileM + cta_rank * kBM;
-        const int n0 = (tile / P.num_m_tiles) * BN + cta_rank * S::kBRows;
-        for (int kb = 0; kb < P.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::kStage;
-          if constexpr (CG == 2) {
+    // ---- TMA producer (both CTAs of a pair: each loads its own A rows and its half of the W rows) ----
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+      const int m0 = (tile % P.num_m_tiles) * kTileM + cta_rank * kBM;
+      const int n0 = (tile / P.num_m_tiles) * BN + cta_rank * S::kBRows;
+      for (int kb = 0; kb < P.num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * S::kStage;
+        if (elect_one()) {
+          if (P.debug == 1 && (phase != 0 || tile != tile0)) {
+            if (cta_rank == 0) mbar_arrive(&full_bar[stage]);  // pretend the data landed
+          } else if constexpr (CG == 2) {
             // all bytes of the pair are accounted on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStage);
             tma_load_2d_2sm(sa, &P.tmap_a, &full_bar[stage], kb * kBK, m0);
@@ -316,21 +329,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
             tma_load_2d(sa, &P.tmap_a, &full_bar[stage], kb * kBK, m0);
             tma_load_2d(sa + S::kA, &P.tmap_w, &full_bar[stage], kb * kBK, n0);
           }
-          if (++stage == S::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == S::kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0) {
       // ---- MMA issuer (leader CTA only) ----
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const uint64_t a_desc0 = make_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t b_desc0 = make_desc_sw128(smem_u32(smem) + S::kA, 16, 1024);
       for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
@@ -338,22 +353,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
         for (int kb = 0; kb < P.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * S::kStage);
-          const uint32_t b_addr = a_addr + S::kA;
+          const uint64_t ad = desc_advance(a_desc0, stage * S::kStage);
+          const uint64_t bd = desc_advance(b_desc0, stage * S::kStage);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 32; ++k) {
-            uint64_t ad = make_desc_sw128(a_addr + k * 32, 16, 1024);
-            uint64_t bd = make_desc_sw128(b_addr + k * 32, 16, 1024);
-            if constexpr (CG == 2)
-              mma_f8f6f4_ss_2sm(d_tmem, ad, bd, P.idesc, (kb | k) != 0 ? 1u : 0u);
-            else
-              mma_f8f6f4_ss(d_tmem, ad, bd, P.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 32; ++k) {
+              if (P.debug == 2) break;
+              if constexpr (CG == 2)
+                mma_f8f6f4_ss_2sm(d_tmem, desc_advance(ad, k * 32), desc_advance(bd, k * 32), P.idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                mma_f8f6f4_ss(d_tmem, desc_advance(ad, k * 32), desc_advance(bd, k * 32), P.idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // smem slot reusable (in both CTAs) once these MMAs have read it
+            if constexpr (CG == 2) tc_commit_2sm(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
+            if (kb == P.num_k_blocks - 1) {
+              if constexpr (CG == 2) tc_commit_2sm(&tfull_bar[as], 3); else tc_commit(&tfull_bar[as]);
+            }
           }
-          // smem slot reusable (in both CTAs) once these MMAs have read it
-          if constexpr (CG == 2) tc_commit_2sm(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
-          if (kb == P.num_k_blocks - 1) {
-            if constexpr (CG == 2) tc_commit_2sm(&tfull_bar[as], 3); else tc_commit(&tfull_bar[as]);
-          }
+          __syncwarp();
           if (++stage == S::kStages) {
             stage = 0;
             phase ^= 1;
@@ -365,7 +382,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
         }
       }
     }
-    __syncwarp();
   } else if (warp >= kEpiWarp0) {
     const int lg = warp & 3;                 // TMEM lane group of this warp
     const int half = (warp - kEpiWarp0) >> 2;  // which half of the BN columns
@@ -460,19 +476,7 @@ static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
   const int tiles = P.num_m_tiles * P.num_n_tiles;
   const int units = sm_count() / CG;  // CTAs (CG == 1) or CTA pairs (CG == 2) that fit on the device
   const int grid = (tiles < units ? tiles : units) * CG;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = S::kTotal;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  FB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P));
+  FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, CG, P));
   return 0;
 }
 
@@ -545,6 +549,11 @@ extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_
 
   GemmParams P;
   P.g = g;
+  static const int dbg = [] {
+    const char* e = getenv("FLUXB200_GEMM_DEBUG");
+    return e ? atoi(e) : 0;
+  }();
+  P.debug = dbg;
   P.num_m_tiles = (g.M + kBM * cg - 1) / (kBM * cg);
   P.num_n_tiles = (g.N + bn - 1) / bn;
   P.num_k_blocks = (g.K + kBK - 1) / kBK;

@@ -1,5 +1,6 @@
 #include "host_util.h"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace fb {
@@ -17,6 +18,14 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   last_error_ref() = buf;
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FLUXB200_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
 }
 
 int sm_count() {

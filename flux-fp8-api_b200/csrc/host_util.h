@@ -31,6 +31,37 @@ int sm_count();
     if (!(cond)) return fb::set_error(FLUXB200_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+// Programmatic dependent launch for our kernels (env FLUXB200_PDL=0 disables).
+bool pdl_enabled();
+
+// cudaLaunchKernelEx with an optional thread-block cluster (x dimension) and the PDL attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // 2-D row-major tensor [rows, cols] of `elem_bytes`-wide elements, row pitch `pitch_bytes`,
 // box = [box_rows, box_cols], SWIZZLE_128B (box_cols*elem_bytes must be 128).
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,

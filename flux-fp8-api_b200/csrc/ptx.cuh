@@ -47,6 +47,15 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (no-ops when the kernel was launched without the PDL attribute)
+// ---------------------------------------------------------------------------------------------
+// Blocks until every kernel this one depends on has completed and its memory is visible.  Everything before it
+// (barrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Allows the next kernel in the stream to be scheduled once all CTAs of this grid have called it (or exited).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -229,6 +238,13 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
   return d;
 }
 
+// Advance a descriptor's start address by `byte_off` (a multiple of 16; the 14-bit address field never carries
+// because shared memory is < 256 KB).  Lets the MMA issuer precompute one descriptor per tile and pay a single
+// 64-bit add per MMA instead of rebuilding the bit-fields.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t byte_off) {
+  return desc + static_cast<uint64_t>(byte_off >> 4);
+}
+
 // Instruction descriptor (upper 32 bits of the "idesc" operand).
 // bits: [4,6) D fmt (1=f32) | [7,10) A fmt | [10,13) B fmt | 15 A major (1=MN) | 16 B major (1=MN)
 //       [17,23) N>>3 | [24,29) M>>4
@@ -275,6 +291,18 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Compile-time accumulate flag (no setp in the issue stream).
+template <bool ACC>
+__device__ __forceinline__ void mma_f16_ss_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  if constexpr (ACC)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc)
+                 : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc)
+                 : "memory");
 }
 // A operand from tensor memory (TS form).
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -324,7 +352,14 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // numeric helpers shared by the epilogues.  bf16 round-trips reproduce the reference's eager
 // "every op rounds to bf16" semantics.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// Round-to-nearest-even to bf16, result kept as fp32.  cvt.rn.bf16x2.f32 (SASS F2FP, full-rate ALU pipe) with a
+// zero low half yields the rounded value directly as fp32 bits; the scalar cvt.rn.bf16.f32 compiles to F2F,
+// which issues at quarter rate through the XU pipe and dominated the LayerNorm / epilogue instruction mix.
+__device__ __forceinline__ float bf16r(float x) {
+  uint32_t u;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(x), "f"(0.f));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

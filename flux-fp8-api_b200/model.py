@@ -21,7 +21,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _cabi as cabi
-from .blocks import DoubleStreamBlock, EmbedND, SingleStreamBlock, tensor_version
+from .blocks import DoubleStreamBlock, EmbedND, ModulationBank, SingleStreamBlock, tensor_version
 from .f8linear import F8Linear
 
 BF16 = torch.bfloat16
@@ -163,9 +163,30 @@ class Flux(nn.Module):
         self._cache = _StepInvariantCache()
         #: set False to recompute txt_in / vector_in / pe every step exactly as the reference does
         self.cache_step_invariants = True
+        #: one batched launch for all Modulation.lin of a step (False: each block runs its own, as the reference)
+        self.batch_modulation = True
 
     def reset_request_cache(self) -> None:
         self._cache.clear()
+
+    def _modulation_bank(self, vec: Tensor) -> Optional[ModulationBank]:
+        """The batched modulation launch, built lazily once every Modulation.lin is a frozen F8Linear (None while
+        calibrating or when modulation is left in bf16, quantize_modulation=False)."""
+        if not self.batch_modulation or vec.dtype != BF16:
+            return None
+        bank = self.__dict__.get("_mod_bank")
+        if bank is not None and not bank.stale():
+            return bank
+        mods = []
+        for b in self.double_blocks:
+            mods += [b.img_mod, b.txt_mod]
+        mods += [b.modulation for b in self.single_blocks]
+        try:
+            bank = ModulationBank(mods)
+        except ValueError:
+            return None
+        self.__dict__["_mod_bank"] = bank
+        return bank
 
     def _invariants_cacheable(self) -> bool:
         """While an embedder F8Linear is still calibrating it must see one call per step, like the reference."""
@@ -196,10 +217,19 @@ class Flux(nn.Module):
         pe = cache.get("pe", (txt_ids, img_ids), lambda: self.pe_embedder(torch.cat((txt_ids, img_ids), dim=1)))
 
         T = txt.shape[1]
-        for block in self.double_blocks:
-            img, txt = block(img=img, txt=txt, vec=vec, pe=pe)
-        x = torch.cat((txt, img), 1)
-        for block in self.single_blocks:
-            x = block(x, vec=vec, pe=pe)
+        bank = self._modulation_bank(vec)
+        if bank is None:
+            for block in self.double_blocks:
+                img, txt = block(img=img, txt=txt, vec=vec, pe=pe)
+            x = torch.cat((txt, img), 1)
+            for block in self.single_blocks:
+                x = block(x, vec=vec, pe=pe)
+        else:
+            mods = iter(bank(vec))  # every block's shift/scale/gate from one batched launch
+            for block in self.double_blocks:
+                img, txt = block(img=img, txt=txt, vec=vec, pe=pe, mods=(next(mods), next(mods)))
+            x = torch.cat((txt, img), 1)
+            for block in self.single_blocks:
+                x = block(x, vec=vec, pe=pe, mod=next(mods)[0])
         x = x[:, T:, ...]
         return self.final_layer(x, vec)

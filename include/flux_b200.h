@@ -123,6 +123,30 @@ int fluxb200_f8_gemv(const void* a_fp8, int a_fmt, const void* w_fp8, int w_fmt,
                      int K, fluxb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * All Modulation.lin of one denoise step in two launches (they share the input `vec`):
+ *   for every layer l:  out[b, out_offset_l + n] = bf16( (q_l(silu(vec[b])) . W_l[n]) * sa_l * sw_l + bias_l[n] )
+ * with q_l the layer's own input quantisation.  Replaces 76 x (SiLU + 3-kernel quantise + _scaled_mm)
+ * per step (modules/flux_model.py:251-257 called at :363-364, :468).  `layers` is a device array.
+ * aq_workspace: fp8 [num_layers, B, K] scratch.  Blocks of 64 output columns: layer l owns blocks
+ * [block_start_l, block_start_l + ceil(N_l / 64)); total_blocks = sum of those.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fluxb200_gemv_layer {
+  const void* w;              /* fp8 [N, K]                                   */
+  const void* bias;           /* bf16 [N] or NULL                             */
+  const float* in_qscale;     /* multiplier used to quantise silu(vec)        */
+  const float* a_scale_recip; /* F8Linear.input_scale_reciprocal              */
+  const float* w_scale_recip; /* F8Linear.scale_reciprocal                    */
+  int32_t N;
+  int32_t out_offset;
+  int32_t block_start;
+  int32_t _pad;
+} fluxb200_gemv_layer;
+
+int fluxb200_modulation_batched(const void* vec_bf16, const fluxb200_gemv_layer* layers, int num_layers,
+                                int total_blocks, void* aq_workspace, void* out_bf16, int64_t ld_out, int B,
+                                int K, int a_fmt, int w_fmt, fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Modulation prologue: y = quantize( bf16(silu(x)), scale )   (modules/flux_model.py:249,252 +
  * float8_quantize.py:274-276).  y_bf16 (optional) receives bf16(silu(x)) for unquantised lins.
  * ------------------------------------------------------------------------------------------- */
@@ -179,6 +203,11 @@ typedef struct fluxb200_attention_args {
 } fluxb200_attention_args;
 
 int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_stream_t stream);
+
+/* Diagnostics: cycle counters of the last attention launch's CTA 0 (host pointer to 16 x uint64):
+ * [0..5] softmax warp: wait-S, tmem load, max, exp, wait-O, store-P; [6] half-steps;
+ * [8..10] MMA issuer: wait-P, wait-KV, issue.  Synchronises the device. */
+int fluxb200_debug_counters(unsigned long long* host_out16);
 
 #ifdef __cplusplus
 }
