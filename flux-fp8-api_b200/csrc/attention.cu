@@ -499,8 +499,8 @@ __global__ void __launch_bounds__(AttnHCfg::kThreads, 1) attention_kernel_halves
   uint64_t* v_empty = v_full + KS;    // KS
   uint64_t* s_ready = v_empty + KS;   // [g][h] = 4
   uint64_t* p_ready = s_ready + 4;    // [g][h] = 4
-  uint64_t* o_done = p_ready + 4;     // [g] = 2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_done = p_ready + 4;     // [g][h] = 4: PV of half h of query tile g retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -529,8 +529,7 @@ __global__ void __launch_bounds__(AttnHCfg::kThreads, 1) attention_kernel_halves
       mbar_init(&s_ready[i], 1);
       mbar_init(&p_ready[i], 4);  // one arrive per softmax warp
     }
-    mbar_init(&o_done[0], 1);
-    mbar_init(&o_done[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&o_done[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -620,7 +619,7 @@ __global__ void __launch_bounds__(AttnHCfg::kThreads, 1) attention_kernel_halves
 #pragma unroll
           for (int kk = 0; kk < kHalf / 16; ++kk)
             mma_f16_ts(d, a0 + kk * 8, desc_advance(bd0, kk * 16 * 128), idesc_pv, (t != 0 || kk != 0) ? 1u : 0u);
-          tc_commit(&o_done[g]);
+          tc_commit(&o_done[g * 2 + hh]);
           if (hh == 1 && g == 1) tc_commit(&v_empty[st]);
         }
         __syncwarp();
@@ -644,19 +643,24 @@ __global__ void __launch_bounds__(AttnHCfg::kThreads, 1) attention_kernel_halves
           tc_fence_after();
           if (dbg) { tB = clk(); d_wp += tB - tA; tA = tB; }
           issue_pv(g, t);
-          if (t + 2 < nt) {
-            const int j1 = (t + 2) >> 1, st1 = j1 % KS;
-            if (hh == 0 && g == 0) {
-              mbar_wait(&k_full[st1], (j1 / KS) & 1);
-              tc_fence_after();
-            }
-            issue_qk(g, t + 2);
-            if (hh == 1 && g == 1) {
-              if (elect_one()) tc_commit(&k_empty[st1]);
-              __syncwarp();
-            }
-          }
           if (dbg) { tB = clk(); d_iss += tB - tA; tA = tB; }
+        }
+        if (t + 2 < nt) {
+          const int j1 = (t + 2) >> 1, st1 = j1 % KS;
+          if (hh == 0) mbar_wait(&k_full[st1], (j1 / KS) & 1);
+          for (int g = 0; g < 2; ++g) {
+            // QK(t+2) overwrites the TMEM columns PV(t) reads P from.  MMAs into different accumulators are not
+            // ordered with respect to each other, so make the dependency explicit: PV_g(t) must have retired.
+            mbar_wait(&o_done[g * 2 + hh], j & 1);
+            tc_fence_after();
+            if (dbg) { tB = clk(); d_wkv += tB - tA; tA = tB; }
+            issue_qk(g, t + 2);
+            if (dbg) { tB = clk(); d_iss += tB - tA; tA = tB; }
+          }
+          if (hh == 1) {
+            if (elect_one()) tc_commit(&k_empty[st1]);
+            __syncwarp();
+          }
         }
       }
       if (dbg) g_attn_dbg[8] = d_wp, g_attn_dbg[9] = d_wkv, g_attn_dbg[10] = d_iss;
@@ -736,20 +740,29 @@ __global__ void __launch_bounds__(AttnHCfg::kThreads, 1) attention_kernel_halves
       l += rs0 + rs1;
       if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
 
-      if (t > 0) {
-        mbar_wait(&o_done[g], (t - 1) & 1);  // previous PV of this query tile finished: O stable
+      // The S slot we are about to overwrite with P(t) last held P(t-2): wait for PV(t-2) (normally long retired;
+      // this barrier is waited every time its half comes round, so its phase parity is always unambiguous).
+      if (t >= 2) {
+        mbar_wait(&o_done[g * 2 + hh], (j - 1) & 1);
+        tc_fence_after();
+      }
+      // The rare O rescale additionally needs the previous half's PV (t-1).  Conditional wait on the other half's
+      // barrier is safe: that phase is waited again (unconditionally) at step t+1 before anything can advance it.
+      if (t > 0 && (warp_grow || P.debug == 2)) {
+        const int tp = t - 1;
+        mbar_wait(&o_done[g * 2 + (tp & 1)], (tp >> 1) & 1);
         tc_fence_after();
         if (dbg) { tB = clk(); d_wait_o += tB - tA; tA = tB; }
-        if (warp_grow) {
+      }
+      if (t > 0 && warp_grow) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t ov[32];
-            tmem_ld32(o_taddr + c * 32, ov);
-            tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t ov[32];
+          tmem_ld32(o_taddr + c * 32, ov);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st32(o_taddr + c * 32, ov);
-          }
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st32(o_taddr + c * 32, ov);
         }
       }
       {
@@ -768,7 +781,10 @@ __global__ void __launch_bounds__(AttnHCfg::kThreads, 1) attention_kernel_halves
     }
 
     // ---------------- epilogue: O / l -> bf16 -> (optional) fp8 ----------------
-    if (P.debug != 1) mbar_wait(&o_done[g], (nt - 1) & 1);
+    if (P.debug != 1) {
+      mbar_wait(&o_done[g * 2 + 0], (n - 1) & 1);  // last PV of each half
+      mbar_wait(&o_done[g * 2 + 1], (n - 1) & 1);
+    }
     tc_fence_after();
     const float inv_l = 1.f / l;
     const bool valid = qrow < a.S && P.debug != 1;
@@ -843,6 +859,421 @@ static int launch_attention_halves(const AttnParams& P, cudaStream_t stream) {
   return 0;
 }
 
+
+// =====================================================================================================
+// Event-driven variant ("v5", default).  Two query tiles per CTA, whole 128-row KV tiles, P over S in TMEM.
+//  * MMA issuer = small state machine polling the barriers of both streams (P_g ready -> issue PV_g; PV_g retired
+//    and K loaded -> issue QK_g of the next tile), so neither stream ever waits behind the other's softmax, and
+//    the TMEM hazard "QK_g(j+1) overwrites the columns PV_g(j) reads P from" is an explicit wait on PV_g(j)
+//    (MMAs into different accumulators are not ordered among themselves).
+//  * softmax = one fused pass per tile: p = exp2(s*c - m) against the running (stale) max while the tile max is
+//    tracked on the side; the row max no longer sits on the critical path in front of the MUFU work.  The first
+//    tile (no running max yet) and the rare tile whose max outgrows the running max by more than 2^8 take an exact
+//    two-step path (the latter rescales O).  Packing to bf16 pairs happens in the same loop.
+// =====================================================================================================
+struct AttnECfg {
+  static constexpr int kStages = 2;
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = 2 * kTileBytes;
+  static constexpr int kVOff = kKOff + kStages * kTileBytes;
+  static constexpr int kBarOff = kVOff + kStages * kTileBytes;
+  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr int kThreads = 384;
+};
+
+__global__ void __launch_bounds__(AttnECfg::kThreads, 1) attention_kernel_events(const __grid_constant__ AttnParams P) {
+  using C = AttnECfg;
+  constexpr int KS = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = q_full + 1;      // KS
+  uint64_t* k_empty = k_full + KS;    // KS
+  uint64_t* v_full = k_empty + KS;    // KS
+  uint64_t* v_empty = v_full + KS;    // KS
+  uint64_t* s_ready = v_empty + KS;   // [g]
+  uint64_t* p_ready = s_ready + 2;    // [g]
+  uint64_t* o_done = p_ready + 2;     // [g]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const fluxb200_attention_args& a = P.a;
+  const int q0 = blockIdx.x * (2 * kBQ);
+  const int h_idx = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * a.H + h_idx;
+  const int n = P.num_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmap_q);
+    tma_prefetch_desc(&P.tmap_k);
+    tma_prefetch_desc(&P.tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_ready[g], 1);
+      mbar_init(&p_ready[g], 4);  // one arrive per softmax warp
+      mbar_init(&o_done[g], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // q, k, v come from the preceding QKV GEMMs
+
+  if (warp < 4) {
+    reg_dec<80>();
+    if (warp == 0) {
+      // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        for (int g = 0; g < 2; ++g) {
+          uint8_t* dst = smem + C::kQOff + g * kTileBytes;
+          tma_load_3d(dst, &P.tmap_q, q_full, 0, q0 + g * kBQ, bh, kEvictFirst);
+          tma_load_3d(dst + kChunkBytes, &P.tmap_q, q_full, 64, q0 + g * kBQ, bh, kEvictFirst);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < n; ++j) {
+        const int st = j % KS;
+        const uint32_t ph = (j / KS) & 1;
+        uint8_t* kd = smem + C::kKOff + st * kTileBytes;
+        uint8_t* vd = smem + C::kVOff + st * kTileBytes;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+          tma_load_3d(kd, &P.tmap_k, &k_full[st], 0, j * kBKV, bh, kEvictLast);
+          tma_load_3d(kd + kChunkBytes, &P.tmap_k, &k_full[st], 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+          tma_load_3d(vd, &P.tmap_v, &v_full[st], 0, j * kBKV, bh, kEvictLast);
+          tma_load_3d(vd + kChunkBytes, &P.tmap_v, &v_full[st], 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ---------------- MMA issuer: event-driven over the two query-tile streams ----------------
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kFmtBF16, kBQ, kBKV, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kFmtBF16, kBQ, kD, 0, 1);  // V is MN-major
+      const uint32_t q_addr = smem_u32(smem + C::kQOff);
+      const uint32_t k_addr = smem_u32(smem + C::kKOff);
+      const uint32_t v_addr = smem_u32(smem + C::kVOff);
+      // (no runtime-indexed arrays in this loop: they would live in local memory)
+      const uint64_t q_desc0 = make_desc_sw128(q_addr, 16, 1024);
+      const uint64_t k_desc0 = make_desc_sw128(k_addr, 16, 1024);
+      const uint64_t v_desc0 = make_desc_sw128(v_addr, kChunkBytes, 1024);
+      auto ready = [&](uint64_t* bar, uint32_t parity) { return __all_sync(0xffffffffu, mbar_try_wait(bar, parity)); };
+
+      mbar_wait(q_full, 0);
+      int jq0 = 0, jq1 = 0;    // next tile whose QK stream 0 / 1 issues
+      int jp0 = 0, jp1 = 0;    // next tile whose PV stream 0 / 1 issues
+      uint32_t k_uses = 0, v_uses = 0;  // bit st: one of the two streams has already used K / V stage st
+      int remaining = 2 * n * 2;  // QK + PV events of both streams
+      int idle = 0;
+      while (remaining > 0) {
+        bool progressed = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          int& jq_g = g == 0 ? jq0 : jq1;
+          int& jp_g = g == 0 ? jp0 : jp1;
+          if (jq_g == jp_g) {
+            // next event of this stream: QK(jq).  Needs K(jq) in smem and, because S(jq) overwrites the columns
+            // PV(jq-1) reads P from, PV(jq-1) retired.
+            const int j = jq_g;
+            if (j < n) {
+              const int st = j % KS;
+              if ((j == 0 || ready(&o_done[g], (j - 1) & 1)) && ready(&k_full[st], (j / KS) & 1)) {
+                tc_fence_after();
+                const uint32_t d = tmem_base + g * 128;
+                const uint64_t ad0 = desc_advance(q_desc0, g * kTileBytes), bd0 = desc_advance(k_desc0, st * kTileBytes);
+                if (elect_one()) {
+#pragma unroll
+                  for (int kk = 0; kk < kD / 16; ++kk) {
+                    const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
+                    mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+                  }
+                  tc_commit(&s_ready[g]);
+                  if ((k_uses >> st) & 1) tc_commit(&k_empty[st]);  // second stream done with this K tile
+                }
+                __syncwarp();
+                k_uses ^= 1u << st;
+                ++jq_g;
+                --remaining;
+                progressed = true;
+              }
+            }
+          } else {
+            // next event: PV(jp).  Needs P(jp) from the softmax warpgroup and V(jp) in smem.
+            const int j = jp_g;
+            const int st = j % KS;
+            if (ready(&p_ready[g], j & 1) && ready(&v_full[st], (j / KS) & 1)) {
+              tc_fence_after();
+              const uint32_t d = tmem_base + 256 + g * 128;
+              const uint64_t bd0 = desc_advance(v_desc0, st * kTileBytes);
+              const uint32_t a0 = tmem_base + g * 128;
+              if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < kBKV / 16; ++kk)
+                  mma_f16_ts(d, a0 + kk * 8, desc_advance(bd0, kk * 2048), idesc_pv, (j != 0 || kk != 0) ? 1u : 0u);
+                tc_commit(&o_done[g]);
+                if ((v_uses >> st) & 1) tc_commit(&v_empty[st]);
+              }
+              __syncwarp();
+              v_uses ^= 1u << st;
+              ++jp_g;
+              --remaining;
+              progressed = true;
+            }
+          }
+        }
+#if FLUXB200_HANG_TRAP_NS
+        if (progressed) {
+          idle = 0;
+        } else if (++idle > (1 << 24)) {
+          if (lane == 0) printf("fluxb200: attention MMA issuer stalled (block %d,%d,%d jq %d,%d jp %d,%d)\n", blockIdx.x,
+                                blockIdx.y, blockIdx.z, jq0, jq1, jp0, jp1);
+          __trap();
+        }
+#endif
+      }
+    }
+  } else {
+    // ---------------- softmax warpgroups ----------------
+    reg_inc<208>();
+    const int g = (warp - 4) >> 2;
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    const uint32_t s_taddr = lane_base + g * 128;
+    const uint32_t o_taddr = lane_base + 256 + g * 128;
+    const float sl2 = P.scale_log2;
+    float m_used = -INFINITY;
+    float l = 0.f;
+#ifdef FLUXB200_ATTN_PROBE
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+#else
+    constexpr bool dbg = false;  // phase timers compiled out (build with -DFLUXB200_ATTN_PROBE to enable)
+#endif
+    unsigned long long d_wait_s = 0, d_ld = 0, d_max = 0, d_exp = 0, d_wait_o = 0, d_st = 0, tA = 0, tB = 0;
+
+    for (int j = 0; j < n; ++j) {
+      if (dbg) tA = clk();
+      mbar_wait(&s_ready[g], j & 1);
+      tc_fence_after();
+      if (dbg) { tB = clk(); d_wait_s += tB - tA; tA = tB; }
+      uint32_t sv[128];
+      {
+        uint32_t(*sv4)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+        tmem_ld32(s_taddr + 0, sv4[0]);
+        tmem_ld32(s_taddr + 32, sv4[1]);
+        tmem_ld32(s_taddr + 64, sv4[2]);
+        tmem_ld32(s_taddr + 96, sv4[3]);
+        tmem_ld_wait();
+      }
+      if (dbg) { tB = clk(); d_ld += tB - tA; tA = tB; }
+      const int kv_left = a.S - j * kBKV;  // columns >= kv_left are out of range (last tile only)
+      if (kv_left < kBKV) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_left) sv[i] = __float_as_uint(-INFINITY);
+      }
+      if (j == 0) {
+        // no running max yet: exact row max first
+        float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]);
+        float m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
+#pragma unroll
+        for (int i = 4; i < 128; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(sv[i]));
+          m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(sv[i + 2]));
+          m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
+        }
+        m_used = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+      }
+      if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
+      // fused pass: exponentiate against the running max, track this tile's max on the side
+      float mx0 = -INFINITY, mx1 = -INFINITY, rs0 = 0.f, rs1 = 0.f;
+      const float neg_m = -m_used;
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        const float s0 = __uint_as_float(sv[i]), s1 = __uint_as_float(sv[i + 1]);
+        mx0 = fmaxf(mx0, s0);
+        mx1 = fmaxf(mx1, s1);
+        const float p0 = fast_exp2(fmaf(s0, sl2, neg_m));
+        const float p1 = fast_exp2(fmaf(s1, sl2, neg_m));
+        rs0 += p0;
+        rs1 += p1;
+        sv[i] = __float_as_uint(p0);
+        sv[i + 1] = __float_as_uint(p1);
+      }
+      float rs = rs0 + rs1;
+      const float m_cand = fmaxf(mx0, mx1) * sl2;
+      // Lazy rescale: the stale max stands unless this tile's max outgrew it by more than 2^8 (rare after the first
+      // tiles).  Then every p of this tile, the running sum and O are multiplied by 2^(m_old - m_new).
+      const bool grow = m_cand > m_used + kRescaleThreshold;
+      const bool warp_grow = __any_sync(0xffffffffu, grow);
+      if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
+      if (warp_grow) {
+        const float m_new = fmaxf(m_used, m_cand);
+        const float alpha = fast_exp2(m_used - m_new);  // <= 1; exactly 1 for rows that did not grow
+        // Growth beyond 2^64 could have overflowed exp2 against the stale max: redo this tile exactly from the
+        // scores still sitting in TMEM (never taken for RMS-normalised q, k: |s*c| is bounded by ~25).
+        const bool redo = __any_sync(0xffffffffu, m_cand > m_used + 64.f);
+        m_used = m_new;
+        l *= alpha;
+        if (redo) {
+          uint32_t(*sv4)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+          tmem_ld32(s_taddr + 0, sv4[0]);
+          tmem_ld32(s_taddr + 32, sv4[1]);
+          tmem_ld32(s_taddr + 64, sv4[2]);
+          tmem_ld32(s_taddr + 96, sv4[3]);
+          tmem_ld_wait();
+          rs = 0.f;
+#pragma unroll
+          for (int i = 0; i < 128; ++i) {
+            const float p = (i < kv_left) ? fast_exp2(fmaf(__uint_as_float(sv[i]), sl2, -m_new)) : 0.f;
+            rs += p;
+            sv[i] = __float_as_uint(p);
+          }
+        } else {
+          rs *= alpha;
+#pragma unroll
+          for (int i = 0; i < 128; ++i) sv[i] = __float_as_uint(__uint_as_float(sv[i]) * alpha);
+        }
+        if (j > 0) {
+          mbar_wait(&o_done[g], (j - 1) & 1);  // O stable (already retired: QK(j) was only issued after it)
+          tc_fence_after();
+          if (dbg) { tB = clk(); d_wait_o += tB - tA; tA = tB; }
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(o_taddr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(o_taddr + c * 32, ov);
+          }
+        }
+      }
+      l += rs;
+      // P (bf16 pairs) over the S columns: column c holds kv (2c, 2c+1) of this row
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            pk[i] = pack_bf16x2(__uint_as_float(sv[half * 64 + 2 * i]), __uint_as_float(sv[half * 64 + 2 * i + 1]));
+          tmem_st32(s_taddr + half * 32, pk);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+      if (dbg) { tB = clk(); d_st += tB - tA; tA = tB; }
+    }
+    if (dbg) {
+      g_attn_dbg[0] = d_wait_s, g_attn_dbg[1] = d_ld, g_attn_dbg[2] = d_max, g_attn_dbg[3] = d_exp;
+      g_attn_dbg[4] = d_wait_o, g_attn_dbg[5] = d_st, g_attn_dbg[6] = n;
+      g_attn_dbg[8] = g_attn_dbg[9] = g_attn_dbg[10] = 0;
+    }
+
+    // ---------------- epilogue: O / l -> bf16 -> (optional) fp8 ----------------
+    mbar_wait(&o_done[g], (n - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const bool valid = qrow < a.S;
+    const bool second = a.out1 != nullptr && qrow >= a.split_row;
+    void* const outp = second ? a.out1 : a.out;
+    const int64_t obase = second ? static_cast<int64_t>(b) * a.out1_batch_stride +
+                                       static_cast<int64_t>(qrow - a.split_row) * a.ldo1 + h_idx * kD
+                                 : static_cast<int64_t>(b) * a.out_batch_stride + static_cast<int64_t>(qrow) * a.ldo + h_idx * kD;
+    float oscale = 1.f;
+    if (a.out_kind == 1) oscale = __ldg(qrow < a.split_row ? a.out_scale0 : a.out_scale1);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t ov[32];
+      tmem_ld32(o_taddr + c * 32, ov);
+      tmem_ld_wait();
+      if (!valid) continue;
+      if (a.out_kind == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + obase + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(ov[q * 8 + 0]) * inv_l, __uint_as_float(ov[q * 8 + 1]) * inv_l);
+          o.y = pack_bf16x2(__uint_as_float(ov[q * 8 + 2]) * inv_l, __uint_as_float(ov[q * 8 + 3]) * inv_l);
+          o.z = pack_bf16x2(__uint_as_float(ov[q * 8 + 4]) * inv_l, __uint_as_float(ov[q * 8 + 5]) * inv_l);
+          o.w = pack_bf16x2(__uint_as_float(ov[q * 8 + 6]) * inv_l, __uint_as_float(ov[q * 8 + 7]) * inv_l);
+          dst[q] = o;
+        }
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(outp) + obase + c * 32);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float o = bf16r(__uint_as_float(ov[q * 16 + tt * 4 + e]) * inv_l);
+              f[e] = a.out_fmt == FLUXB200_E5M2 ? quant_pre<1>(o, oscale) : quant_pre<0>(o, oscale);
+            }
+            if (a.out_fmt == FLUXB200_E5M2)
+              w[tt] = to_fp8x2<1>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<1>(f[2], f[3])) << 16);
+            else
+              w[tt] = to_fp8x2<0>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<0>(f[2], f[3])) << 16);
+          }
+          dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_attention_events(const AttnParams& P, cudaStream_t stream) {
+  using C = AttnECfg;
+  static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
+  static bool attr_set = false;
+  if (!attr_set) {
+    FB_CUDA_OK(cudaFuncSetAttribute(attention_kernel_events, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+    attr_set = true;
+  }
+  const fluxb200_attention_args& a = P.a;
+  dim3 grid((a.S + 2 * kBQ - 1) / (2 * kBQ), a.H, a.B);
+  FB_CUDA_OK(launch_kernel(attention_kernel_events, grid, dim3(C::kThreads), C::kTotal, stream, 1, P));
+  return 0;
+}
+
 template <int NQ, bool TS>
 static int launch_attention(const AttnParams& P, cudaStream_t stream) {
   using C = AttnCfg<NQ, TS>;
@@ -899,8 +1330,10 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
   if ((rc = make_tmap_3d(&P.tmap_v, a.v, 2, kD, a.S, bhn, row_bytes, row_bytes * a.S, 64, kBKV, 1))) return rc;
 
   switch (a.variant) {
-    case 0: return launch_attention_halves(P, stream);      // 2 query tiles x 2 KV halves in flight (default)
-    case 1: return launch_attention<2, true>(P, stream);   // 2 query tiles, P through TMEM
+    case 0:                                                // default = fastest measured (profiles/r1_attention_variants.md)
+    case 1: return launch_attention<2, true>(P, stream);   // 2 query tiles, whole KV tiles, P through TMEM
+    case 5: return launch_attention_halves(P, stream);     // 2 query tiles x 2 KV halves in flight, explicit PV->QK waits
+    case 6: return launch_attention_events(P, stream);     // event-driven issuer + fused single-pass softmax
     case 2: return launch_attention<1, false>(P, stream);  // 1 query tile, P through smem (SS MMA)
     case 3: return launch_attention<1, true>(P, stream);   // 1 query tile, P through TMEM
     case 4: return launch_attention<2, false>(P, stream);  // 2 query tiles, P through smem

@@ -69,6 +69,31 @@ def test_blocks_and_forward_match_reference_outputs(gold, cpu_semantics, monkeyp
     assert maxdiff(results["fused"], results["eager"]) <= 2.0 ** -5
 
 
+def test_batched_modulation_matches_per_layer(gold):
+    """ModulationBank (one launch pair for every Modulation.lin) == each Modulation.forward on its own, to 1 bf16
+    ulp (the two GEMV kernels accumulate in a different order), for several batch sizes."""
+    from flux_fp8_api_b200 import blocks
+
+    net = tiny_net(gold)
+    mods = [net.double_blocks[0].img_mod, net.double_blocks[0].txt_mod, net.single_blocks[0].modulation]
+    bank = blocks.ModulationBank(mods)
+    assert not bank.stale()
+    with torch.inference_mode():
+        for B in (1, 2, 5):
+            vec = torch.randn(B, net.hidden_size, device=DEV, generator=torch.Generator(device=DEV).manual_seed(B)).to(BF16)
+            for m, (o1, o2) in zip(mods, bank(vec)):
+                r1, r2 = m(vec)
+                for ours, ref in zip(tuple(o1) + (tuple(o2) if o2 else ()), tuple(r1) + (tuple(r2) if r2 else ())):
+                    assert ours.shape == ref.shape
+                    assert maxdiff(ours, ref) <= 2.0 ** -7 * max(1.0, ref.abs().max().item())
+        # and the model gives the same prediction with and without the bank
+        inp = {k: v.to(DEV) for k, v in gold["inputs"].items()}
+        y_bank = net(**inp)
+        net.batch_modulation = False
+        y_layer = net(**inp)
+        assert maxdiff(y_bank, y_layer) <= 2.0 ** -5
+
+
 def test_graph_replay_equals_eager_launch(gold):
     from flux_fp8_api_b200 import pipeline as PL
 
