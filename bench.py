@@ -305,6 +305,13 @@ def main():
             a[2] += 1
         gf, gms, gn = agg["f8_gemm"]
         af, ams, an = agg["attention"]
+        hbm = {}
+        for kind in ("ln_mod_quant", "modulation_batched"):
+            if kind in agg:
+                bts, ms_, cnt = agg[kind]
+                hbm[kind] = {"achieved": bts / (ms_ * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": bts / (ms_ * 1e-3) / 1e9 / peaks["hbm_gbs"], "launches_per_step": cnt // 2,
+                             "ms_per_step": ms_ / 2}
         fp8_peak = 2.0 * peaks["bf16_tflops_sustained"]
         achieved = gf / (gms * 1e-3) / 1e12
         roof = {
@@ -315,6 +322,7 @@ def main():
             "attention": {"achieved": af / (ams * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                           "frac": af / (ams * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
                           "launches_per_step": an // 2, "ms_per_step": ams / 2},
+            "hbm_kernels": hbm,
             "step_tensor_frac": (F8_FLOPS / (fp8_peak * 1e12) + ATTN_FLOPS / (peaks["bf16_tflops_sustained"] * 1e12))
                                 / (ms_per_step * 1e-3),
             "fp8_pipe_util_nominal": F8_FLOPS / (ms_per_step * 1e-3) / 4.5e15,

@@ -28,6 +28,7 @@ EXPORTS = (
     "fluxb200_quantize",
     "fluxb200_amax",
     "fluxb200_f8_gemm",
+    "fluxb200_f8_gemm_grouped",
     "fluxb200_f8_gemv",
     "fluxb200_modulation_batched",
     "fluxb200_silu_quant",
@@ -144,6 +145,7 @@ def load() -> C.CDLL:
     lib.fluxb200_quantize.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     lib.fluxb200_amax.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.fluxb200_f8_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    lib.fluxb200_f8_gemm_grouped.argtypes = [C.POINTER(GemmArgs), C.c_int, C.c_void_p]
     lib.fluxb200_f8_gemv.argtypes = [
         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_int, C.c_int, C.c_int, C.c_void_p,

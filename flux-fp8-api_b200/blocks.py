@@ -233,10 +233,11 @@ class ModulationBank:
         vec = vec.contiguous()
         out = torch.empty((B, self.total_n), dtype=BF16, device=vec.device)
         aq = torch.empty((len(self.mods), B, self.K), dtype=torch.uint8, device=vec.device)
-        cabi.check(cabi.load().fluxb200_modulation_batched(
-            vec.data_ptr(), self.table.data_ptr(), len(self.mods), self.total_blocks, aq.data_ptr(), out.data_ptr(),
-            out.stride(0), B, self.K, cabi.fp8_fmt(self.in_dtype), cabi.E4M3, cabi.stream_ptr()),
-            "fluxb200_modulation_batched")
+        ops._timed("modulation_batched", float(self.total_n) * self.K,
+                   lambda: cabi.check(cabi.load().fluxb200_modulation_batched(
+                       vec.data_ptr(), self.table.data_ptr(), len(self.mods), self.total_blocks, aq.data_ptr(),
+                       out.data_ptr(), out.stride(0), B, self.K, cabi.fp8_fmt(self.in_dtype), cabi.E4M3,
+                       cabi.stream_ptr()), "fluxb200_modulation_batched"))
         res = []
         for m, off in zip(self.mods, self.offsets):
             chunks = out[:, None, off:off + m.lin.out_features].chunk(m.multiplier, dim=-1)
@@ -257,6 +258,9 @@ def _gate2d(gate: Tensor) -> Tensor:
 # DoubleStreamBlock
 # ------------------------------------------------------------------------------------------------
 class DoubleStreamBlock(nn.Module):
+    #: launch each txt/img GEMM pair as one grouped kernel (False: two launches, for A/B measurements)
+    group_streams = True
+
     def __init__(self, hidden_size: int, num_heads: int, mlp_ratio: float, qkv_bias: bool = False,
                  dtype: torch.dtype = torch.float16, quantized_modulation: bool = False, prequantized: bool = False):
         super().__init__()
@@ -307,12 +311,19 @@ class DoubleStreamBlock(nn.Module):
         q = torch.empty((B, H, S, HEAD_DIM), dtype=BF16, device=dev)
         k, v = torch.empty_like(q), torch.empty_like(q)
 
-        for x, mod, attn, rows, off in ((txt, txt_mod1, self.txt_attn, T, 0), (img, img_mod1, self.img_attn, L, T)):
+        # The txt and img streams use different weights on different row counts; each pair of GEMMs goes out as ONE
+        # grouped launch (the txt problem alone, M = 512 per sample, would leave most SMs idle).
+        streams = ((txt, txt_mod1, txt_mod2, self.txt_attn, self.txt_mlp, T, 0),
+                   (img, img_mod1, img_mod2, self.img_attn, self.img_mlp, L, T))
+        group = []
+        for x, mod1, _, attn, _, rows, off in streams:
             lin = attn.qkv
-            a8, _ = ops.ln_mod_quant(x, mod.shift, mod.scale, lin.qscale, lin.input_float8_dtype)
+            a8, _ = ops.ln_mod_quant(x, mod1.shift, mod1.scale, lin.qscale, lin.input_float8_dtype)
             ops.f8_gemm_qkv_rope(a8.view(-1, D), lin.float8_data, lin.bias, lin.input_scale_reciprocal,
                                  lin.scale_reciprocal, q, k, v, attn.norm.query_norm.weight_fp32(),
-                                 attn.norm.key_norm.weight_fp32(), cos, sin, rows_per_batch=rows, seq_offset=off)
+                                 attn.norm.key_norm.weight_fp32(), cos, sin, rows_per_batch=rows, seq_offset=off,
+                                 defer=group)
+        self._launch(group)
 
         tp, ip = self.txt_attn.proj, self.img_attn.proj
         if tp.input_float8_dtype != ip.input_float8_dtype:
@@ -322,20 +333,42 @@ class DoubleStreamBlock(nn.Module):
         ops.attention(q, k, v, out=txt_a8, out_scale0=tp.qscale, out_scale1=ip.qscale, split_row=T,
                       out1=img_a8)
 
-        outs = []
-        for x, a8, mod1, mod2, attn, mlp, rows in ((img, img_a8, img_mod1, img_mod2, self.img_attn, self.img_mlp, L),
-                                                   (txt, txt_a8, txt_mod1, txt_mod2, self.txt_attn, self.txt_mlp, T)):
-            proj, up, down = attn.proj, mlp[0], mlp[2]
-            # x = x + gate1 * proj(attn)
-            y = ops.f8_gemm_gate_residual(a8.view(-1, D), proj.float8_data, proj.bias, proj.input_scale_reciprocal,
-                                          proj.scale_reciprocal, x.view(-1, D), _gate2d(mod1.gate), rows)
-            # x = x + gate2 * mlp((1 + scale2) * LN(x) + shift2)
+        # x = x + gate1 * proj(attn)
+        ys, group = [], []
+        for (x, mod1, _, attn, _, rows, _), a8 in zip(streams, (txt_a8, img_a8)):
+            proj = attn.proj
+            ys.append(ops.f8_gemm_gate_residual(a8.view(-1, D), proj.float8_data, proj.bias, proj.input_scale_reciprocal,
+                                                proj.scale_reciprocal, x.view(-1, D), _gate2d(mod1.gate), rows,
+                                                defer=group))
+        self._launch(group)
+        # x = x + gate2 * mlp((1 + scale2) * LN(x) + shift2)
+        hs, group = [], []
+        for (x, _, mod2, _, mlp, rows, _), y in zip(streams, ys):
+            up, down = mlp[0], mlp[2]
             m8, _ = ops.ln_mod_quant(y.view(B, rows, D), mod2.shift, mod2.scale, up.qscale, up.input_float8_dtype)
-            h8 = ops.f8_gemm_gelu_quant(m8.view(-1, D), up.float8_data, up.bias, up.input_scale_reciprocal,
-                                        up.scale_reciprocal, down.qscale, down.input_float8_dtype)
+            hs.append(ops.f8_gemm_gelu_quant(m8.view(-1, D), up.float8_data, up.bias, up.input_scale_reciprocal,
+                                             up.scale_reciprocal, down.qscale, down.input_float8_dtype, defer=group))
+        self._launch(group)
+        group = []
+        for (x, _, mod2, _, mlp, rows, _), y, h8 in zip(streams, ys, hs):
+            down = mlp[2]
             ops.f8_gemm_gate_residual(h8, down.float8_data, down.bias, down.input_scale_reciprocal,
-                                      down.scale_reciprocal, y, _gate2d(mod2.gate), rows, out=y)
-            outs.append(y.view(B, rows, D))
+                                      down.scale_reciprocal, y, _gate2d(mod2.gate), rows, out=y, defer=group)
+        self._launch(group)
+        txt_out, img_out = ys[0].view(B, T, D), ys[1].view(B, L, D)
+        return img_out, txt_out
+
+    @staticmethod
+    def _launch(group):
+        """Launch the txt/img pair grouped when the two problems are compatible, else one by one."""
+        a, b = group
+        same = (a.N == b.N and a.K == b.K and a.a_fmt == b.a_fmt and a.w_fmt == b.w_fmt and a.out_fmt == b.out_fmt)
+        if same and DoubleStreamBlock.group_streams:
+            ops.run_gemm_group(group)
+        else:
+            ops.run_gemm(a)
+            ops.run_gemm(b)
+
         return outs[0], outs[1]
 
     def _forward_eager(self, img, txt, pe, mods):

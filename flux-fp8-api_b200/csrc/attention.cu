@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
 #pragma unroll
           for (int kk = 0; kk < kD / 16; ++kk) {
             const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
-            mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+            if (P.debug == 3)  // timing experiment: A operand (Q) from TMEM instead of shared memory
+              mma_f16_ts(d, tmem_base + 256 + g * 128 + kk * 8, desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+            else
+              mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
           }
         }
         __syncwarp();
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
           const int st = j % KS;
           mbar_wait(&v_full[st], (j / KS) & 1);
           for (int g = 0; g < 2; ++g) {
-            mbar_wait(&p_ready[g], j & 1);
+            if (P.debug == 0) mbar_wait(&p_ready[g], j & 1);
             tc_fence_after();
             issue_pv(g, g, st, j == 0);
             commit(&o_done[g]);
@@ -248,6 +251,10 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
               if (g == 1) commit(&k_empty[st1]);
             }
           }
+        }
+        if (P.debug != 0) {  // drain the tensor pipe before teardown
+          commit(q_full);
+          mbar_wait(q_full, 1);
         }
       } else {
         issue_qk(0, 0, 0);
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
 
     const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
     unsigned long long d_wait_s = 0, d_ld = 0, d_max = 0, d_exp = 0, d_wait_o = 0, d_st = 0, tA = 0, tB = 0;
-    for (int j = 0; j < n; ++j) {
+    for (int j = 0; j < (P.debug != 0 ? 0 : n); ++j) {
       const int slot = NQ == 2 ? g : (j & 1);
       const uint32_t sph = NQ == 2 ? (j & 1) : ((j >> 1) & 1);
       if (dbg) tA = clk();
@@ -402,10 +409,10 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
     }
 
     // ---------------- epilogue: O / l -> bf16 -> (optional) fp8 ----------------
-    mbar_wait(&o_done[g], (n - 1) & 1);
+    if (P.debug == 0) mbar_wait(&o_done[g], (n - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l;
-    const bool valid = qrow < a.S;
+    const bool valid = qrow < a.S && P.debug == 0;
     const bool second = a.out1 != nullptr && qrow >= a.split_row;
     void* const outp = second ? a.out1 : a.out;
     const int64_t obase = second ? static_cast<int64_t>(b) * a.out1_batch_stride +

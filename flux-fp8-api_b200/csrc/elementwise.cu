@@ -145,6 +145,13 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
   for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
   const float rstd = rsqrtf(var / D + eps);
   const float s = in_scale ? __ldg(in_scale) : 1.f;
+  // bf16-in / bf16-out products and sums are done with packed HMUL2/HADD2.BF16: for bf16 operands they round the
+  // exact result once, which equals the reference's fp32 op followed by a bf16 rounding (the fp32 intermediate is
+  // exact, or differs from the exact value far below half a bf16 ulp).  The quantising multiply can go packed only
+  // when the scale itself is a bf16 value (always true under the CUDA scale semantics).
+  const bool s_is_bf16 = bf16r(s) == s;
+  const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.f, 1.f);
+  const __nv_bfloat162 s2 = __floats2bfloat162_rn(s, s);
   const uint4* shp = reinterpret_cast<const uint4*>(shift + static_cast<int64_t>(b) * mod_stride);
   const uint4* scp = reinterpret_cast<const uint4*>(scale + static_cast<int64_t>(b) * mod_stride);
 #pragma unroll
@@ -152,36 +159,37 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
     if (i < ni) {
       uint4 sh = __ldg(shp + i * 32 + lane);
       uint4 sc = __ldg(scp + i * 32 + lane);
-      uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-      uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w};
-      uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
-      float m[8];
+      const uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+      const uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w};
+      const uint32_t scw[4] = {sc.x, sc.y, sc.z, sc.w};
+      uint32_t mb[4];   // modulated values as bf16 pairs
+      float q[8];       // quantiser inputs (pre-clamp)
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float2 f = unpack_bf16x2(w[t]);
-        float2 fs = unpack_bf16x2(shw[t]);
-        float2 fc = unpack_bf16x2(scw[t]);
-        float n0 = bf16r((f.x - mean) * rstd);
-        float n1 = bf16r((f.y - mean) * rstd);
+        const float2 f = unpack_bf16x2(w[t]);
+        const __nv_bfloat162 n2 = __floats2bfloat162_rn((f.x - mean) * rstd, (f.y - mean) * rstd);
+        const __nv_bfloat162 sc2 = *reinterpret_cast<const __nv_bfloat162*>(&scw[t]);
+        const __nv_bfloat162 sh2 = *reinterpret_cast<const __nv_bfloat162*>(&shw[t]);
         // (1 + scale) * ln + shift with eager bf16 rounding after each op
-        m[t * 2 + 0] = bf16r(bf16r(bf16r(1.f + fc.x) * n0) + fs.x);
-        m[t * 2 + 1] = bf16r(bf16r(bf16r(1.f + fc.y) * n1) + fs.y);
+        // (_rn forms: no contraction of the product and the sum into one HFMA2 -- each op rounds, as eager torch does)
+        const __nv_bfloat162 m2 = __hadd2_rn(__hmul2_rn(__hadd2_rn(one2, sc2), n2), sh2);
+        mb[t] = *reinterpret_cast<const uint32_t*>(&m2);
+        if (s_is_bf16) {
+          const __nv_bfloat162 p2 = __hmul2_rn(m2, s2);
+          const float2 pf = __bfloat1622float2(p2);
+          q[t * 2] = pf.x, q[t * 2 + 1] = pf.y;
+        } else {
+          const float2 mf = __bfloat1622float2(m2);
+          q[t * 2] = bf16r(mf.x * s), q[t * 2 + 1] = bf16r(mf.y * s);
+        }
       }
       const int64_t col = static_cast<int64_t>(i * 32 + lane) * 8;
-      if (yb) {
-        uint4 o;
-        o.x = pack_bf16x2(m[0], m[1]);
-        o.y = pack_bf16x2(m[2], m[3]);
-        o.z = pack_bf16x2(m[4], m[5]);
-        o.w = pack_bf16x2(m[6], m[7]);
-        *reinterpret_cast<uint4*>(yb + static_cast<int64_t>(row) * ldyb + col) = o;
-      }
+      if (yb) *reinterpret_cast<uint4*>(yb + static_cast<int64_t>(row) * ldyb + col) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
       if (yq) {
+        // clamp(+-max) then cast == saturating cast
         uint2 o;
-        o.x = to_fp8x2<FMT>(quant_pre<FMT>(m[0], s), quant_pre<FMT>(m[1], s)) |
-              (static_cast<uint32_t>(to_fp8x2<FMT>(quant_pre<FMT>(m[2], s), quant_pre<FMT>(m[3], s))) << 16);
-        o.y = to_fp8x2<FMT>(quant_pre<FMT>(m[4], s), quant_pre<FMT>(m[5], s)) |
-              (static_cast<uint32_t>(to_fp8x2<FMT>(quant_pre<FMT>(m[6], s), quant_pre<FMT>(m[7], s))) << 16);
+        o.x = to_fp8x2<FMT>(q[0], q[1]) | (static_cast<uint32_t>(to_fp8x2<FMT>(q[2], q[3])) << 16);
+        o.y = to_fp8x2<FMT>(q[4], q[5]) | (static_cast<uint32_t>(to_fp8x2<FMT>(q[6], q[7])) << 16);
         *reinterpret_cast<uint2*>(yq + static_cast<int64_t>(row) * ldy + col) = o;
       }
     }

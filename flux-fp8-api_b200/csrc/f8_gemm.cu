@@ -41,19 +41,38 @@ struct GemmSmem {
   static constexpr int kBarOff = kStages * kStage;
   // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr, norm weights (2*128 fp32)
   static constexpr int kNormOff = kBarOff + 256;
-  static constexpr int kTotal = kNormOff + 2 * kHeadDim * 4 + 1024 /*alignment slack*/;
+  static constexpr int kTotal = kNormOff + 2 * 2 * kHeadDim * 4 + 1024 /*alignment slack*/;
 };
 
+// Up to two problems that share N, K, formats and epilogue (the txt and img streams of a DoubleStreamBlock) run
+// as one persistent launch: tiles [0, tiles0) belong to problem 0, the rest to problem 1.
 struct GemmParams {
-  CUtensorMap tmap_a;
-  CUtensorMap tmap_w;
-  fluxb200_gemm_args g;
-  int num_m_tiles, num_n_tiles, num_k_blocks;
+  CUtensorMap tmap_a[2];
+  CUtensorMap tmap_w[2];
+  fluxb200_gemm_args g[2];
+  int num_m_tiles[2];
+  int tiles0, num_tiles;
+  int num_n_tiles, num_k_blocks;
   uint32_t idesc;
   // Timing experiments only (env FLUXB200_GEMM_DEBUG; results are garbage): 1 = no TMA traffic after the ring is
   // first filled (pure MMA issue rate), 2 = no MMAs (pure TMA pipeline rate).
   int debug;
 };
+
+struct TileCoord {
+  int pi;     // problem index
+  int m_blk;  // tile row (in units of the M tile of the launch)
+  int n_blk;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) {
+  TileCoord c;
+  c.pi = tile >= P.tiles0 ? 1 : 0;
+  const int local = tile - (c.pi ? P.tiles0 : 0);
+  const int nm = P.num_m_tiles[c.pi];
+  c.m_blk = local % nm;
+  c.n_blk = local / nm;
+  return c;
+}
 
 struct RowInfo {
   int row;    // global row
@@ -115,8 +134,7 @@ __device__ __forceinline__ void store_fp8x32(uint8_t* dst, const float (&p)[32])
   }
 }
 
-__device__ __forceinline__ void epi_plain(const GemmParams& P, const RowInfo& ri, int col, const float (&y)[32]) {
-  const fluxb200_gemm_args& g = P.g;
+__device__ __forceinline__ void epi_plain(const fluxb200_gemm_args& g, const RowInfo& ri, int col, const float (&y)[32]) {
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col;
   if (col + 32 <= g.N) {
     store_bf16x32(dst, y);
@@ -127,9 +145,8 @@ __device__ __forceinline__ void epi_plain(const GemmParams& P, const RowInfo& ri
   }
 }
 
-__device__ __forceinline__ void epi_gate_residual(const GemmParams& P, const RowInfo& ri, int col,
+__device__ __forceinline__ void epi_gate_residual(const fluxb200_gemm_args& g, const RowInfo& ri, int col,
                                                   float (&y)[32]) {
-  const fluxb200_gemm_args& g = P.g;
   const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.gate) +
                                                    static_cast<int64_t>(ri.b) * g.gate_batch_stride + col);
   const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.resid) +
@@ -152,9 +169,8 @@ __device__ __forceinline__ void epi_gate_residual(const GemmParams& P, const Row
   store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, y);
 }
 
-__device__ __forceinline__ void epi_gelu_quant(const GemmParams& P, const RowInfo& ri, int out_col, float oscale,
+__device__ __forceinline__ void epi_gelu_quant(const fluxb200_gemm_args& g, const RowInfo& ri, int out_col, float oscale,
                                                float (&y)[32]) {
-  const fluxb200_gemm_args& g = P.g;
   uint8_t* dst = reinterpret_cast<uint8_t*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + out_col;
   if (g.out_fmt == FLUXB200_E5M2) {
 #pragma unroll
@@ -169,9 +185,8 @@ __device__ __forceinline__ void epi_gelu_quant(const GemmParams& P, const RowInf
 
 // One thread owns one (row, head): 128 accumulator columns starting at TMEM address `taddr`.
 // which: 0 = q, 1 = k (RMSNorm + RoPE), 2 = v (copy).
-__device__ __forceinline__ void epi_qkv_head(const GemmParams& P, const RowInfo& ri, uint32_t taddr, int col0,
+__device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const RowInfo& ri, uint32_t taddr, int col0,
                                              float s, const float* norm_smem) {
-  const fluxb200_gemm_args& g = P.g;
   const int hd = g.num_heads * kHeadDim;
   const int which = col0 / hd;
   const int head = (col0 - which * hd) / kHeadDim;
@@ -256,15 +271,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const fluxb200_gemm_args& g = P.g;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;  // 0 = leader of the pair
   const int tile0 = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
   const int tile_stride = CG == 2 ? gridDim.x >> 1 : gridDim.x;
   constexpr int kTileM = kBM * CG;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&P.tmap_a);
-    tma_prefetch_desc(&P.tmap_w);
+    tma_prefetch_desc(&P.tmap_a[0]);
+    tma_prefetch_desc(&P.tmap_w[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S::kStages; ++i) {
@@ -288,9 +302,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   }
   if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
     // (norm weights are parameters, never written by a preceding kernel: safe before griddepcontrol.wait)
-    if (threadIdx.x < 2 * kHeadDim)
-      norm_smem[threadIdx.x] =
-          threadIdx.x < kHeadDim ? g.q_norm_w[threadIdx.x] : g.k_norm_w[threadIdx.x - kHeadDim];
+    for (int i = threadIdx.x; i < 4 * kHeadDim; i += kGemmThreads) {
+      const fluxb200_gemm_args& gp = P.g[(i >= 2 * kHeadDim && P.tiles0 < P.num_tiles) ? 1 : 0];
+      const int k = i & (2 * kHeadDim - 1);
+      norm_smem[i] = k < kHeadDim ? gp.q_norm_w[k] : gp.k_norm_w[k - kHeadDim];
+    }
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -301,7 +317,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   pdl_wait();
   pdl_launch_dependents();
 
-  const int num_tiles = P.num_m_tiles * P.num_n_tiles;
+  const int num_tiles = P.num_tiles;
 
   // Producer and issuer run their loops warp-uniformly; only the TMA / MMA / commit instructions are predicated on
   // one elected lane, so descriptors and addresses stay in uniform registers (a `lane == 0` loop makes ptxas wrap
@@ -311,8 +327,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-      const int m0 = (tile % P.num_m_tiles) * kTileM + cta_rank * kBM;
-      const int n0 = (tile / P.num_m_tiles) * BN + cta_rank * S::kBRows;
+      const TileCoord tc = decode_tile(P, tile);
+      const int m0 = tc.m_blk * kTileM + cta_rank * kBM;
+      const int n0 = tc.n_blk * BN + cta_rank * S::kBRows;
+      const CUtensorMap* tm_a = &P.tmap_a[tc.pi];
+      const CUtensorMap* tm_w = &P.tmap_w[tc.pi];
       for (int kb = 0; kb < P.num_k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStage;
@@ -322,12 +341,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
           } else if constexpr (CG == 2) {
             // all bytes of the pair are accounted on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStage);
-            tma_load_2d_2sm(sa, &P.tmap_a, &full_bar[stage], kb * kBK, m0);
-            tma_load_2d_2sm(sa + S::kA, &P.tmap_w, &full_bar[stage], kb * kBK, n0);
+            tma_load_2d_2sm(sa, tm_a, &full_bar[stage], kb * kBK, m0);
+            tma_load_2d_2sm(sa + S::kA, tm_w, &full_bar[stage], kb * kBK, n0);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], S::kStage);
-            tma_load_2d(sa, &P.tmap_a, &full_bar[stage], kb * kBK, m0);
-            tma_load_2d(sa + S::kA, &P.tmap_w, &full_bar[stage], kb * kBK, n0);
+            tma_load_2d(sa, tm_a, &full_bar[stage], kb * kBK, m0);
+            tma_load_2d(sa + S::kA, tm_w, &full_bar[stage], kb * kBK, n0);
           }
         }
         __syncwarp();
@@ -386,15 +405,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
     const int lg = warp & 3;                 // TMEM lane group of this warp
     const int half = (warp - kEpiWarp0) >> 2;  // which half of the BN columns
     constexpr int kHalfCols = BN / 2;
-    const float s = __ldg(g.a_scale_recip) * __ldg(g.w_scale_recip);
-    float oscale = 0.f;
-    if constexpr (EPI == FLUXB200_EPI_GELU_QUANT || EPI == FLUXB200_EPI_LINEAR1) oscale = __ldg(g.out_scale);
-    const int rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-      const int m0 = (tile % P.num_m_tiles) * kTileM + cta_rank * kBM;
-      const int n0 = (tile / P.num_m_tiles) * BN;
+      const TileCoord tc = decode_tile(P, tile);
+      const fluxb200_gemm_args& g = P.g[tc.pi];
+      const float s = __ldg(g.a_scale_recip) * __ldg(g.w_scale_recip);
+      float oscale = 0.f;
+      if constexpr (EPI == FLUXB200_EPI_GELU_QUANT || EPI == FLUXB200_EPI_LINEAR1) oscale = __ldg(g.out_scale);
+      const int rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
+      const int m0 = tc.m_blk * kTileM + cta_rank * kBM;
+      const int n0 = tc.n_blk * BN;
       RowInfo ri;
       ri.row = m0 + lg * 32 + lane;
       ri.valid = ri.row < g.M;
@@ -411,7 +432,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
         if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
           static_assert(kHalfCols == kHeadDim || (EPI != FLUXB200_EPI_QKV_ROPE && EPI != FLUXB200_EPI_LINEAR1),
                         "QKV epilogues need BN == 256");
-          epi_qkv_head(P, ri, taddr, col0, s, norm_smem);
+          epi_qkv_head(g, ri, taddr, col0, s, norm_smem + tc.pi * 2 * kHeadDim);
         }
       } else {
         const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
@@ -432,13 +453,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
           }
           if (!ri.valid) continue;
           if constexpr (EPI == FLUXB200_EPI_PLAIN) {
-            epi_plain(P, ri, col, y);
+            epi_plain(g, ri, col, y);
           } else if constexpr (EPI == FLUXB200_EPI_GATE_RESIDUAL) {
-            epi_gate_residual(P, ri, col, y);
+            epi_gate_residual(g, ri, col, y);
           } else if constexpr (EPI == FLUXB200_EPI_GELU_QUANT) {
-            epi_gelu_quant(P, ri, g.out_col_offset + col, oscale, y);
+            epi_gelu_quant(g, ri, g.out_col_offset + col, oscale, y);
           } else if constexpr (EPI == FLUXB200_EPI_LINEAR1) {
-            epi_gelu_quant(P, ri, g.out_col_offset + col - 3 * g.num_heads * kHeadDim, oscale, y);
+            epi_gelu_quant(g, ri, g.out_col_offset + col - 3 * g.num_heads * kHeadDim, oscale, y);
           }
         }
       }
@@ -473,7 +494,7 @@ static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
-  const int tiles = P.num_m_tiles * P.num_n_tiles;
+  const int tiles = P.num_tiles;
   const int units = sm_count() / CG;  // CTAs (CG == 1) or CTA pairs (CG == 2) that fit on the device
   const int grid = (tiles < units ? tiles : units) * CG;
   FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, CG, P));
@@ -482,21 +503,16 @@ static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
 
 }  // namespace fb
 
-extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_t stream_) {
-  using namespace fb;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  FB_REQUIRE(args != nullptr, "fluxb200_f8_gemm: args is NULL");
-  const fluxb200_gemm_args& g = *args;
+namespace fb {
+
+static int validate_gemm(const fluxb200_gemm_args& g) {
   FB_REQUIRE(g.a && g.w && g.a_scale_recip && g.w_scale_recip, "fluxb200_f8_gemm: null operand");
   FB_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "fluxb200_f8_gemm: bad shape M=%d N=%d K=%d", g.M, g.N, g.K);
   FB_REQUIRE(g.K % 16 == 0, "fluxb200_f8_gemm: K=%d must be a multiple of 16", g.K);
   FB_REQUIRE((g.a_fmt == 0 || g.a_fmt == 1) && (g.w_fmt == 0 || g.w_fmt == 1), "fluxb200_f8_gemm: bad fp8 format");
   FB_REQUIRE(g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0,
              "fluxb200_f8_gemm: bias must be 16-byte aligned");
-
   const int epi = g.epilogue;
-  const bool qkv = epi == FLUXB200_EPI_QKV_ROPE || epi == FLUXB200_EPI_LINEAR1;
-  int bn = 256;
   switch (epi) {
     case FLUXB200_EPI_PLAIN:
       FB_REQUIRE(g.out && g.ldo >= g.N && g.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15) == 0,
@@ -518,28 +534,48 @@ extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_
       FB_REQUIRE(g.N > 3 * g.num_heads * kHeadDim && (g.N - 3 * g.num_heads * kHeadDim) % 128 == 0,
                  "fluxb200_f8_gemm(LINEAR1): N must be 3*H*128 + k*128");
       // fallthrough
-    case FLUXB200_EPI_QKV_ROPE:
+    case FLUXB200_EPI_QKV_ROPE: {
       FB_REQUIRE(g.q && g.k && g.v && g.q_norm_w && g.k_norm_w && g.rope_cos && g.rope_sin,
                  "fluxb200_f8_gemm(QKV): null operand");
       FB_REQUIRE(g.num_heads > 0 && (epi == FLUXB200_EPI_LINEAR1 || g.N == 3 * g.num_heads * kHeadDim),
                  "fluxb200_f8_gemm(QKV_ROPE): N must equal 3*H*128");
       FB_REQUIRE(g.seq_total > 0 && g.seq_offset >= 0, "fluxb200_f8_gemm(QKV): bad sequence geometry");
-      {
-        const int rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
-        FB_REQUIRE(g.seq_offset + rpb <= g.seq_total, "fluxb200_f8_gemm(QKV): seq_offset+rows_per_batch > seq_total");
-        FB_REQUIRE(g.M % rpb == 0, "fluxb200_f8_gemm(QKV): M must be a multiple of rows_per_batch");
-      }
+      const int rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
+      FB_REQUIRE(g.seq_offset + rpb <= g.seq_total, "fluxb200_f8_gemm(QKV): seq_offset+rows_per_batch > seq_total");
+      FB_REQUIRE(g.M % rpb == 0, "fluxb200_f8_gemm(QKV): M must be a multiple of rows_per_batch");
       break;
+    }
     default:
       return set_error(FLUXB200_ERR_INVALID, "fluxb200_f8_gemm: unknown epilogue %d", epi);
   }
-  if (!qkv && (g.N <= 128 || (g.N % 256 != 0 && g.N % 128 == 0) ||
-               (static_cast<int64_t>((g.M + 127) / 128) * ((g.N + 255) / 256) < sm_count() / 2)))
-    bn = 128;
+  return 0;
+}
+
+static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_t stream) {
+  FB_REQUIRE(args != nullptr && (count == 1 || count == 2), "fluxb200_f8_gemm: args NULL or count not in {1,2}");
+  for (int i = 0; i < count; ++i) {
+    int rc = validate_gemm(args[i]);
+    if (rc) return rc;
+  }
+  const fluxb200_gemm_args& g = args[0];
+  if (count == 2) {
+    const fluxb200_gemm_args& h = args[1];
+    FB_REQUIRE(h.N == g.N && h.K == g.K && h.epilogue == g.epilogue && h.a_fmt == g.a_fmt && h.w_fmt == g.w_fmt &&
+                   h.num_heads == g.num_heads && h.out_fmt == g.out_fmt,
+               "fluxb200_f8_gemm_grouped: problems must share N, K, formats and epilogue");
+  }
+  const int epi = g.epilogue;
+  const bool qkv = epi == FLUXB200_EPI_QKV_ROPE || epi == FLUXB200_EPI_LINEAR1;
+  int64_t tiles128 = 0, tiles256 = 0;
+  for (int i = 0; i < count; ++i) {
+    tiles128 += static_cast<int64_t>((args[i].M + 127) / 128) * ((g.N + 255) / 256);
+    tiles256 += static_cast<int64_t>((args[i].M + 255) / 256) * ((g.N + 255) / 256);
+  }
+  int bn = 256;
+  if (!qkv && (g.N <= 128 || (g.N % 256 != 0 && g.N % 128 == 0) || tiles128 < sm_count() / 2)) bn = 128;
   // 2-CTA tiling (256 x 256 per SM pair) when it fills most of the machine; FLUXB200_GEMM_CG=1|2 forces a form.
   int cg = 1;
-  const int64_t tiles2 = static_cast<int64_t>((g.M + 255) / 256) * ((g.N + 255) / 256);
-  if (bn == 256 && g.N >= 256 && tiles2 >= (sm_count() / 2) * 3 / 4) cg = 2;
+  if (bn == 256 && g.N >= 256 && tiles256 >= (sm_count() / 2) * 3 / 4) cg = 2;
   static const int forced_cg = [] {
     const char* e = getenv("FLUXB200_GEMM_CG");
     return e ? atoi(e) : 0;
@@ -548,21 +584,34 @@ extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_
   if (forced_cg == 2 && g.N >= 256 && (qkv || g.N % 256 == 0 || epi == FLUXB200_EPI_PLAIN)) { cg = 2; bn = 256; }
 
   GemmParams P;
-  P.g = g;
   static const int dbg = [] {
     const char* e = getenv("FLUXB200_GEMM_DEBUG");
     return e ? atoi(e) : 0;
   }();
   P.debug = dbg;
-  P.num_m_tiles = (g.M + kBM * cg - 1) / (kBM * cg);
   P.num_n_tiles = (g.N + bn - 1) / bn;
   P.num_k_blocks = (g.K + kBK - 1) / kBK;
   P.idesc = make_idesc(g.a_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3, g.w_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3,
                        kBM * cg, bn);
-  int rc = make_tmap_2d(&P.tmap_a, g.a, 1, g.M, g.K, g.K, kBM, kBK);
-  if (rc) return rc;
-  rc = make_tmap_2d(&P.tmap_w, g.w, 1, g.N, g.K, g.K, bn / cg, kBK);
-  if (rc) return rc;
+  P.tiles0 = 0;
+  P.num_tiles = 0;
+  for (int i = 0; i < 2; ++i) {
+    const fluxb200_gemm_args& gi = args[i < count ? i : 0];
+    P.g[i] = gi;
+    P.num_m_tiles[i] = (gi.M + kBM * cg - 1) / (kBM * cg);
+    if (i < count) {
+      int rc = make_tmap_2d(&P.tmap_a[i], gi.a, 1, gi.M, gi.K, gi.K, kBM, kBK);
+      if (rc) return rc;
+      rc = make_tmap_2d(&P.tmap_w[i], gi.w, 1, gi.N, gi.K, gi.K, bn / cg, kBK);
+      if (rc) return rc;
+      const int t = P.num_m_tiles[i] * P.num_n_tiles;
+      if (i == 0) P.tiles0 = t;
+      P.num_tiles += t;
+    } else {
+      P.tmap_a[i] = P.tmap_a[0];
+      P.tmap_w[i] = P.tmap_w[0];
+    }
+  }
 
 #define FB_LAUNCH(BN_, EPI_) return launch_gemm<BN_, EPI_, 1>(P, stream)
 #define FB_LAUNCH2(EPI_) return launch_gemm<256, EPI_, 2>(P, stream)
@@ -592,4 +641,14 @@ extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_
 #undef FB_LAUNCH
 #undef FB_LAUNCH2
   return set_error(FLUXB200_ERR_INVALID, "fluxb200_f8_gemm: no kernel for epilogue %d / BN %d", epi, bn);
+}
+
+}  // namespace fb
+
+extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_t stream_) {
+  return fb::run_gemm_group(args, 1, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int fluxb200_f8_gemm_grouped(const fluxb200_gemm_args* args, int count, fluxb200_stream_t stream_) {
+  return fb::run_gemm_group(args, count, reinterpret_cast<cudaStream_t>(stream_));
 }

@@ -16,6 +16,11 @@ from . import _cabi as cabi
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
 
+#: when set to a list, the GEMM / attention / LayerNorm wrappers append (kind, work, start_event, end_event) per launch
+#: (work = flops, or bytes for the HBM-bound kernels): CUDA-event timing of individual kernels on the launching
+#: stream (bench.py's roofline pass)
+KERNEL_TIMELINE = None
+
 
 def _contig(t: Tensor, what: str) -> Tensor:
     if not t.is_contiguous():
@@ -86,10 +91,12 @@ def ln_mod_quant(x: Tensor, shift: Tensor, scale: Tensor, in_scale: Optional[Ten
     if yq is None and dtype is not None:
         yq = torch.empty((B, L, D), dtype=dtype, device=x.device)
     yb = torch.empty((B, L, D), dtype=BF16, device=x.device) if want_bf16 else None
-    cabi.check(cabi.load().fluxb200_ln_mod_quant(
-        x.data_ptr(), x.stride(1), sh.data_ptr(), sc.data_ptr(), sh.stride(0) if B > 1 else D,
-        cabi.ptr(yq), yq.stride(-2) if yq is not None else 0, cabi.ptr(yb), D, cabi.ptr(in_scale),
-        cabi.fp8_fmt(dtype) if dtype is not None else 0, B, L, D, eps, cabi.stream_ptr()), "fluxb200_ln_mod_quant")
+    _timed("ln_mod_quant", B * L * D * (2.0 + (1.0 if yq is not None else 0.0) + (2.0 if yb is not None else 0.0)),
+           lambda: cabi.check(cabi.load().fluxb200_ln_mod_quant(
+               x.data_ptr(), x.stride(1), sh.data_ptr(), sc.data_ptr(), sh.stride(0) if B > 1 else D,
+               cabi.ptr(yq), yq.stride(-2) if yq is not None else 0, cabi.ptr(yb), D, cabi.ptr(in_scale),
+               cabi.fp8_fmt(dtype) if dtype is not None else 0, B, L, D, eps, cabi.stream_ptr()),
+               "fluxb200_ln_mod_quant"))
     return yq, yb
 
 
@@ -135,12 +142,9 @@ def gemm_args(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tenso
     g.N = w.shape[0]
     g.a_fmt, g.w_fmt = cabi.fp8_fmt(a.dtype), cabi.fp8_fmt(w.dtype)
     g.epilogue = epilogue
+    # deferred (grouped) launches only hold raw pointers: keep the operands alive until the launch has been enqueued
+    g._keep = [a, w, bias, a_scale_recip, w_scale_recip]
     return g
-
-
-#: when set to a list, run_gemm / attention append (kind, flops, start_event, end_event) per launch: CUDA-event
-#: timing of individual kernels on the launching stream (bench.py's roofline pass)
-KERNEL_TIMELINE = None
 
 
 def _timed(kind: str, flops: float, launch) -> None:
@@ -159,6 +163,17 @@ def run_gemm(g: cabi.GemmArgs) -> None:
            lambda: cabi.check(cabi.load().fluxb200_f8_gemm(C.byref(g), cabi.stream_ptr()), "fluxb200_f8_gemm"))
 
 
+def run_gemm_group(gs) -> None:
+    """One persistent launch for up to two GEMM problems sharing N, K, formats and epilogue."""
+    gs = list(gs)
+    if len(gs) == 1:
+        return run_gemm(gs[0])
+    arr = (cabi.GemmArgs * len(gs))(*gs)
+    _timed("f8_gemm", sum(2.0 * g.M * g.N * g.K for g in gs),
+           lambda: cabi.check(cabi.load().fluxb200_f8_gemm_grouped(arr, len(gs), cabi.stream_ptr()),
+                              "fluxb200_f8_gemm_grouped"))
+
+
 def f8_gemm(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tensor, w_scale_recip: Tensor,
             out: Optional[Tensor] = None) -> Tensor:
     """bf16( (A.W^T) * sa * sw + bias ): the torch._scaled_mm call of F8Linear.forward."""
@@ -173,8 +188,9 @@ def f8_gemm(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tensor,
 
 
 def f8_gemm_gate_residual(a, w, bias, sa, sw, resid: Tensor, gate: Tensor, rows_per_batch: int,
-                          out: Optional[Tensor] = None) -> Tensor:
-    """out = resid + gate[b] * linear(a)   (resid [M,N] bf16 view, gate [B,N] view)."""
+                          out: Optional[Tensor] = None, defer: Optional[list] = None) -> Tensor:
+    """out = resid + gate[b] * linear(a)   (resid [M,N] bf16 view, gate [B,N] view).  With `defer` (a list) the
+    launch arguments are appended to it instead of being launched (see run_gemm_group)."""
     g = gemm_args(a, w, bias, sa, sw, cabi.EPI_GATE_RESIDUAL)
     if out is None:
         out = torch.empty((g.M, g.N), dtype=BF16, device=a.device)
@@ -182,25 +198,33 @@ def f8_gemm_gate_residual(a, w, bias, sa, sw, resid: Tensor, gate: Tensor, rows_
     g.resid, g.ldr = resid.data_ptr(), resid.stride(0)
     g.gate, g.gate_batch_stride = gate.data_ptr(), gate.stride(0)
     g.rows_per_batch = rows_per_batch
-    run_gemm(g)
+    g._keep += [out, resid, gate]
+    if defer is not None:
+        defer.append(g)
+    else:
+        run_gemm(g)
     return out
 
 
 def f8_gemm_gelu_quant(a, w, bias, sa, sw, out_scale: Tensor, out_dtype: torch.dtype, out: Optional[Tensor] = None,
-                       out_col_offset: int = 0) -> Tensor:
+                       out_col_offset: int = 0, defer: Optional[list] = None) -> Tensor:
     g = gemm_args(a, w, bias, sa, sw, cabi.EPI_GELU_QUANT)
     if out is None:
         out = torch.empty((g.M, g.N), dtype=out_dtype, device=a.device)
     g.out, g.ldo = out.data_ptr(), out.stride(0)
     g.out_scale, g.out_fmt, g.out_col_offset = out_scale.data_ptr(), cabi.fp8_fmt(out_dtype), out_col_offset
-    run_gemm(g)
+    g._keep += [out, out_scale]
+    if defer is not None:
+        defer.append(g)
+    else:
+        run_gemm(g)
     return out
 
 
 def f8_gemm_qkv_rope(a, w, bias, sa, sw, q: Tensor, k: Tensor, v: Tensor, q_norm_w: Tensor, k_norm_w: Tensor,
                      cos: Tensor, sin: Tensor, rows_per_batch: int, seq_offset: int,
                      mlp_out: Optional[Tensor] = None, mlp_scale: Optional[Tensor] = None,
-                     mlp_col_offset: int = 0) -> None:
+                     mlp_col_offset: int = 0, defer: Optional[list] = None) -> None:
     """QKV (or SingleStreamBlock.linear1 when mlp_out is given) GEMM writing normalised+rotated q,k and v
     straight into the joint [B,H,S,128] buffers."""
     epi = cabi.EPI_LINEAR1 if mlp_out is not None else cabi.EPI_QKV_ROPE
@@ -215,7 +239,11 @@ def f8_gemm_qkv_rope(a, w, bias, sa, sw, q: Tensor, k: Tensor, v: Tensor, q_norm
     if mlp_out is not None:
         g.out, g.ldo = mlp_out.data_ptr(), mlp_out.stride(0)
         g.out_scale, g.out_fmt, g.out_col_offset = mlp_scale.data_ptr(), cabi.fp8_fmt(mlp_out.dtype), mlp_col_offset
-    run_gemm(g)
+    g._keep += [q, k, v, q_norm_w, k_norm_w, cos, sin, mlp_out, mlp_scale]
+    if defer is not None:
+        defer.append(g)
+    else:
+        run_gemm(g)
 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, out: Optional[Tensor] = None, out_scale0: Optional[Tensor] = None,

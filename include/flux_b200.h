@@ -116,6 +116,11 @@ typedef struct fluxb200_gemm_args {
 
 int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_t stream);
 
+/* `count` (1 or 2) problems that share N, K, fp8 formats and epilogue in ONE persistent launch: the txt and img
+ * streams of a DoubleStreamBlock apply different weights to different row counts (modules/flux_model.py:369/376,
+ * 387/393, 388-396), and the txt problem alone (M = 512) cannot fill 148 SMs. */
+int fluxb200_f8_gemm_grouped(const fluxb200_gemm_args* args, int count, fluxb200_stream_t stream);
+
 /* Skinny-M variant for Modulation.lin / MLPEmbedder (M = batch <= 16): weight-streaming GEMV.
  *   out[m, n] = bf16( (sum_k A[m,k]*W[n,k]) * sa * sw + bias[n] )   modules/flux_model.py:252 */
 int fluxb200_f8_gemv(const void* a_fp8, int a_fmt, const void* w_fp8, int w_fmt, const void* bias_bf16,
