@@ -369,8 +369,6 @@ class DoubleStreamBlock(nn.Module):
             ops.run_gemm(a)
             ops.run_gemm(b)
 
-        return outs[0], outs[1]
-
     def _forward_eager(self, img, txt, pe, mods):
         (img_mod1, img_mod2), (txt_mod1, txt_mod2) = mods
 

@@ -69,6 +69,17 @@ __device__ __forceinline__ float fast_exp2_pinned(float x) {
   return y;
 }
 
+// exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest range reduction x = n + f, f in [-0.5, 0.5], cubic minimax
+// 2^f (max relative error 1.0e-4, a twentieth of a bf16 ulp of P), exponent patched in with an integer add.
+// Used for a quarter of the elements so the MUFU-bound exp phase shortens (the trick FlashAttention-4 uses).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float r = x + 12582912.f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (r - 12582912.f);
+  const float p = fmaf(fmaf(fmaf(0.05500892f, f, 0.24221096f), f, 0.69328293f), f, 1.f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
 template <int REGS>
 __device__ __forceinline__ void reg_inc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
@@ -78,7 +89,7 @@ __device__ __forceinline__ void reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
 }
 
-template <int NQ, bool TS>
+template <int NQ, bool TS, bool FAST = false>
 __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams P) {
   using C = AttnCfg<NQ, TS>;
   constexpr int KS = C::kStages;
@@ -195,10 +206,11 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
 #pragma unroll
           for (int kk = 0; kk < kD / 16; ++kk) {
             const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
-            if (P.debug == 3)  // timing experiment: A operand (Q) from TMEM instead of shared memory
-              mma_f16_ts(d, tmem_base + 256 + g * 128 + kk * 8, desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
-            else
-              mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+#ifdef FLUXB200_ATTN_EXPERIMENT_TS_QK  // timing experiment only: A operand (Q) from TMEM instead of shared memory
+            mma_f16_ts(d, tmem_base + 256 + g * 128 + kk * 8, desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+#else
+            mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+#endif
           }
         }
         __syncwarp();
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
           const int st = j % KS;
           mbar_wait(&v_full[st], (j / KS) & 1);
           for (int g = 0; g < 2; ++g) {
-            if (P.debug == 0) mbar_wait(&p_ready[g], j & 1);
+            if (P.debug != 1) mbar_wait(&p_ready[g], j & 1);
             tc_fence_after();
             issue_pv(g, g, st, j == 0);
             commit(&o_done[g]);
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
             }
           }
         }
-        if (P.debug != 0) {  // drain the tensor pipe before teardown
+        if (P.debug == 1) {  // drain the tensor pipe before teardown
           commit(q_full);
           mbar_wait(q_full, 1);
         }
@@ -294,13 +306,17 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
     // Ping-pong token between the two softmax warpgroups (named barriers 1 and 2): only one of them is in its
     // MUFU-bound exp phase at a time, so while one exponentiates the tensor pipe works on the other's tiles.
     // Without it both run in lock-step and the exp phases and the MMAs serialise (profiles/r1_attention.md).
-    if constexpr (NQ == 2) {
+    if (NQ == 2 && P.debug != 4) {
       if (g == 1) named_bar_arrive(1, 256);  // hand the first turn to warpgroup 0
     }
 
+#ifdef FLUXB200_ATTN_PROBE
     const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+#else
+    constexpr bool dbg = false;  // phase timers compiled out (build with -DFLUXB200_ATTN_PROBE to enable)
+#endif
     unsigned long long d_wait_s = 0, d_ld = 0, d_max = 0, d_exp = 0, d_wait_o = 0, d_st = 0, tA = 0, tB = 0;
-    for (int j = 0; j < (P.debug != 0 ? 0 : n); ++j) {
+    for (int j = 0; j < (P.debug == 1 ? 0 : n); ++j) {
       const int slot = NQ == 2 ? g : (j & 1);
       const uint32_t sph = NQ == 2 ? (j & 1) : ((j >> 1) & 1);
       if (dbg) tA = clk();
@@ -323,9 +339,23 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
         for (int i = 0; i < 128; ++i)
           if (i >= kv_left) sv[i] = __float_as_uint(-INFINITY);
       }
-      float mx = __uint_as_float(sv[0]);
+      float mx;
+      if constexpr (FAST) {  // four independent chains instead of one 128-deep dependency chain
+        float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]);
+        float m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
 #pragma unroll
-      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 4; i < 128; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(sv[i]));
+          m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(sv[i + 2]));
+          m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {
+        mx = __uint_as_float(sv[0]);
+#pragma unroll
+        for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      }
       const float m_cand = mx * sl2;
       // Lazy rescale: keep the stale max unless it is more than 2^8 below the new one.
       const bool grow = m_cand > m_used + kRescaleThreshold;
@@ -340,14 +370,31 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       float rs = 0.f;
       const float neg_m = -m_used;
       if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
-      if constexpr (NQ == 2) named_bar_sync(1 + g, 256);  // wait for our turn
+      if (NQ == 2 && P.debug != 4) named_bar_sync(1 + g, 256);  // wait for our turn
+      if constexpr (FAST && TS) {
+        // one pass: 3 of 4 exponentials on the MUFU, 1 of 4 on the FMA pipe; bf16 pairs packed in place
+        float rs1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 128; ++i) {
-        float p = fast_exp2_pinned(fmaf(__uint_as_float(sv[i]), sl2, neg_m));
-        rs += p;
-        sv[i] = __float_as_uint(p);
+        for (int i = 0; i < 128; i += 4) {
+          const float p0 = fast_exp2_pinned(fmaf(__uint_as_float(sv[i]), sl2, neg_m));
+          const float p1 = fast_exp2_pinned(fmaf(__uint_as_float(sv[i + 1]), sl2, neg_m));
+          const float p2 = fast_exp2_pinned(fmaf(__uint_as_float(sv[i + 2]), sl2, neg_m));
+          const float p3 = poly_exp2(fmaf(__uint_as_float(sv[i + 3]), sl2, neg_m));
+          rs += p0 + p1;
+          rs1 += p2 + p3;
+          sv[i >> 1] = pack_bf16x2(p0, p1);
+          sv[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
+        rs += rs1;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          float p = fast_exp2_pinned(fmaf(__uint_as_float(sv[i]), sl2, neg_m));
+          rs += p;
+          sv[i] = __float_as_uint(p);
+        }
       }
-      if constexpr (NQ == 2) named_bar_arrive(1 + (g ^ 1), 256);  // pass the turn
+      if (NQ == 2 && P.debug != 4) named_bar_arrive(1 + (g ^ 1), 256);  // pass the turn
       l += rs;
       if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
 
@@ -367,7 +414,12 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
           }
         }
       }
-      if constexpr (TS) {
+      if constexpr (FAST && TS) {
+        uint32_t(*pk)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);  // packed in the exp loop
+        tmem_st32(lane_base + slot * 128, pk[0]);
+        tmem_st32(lane_base + slot * 128 + 32, pk[1]);
+        tmem_st_wait();
+      } else if constexpr (TS) {
         // P (bf16 pairs) over the S slot: column c holds kv (2c, 2c+1) of this row
         uint32_t pk[32];
 #pragma unroll
@@ -409,10 +461,10 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
     }
 
     // ---------------- epilogue: O / l -> bf16 -> (optional) fp8 ----------------
-    if (P.debug == 0) mbar_wait(&o_done[g], (n - 1) & 1);
+    if (P.debug != 1) mbar_wait(&o_done[g], (n - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l;
-    const bool valid = qrow < a.S && P.debug == 0;
+    const bool valid = qrow < a.S && P.debug != 1;
     const bool second = a.out1 != nullptr && qrow >= a.split_row;
     void* const outp = second ? a.out1 : a.out;
     const int64_t obase = second ? static_cast<int64_t>(b) * a.out1_batch_stride +
@@ -1281,12 +1333,12 @@ static int launch_attention_events(const AttnParams& P, cudaStream_t stream) {
   return 0;
 }
 
-template <int NQ, bool TS>
+template <int NQ, bool TS, bool FAST = false>
 static int launch_attention(const AttnParams& P, cudaStream_t stream) {
   using C = AttnCfg<NQ, TS>;
   static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
   static bool attr_set = false;
-  auto kern = attention_kernel<NQ, TS>;
+  auto kern = attention_kernel<NQ, TS, FAST>;
   if (!attr_set) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     attr_set = true;
@@ -1337,7 +1389,8 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
   if ((rc = make_tmap_3d(&P.tmap_v, a.v, 2, kD, a.S, bhn, row_bytes, row_bytes * a.S, 64, kBKV, 1))) return rc;
 
   switch (a.variant) {
-    case 0:                                                // default = fastest measured (profiles/r1_attention_variants.md)
+    case 0: return launch_attention<2, true, true>(P, stream);  // default: variant 1 + tightened softmax (4-way max,
+                                                                // 1/4 of the exponentials on the FMA pipe, in-loop packing)
     case 1: return launch_attention<2, true>(P, stream);   // 2 query tiles, whole KV tiles, P through TMEM
     case 5: return launch_attention_halves(P, stream);     // 2 query tiles x 2 KV halves in flight, explicit PV->QK waits
     case 6: return launch_attention_events(P, stream);     // event-driven issuer + fused single-pass softmax

@@ -271,7 +271,7 @@ def attn_ref(q, k, v):
     return x.reshape(B, S, H * D)
 
 
-def group_attention(variants=(0, 2, 3, 4, 5, 6)):
+def group_attention(variants=(0, 1, 2, 3, 4, 5, 6)):
     from flux_fp8_api_b200 import ops
     from oracle import flux_oracle as O
     g = torch.Generator(device=DEV).manual_seed(4)

@@ -165,9 +165,9 @@ def test_epilogue_gelu_quant(ops, O, M, N, K):
     ref = O.quantize(ge, so, E5M2)
     assert torch.isfinite(out.float()).all()
     assert (out.float() != ref.float()).float().mean().item() < 0.002  # rare 1-ulp GELU / accumulation flips
-    # a flipped element moves by one e5m2 step (25 % of its magnitude at most)
-    d = (out.float() - ref.float()).abs()
-    assert (d <= 0.26 * ref.float().abs() + 1e-6).all()
+    # a flipped element moves by one e5m2 step (25 % of its magnitude at most); compare de-quantised values
+    o, r = out.float() / so, ref.float() / so
+    assert ((o - r).abs() <= 0.26 * torch.maximum(o.abs(), r.abs()) + 2.0 ** -8).all()
 
 
 @pytest.mark.parametrize("B,L,T,H,K,mlp", [(2, 128, 64, 2, 256, 0), (1, 256, 128, 2, 256, 512), (1, 200, 56, 2, 256, 256),
@@ -215,7 +215,7 @@ def attn_ref(O, q, k, v):
     return x.reshape(q.shape[0], q.shape[2], -1)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("B,H,S,std", [(1, 1, 128, 1.0), (2, 2, 384, 2.0), (1, 2, 320, 1.0), (1, 3, 1000, 1.5)])
 def test_attention_small(ops, O, variant, B, H, S, std):
     g = gen(19)
