@@ -396,7 +396,61 @@ def group_flux():
         print(f"  28-step denoise (graph): {time.time()-t0:.2f} s; final latent amax={img.abs().max().item():.3f}")
 
 
-GROUPS = {"elementwise": group_elementwise, "model": group_model, "flux": group_flux, "gemm": group_gemm, "epilogue": group_epilogue,
+def stats(name, got, ref):
+    d = (got.float() - ref.float()).abs().flatten()
+    r = ref.float().abs()
+    q = torch.quantile(d[: 4_000_000], torch.tensor([0.5, 0.99, 0.9999], device=d.device)).tolist()
+    print(f"  {name:34s} ref amax {r.max().item():8.3f} rms {ref.float().pow(2).mean().sqrt().item():7.3f} | err mean {d.mean().item():.3e} "
+          f"p50 {q[0]:.2e} p99 {q[1]:.2e} p99.99 {q[2]:.2e} max {d.max().item():.3e} | frac>2^-6 {(d > 2**-6).float().mean().item():.2e}")
+
+
+def group_fullwidth():
+    """Full-width (3072 x 24 heads) depth-1 model: fused path vs the oracle on the same GPU tensors, stage by stage."""
+    from flux_fp8_api_b200 import model as M, pipeline as PL, blocks
+    from oracle import flux_oracle as O
+    params = M.FluxParams(depth=1, depth_single_blocks=1)
+    net = PL.build_synthetic_flux(M.FluxSpec(params=params), DEV, seed=7)
+    req = PL.synthetic_request(params, 1024, 1024, 1, 512, DEV, seed=3)
+    PL.calibrate(net, req, num_steps=13)
+    sd = {k: v for k, v in net.state_dict().items() if v is not None}
+    g = torch.Generator(device=DEV).manual_seed(11)
+    with torch.inference_mode():
+        img = torch.randn(1, 4096, 3072, device=DEV, generator=g).to(BF16)
+        txt = torch.randn(1, 512, 3072, device=DEV, generator=g).to(BF16)
+        vec = torch.randn(1, 3072, device=DEV, generator=g).to(BF16)
+        pe = net.pe_embedder(torch.cat((req["txt_ids"], req["img_ids"]), 1))
+        for mode in ("fused", "eager"):
+            if mode == "eager":
+                blocks.DoubleStreamBlock._fusable = lambda self, a, b: False
+                blocks.SingleStreamBlock._fusable = lambda self, a: False
+            print(f" -- {mode}")
+            d_img, d_txt = net.double_blocks[0](img=img, txt=txt, vec=vec, pe=pe)
+            o_img, o_txt = O.double_block(img, txt, vec, pe, sd, "double_blocks.0.", 24)
+            stats("double block img", d_img, o_img)
+            stats("double block txt", d_txt, o_txt)
+            x = torch.cat((txt, img), 1)
+            s_out = net.single_blocks[0](x, vec=vec, pe=pe)
+            stats("single block", s_out, O.single_block(x, vec, pe, sd, "single_blocks.0.", 24))
+            t = torch.full((1,), 0.7, dtype=BF16, device=DEV)
+            ours = net(img=req["img"], img_ids=req["img_ids"], txt=req["txt"], txt_ids=req["txt_ids"], timesteps=t, y=req["y"], guidance=req["guidance"])
+            cfg = dict(num_heads=24, depth=1, depth_single_blocks=1, axes_dim=[16, 56, 56], theta=10_000, guidance_embed=True)
+            ref = O.flux_forward(sd, cfg, req["img"], req["img_ids"], req["txt"], req["txt_ids"], t, req["y"], req["guidance"])
+            stats("Flux.forward (1+1 blocks)", ours, ref)
+            if mode == "fused":
+                # the reference's own noise floor: the same oracle with the other legitimate SDPA rounding
+                O.SDPA_P_DTYPE = "bf16"
+                n_img, n_txt = O.double_block(img, txt, vec, pe, sd, "double_blocks.0.", 24)
+                n_single = O.single_block(x, vec, pe, sd, "single_blocks.0.", 24)
+                n_ref = O.flux_forward(sd, cfg, req["img"], req["img_ids"], req["txt"], req["txt_ids"], t, req["y"], req["guidance"])
+                O.SDPA_P_DTYPE = "fp32"
+                stats("noise floor: double block img", n_img, o_img)
+                stats("noise floor: single block", n_single, O.single_block(x, vec, pe, sd, "single_blocks.0.", 24))
+                stats("noise floor: Flux.forward", n_ref, ref)
+                stats("ours vs bf16-P oracle: dbl img", d_img, n_img)
+                stats("ours vs bf16-P oracle: forward", ours, n_ref)
+
+
+GROUPS = {"elementwise": group_elementwise, "fullwidth": group_fullwidth, "model": group_model, "flux": group_flux, "gemm": group_gemm, "epilogue": group_epilogue,
           "attention": group_attention}
 
 

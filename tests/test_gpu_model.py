@@ -172,3 +172,77 @@ def test_quantize_flow_swaps_the_same_layers_as_the_reference(gold):
     spec2 = M.FluxSpec(params=spec.params, quantize_modulation=False)
     net2 = PL.build_synthetic_flux(spec2, DEV, seed=3)
     assert sum(isinstance(m, F8Linear) for m in net2.modules()) == 10
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at full width (hidden 3072, 24 heads), one double + one single block deep:
+# the fused CUDA path against the oracle evaluated on the same GPU tensors (torch's CUDA semantics, the
+# reference's real target).  Sequence lengths: c2 1024^2 dev (S=4608), c3 1024^2 schnell (S=4352, no guidance),
+# c4 768^2 (S=2816), c5 1536^2 with quantize_modulation=False (S=9728, bf16 Modulation.lin).
+#
+# Tolerance.  An fp8 pipeline is chaotic at the ulp level: a 1-ulp bf16 difference anywhere upstream flips
+# the e5m2 rounding (25 % relative step) of a few percent of the next layer's activations, every flipped
+# activation perturbs a whole output row of the next GEMM, and the perturbation compounds through the
+# double block's two sequential quantise->GEMM stages and again through the single block (measured:
+# profiles/r1_parity_noise_floor.md).  No two independent implementations -- including the reference run with
+# a different SDPA backend -- agree to 2^-4 max-abs at this width.  The bar is therefore the REFERENCE'S OWN
+# NOISE FLOOR: the oracle is evaluated a second time with the other legitimate rounding of the attention
+# probabilities (bf16 P as flash/cuDNN SDPA do, against fp32 P of the math backend; oracle.SDPA_P_DTYPE), and
+# our error against the oracle must not exceed that oracle-vs-oracle spread by more than 25 % (mean) /
+# 50 % (p99.99, max), at every width-preserving stage the golden fixtures cover at 2^-4 absolute.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,res,text_len,guidance,qmod,batch", [
+    ("c2-dev-1024", 1024, 512, True, True, 1),
+    ("c3-schnell-1024", 1024, 256, False, True, 1),
+    ("c4-dev-768", 768, 512, True, True, 2),
+    ("c5-dev-1536-bf16mod", 1536, 512, True, False, 1),
+])
+def test_baseline_configs_full_width(lib, name, res, text_len, guidance, qmod, batch):
+    from flux_fp8_api_b200 import model as M, pipeline as PL
+    from oracle import flux_oracle as O
+
+    params = M.FluxParams(depth=1, depth_single_blocks=1, guidance_embed=guidance)
+    spec = M.FluxSpec(params=params, quantize_modulation=qmod)
+    net = PL.build_synthetic_flux(spec, DEV, seed=7)
+    req = PL.synthetic_request(params, res, res, batch, text_len, DEV, seed=3)
+    if not guidance:
+        req["guidance"] = None
+    PL.calibrate(net, req, num_steps=13, shift=guidance)
+    assert PL.all_frozen(net)
+    sd = {k: v for k, v in net.state_dict().items() if v is not None}
+    cfg = dict(num_heads=24, depth=1, depth_single_blocks=1, axes_dim=[16, 56, 56], theta=10_000,
+               guidance_embed=guidance)
+    t = torch.full((batch,), 0.7, dtype=BF16, device=DEV)
+    with torch.inference_mode():
+        ours = net(img=req["img"], img_ids=req["img_ids"], txt=req["txt"], txt_ids=req["txt_ids"], timesteps=t,
+                   y=req["y"], guidance=req["guidance"])
+        ref = O.flux_forward(sd, cfg, req["img"], req["img_ids"], req["txt"], req["txt_ids"], t, req["y"], req["guidance"])
+        O.SDPA_P_DTYPE = "bf16"
+        try:
+            ref_b = O.flux_forward(sd, cfg, req["img"], req["img_ids"], req["txt"], req["txt_ids"], t, req["y"],
+                                   req["guidance"])
+        finally:
+            O.SDPA_P_DTYPE = "fp32"
+        assert torch.isfinite(ours.float()).all()
+
+        def spread(a, b):
+            e = (a.float() - b.float()).abs().flatten()
+            return e.mean().item(), torch.quantile(e[:: max(1, e.numel() // 1_000_000)], 0.9999).item(), e.max().item()
+
+        floor = spread(ref_b, ref)
+        # the closer of the two oracle roundings (our kernel rounds P to bf16 like the flash backends)
+        err = min(spread(ours, ref), spread(ours, ref_b), key=lambda s: s[0])
+        worst = max(spread(ours, ref), spread(ours, ref_b), key=lambda s: s[0])
+        print(f"{name}: ours-oracle mean/p99.99/max = {err[0]:.3e}/{err[1]:.3e}/{err[2]:.3e}; "
+              f"oracle noise floor = {floor[0]:.3e}/{floor[1]:.3e}/{floor[2]:.3e}; ref amax {ref.abs().max().item():.3f}")
+        assert worst[0] <= 1.25 * floor[0] + 2.0 ** -9
+        assert worst[1] <= 1.5 * floor[1] + 2.0 ** -7
+        assert worst[2] <= 1.5 * floor[2] + 2.0 ** -6
+        # no systematic offset: the mean signed error is far below the mean absolute error
+        bias = (ours.float() - ref.float()).mean().abs().item()
+        assert bias <= 0.05 * err[0] + 1e-4, bias
+        # and the CUDA-graph session reproduces the eager-launch step bit for bit at this shape
+        sched = PL.get_schedule(4, req["img"].shape[1], shift=guidance)
+        sess_g = PL.DenoiseSession(net, req, use_graph=True)
+        sess_e = PL.DenoiseSession(net, req, use_graph=False)
+        assert torch.equal(sess_g.step_device(req["img"], sched[0], sched[1]), sess_e.step_device(req["img"], sched[0], sched[1]))
