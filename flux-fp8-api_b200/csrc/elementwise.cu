@@ -3,6 +3,8 @@
 // All reproduce the reference's eager bf16 rounding points.
 #include "flux_b200.h"
 #include "host_util.h"
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace fb {
@@ -95,8 +97,10 @@ __global__ void __launch_bounds__(256) silu_quant_kernel(const __nv_bfloat16* __
 // ---------------------------------------------------------------------------------------------
 constexpr int kLnMaxIter = 16;  // D <= 16*256 = 4096
 
-template <int FMT>
-__global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+// NI = D/256 when known at compile time (12 for hidden 3072: the row lives in 48 registers and four 256-thread
+// blocks fit per SM, so the 4608-row launch is a single wave); NI = 0 is the generic predicated form.
+template <int FMT, int NI>
+__global__ void __launch_bounds__(256, NI == 0 ? 2 : 4) ln_mod_quant_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
                                                            const __nv_bfloat16* __restrict__ shift,
                                                            const __nv_bfloat16* __restrict__ scale,
                                                            int64_t mod_stride, uint8_t* __restrict__ yq, int64_t ldy,
@@ -108,13 +112,14 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
   const int b = row / L;
-  const int ni = D / 256;
+  const int ni = NI ? NI : D / 256;
+  constexpr int kIter = NI ? NI : kLnMaxIter;
   const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
-  uint4 xv[kLnMaxIter];
+  uint4 xv[kIter];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxIter; ++i) {
-    if (i < ni) {
+  for (int i = 0; i < kIter; ++i) {
+    if (NI || i < ni) {
       xv[i] = __ldg(xp + i * 32 + lane);
       uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
 #pragma unroll
@@ -127,10 +132,15 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / D;
+  // Opaque no-op on the packed row: stops the compiler from keeping the 96 unpacked fp32 values of the previous
+  // pass alive (CSE of the unpack), which costs 2x the registers of the packed row and halves occupancy.
+#pragma unroll
+  for (int i = 0; i < kIter; ++i)
+    asm volatile("" : "+r"(xv[i].x), "+r"(xv[i].y), "+r"(xv[i].z), "+r"(xv[i].w));
   float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxIter; ++i) {
-    if (i < ni) {
+  for (int i = 0; i < kIter; ++i) {
+    if (NI || i < ni) {
       uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -144,6 +154,11 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
   const float rstd = rsqrtf(var / D + eps);
+  // Opaque no-op on the packed row: stops the compiler from keeping the 96 unpacked fp32 values of the previous
+  // pass alive (CSE of the unpack), which costs 2x the registers of the packed row and halves occupancy.
+#pragma unroll
+  for (int i = 0; i < kIter; ++i)
+    asm volatile("" : "+r"(xv[i].x), "+r"(xv[i].y), "+r"(xv[i].z), "+r"(xv[i].w));
   const float s = in_scale ? __ldg(in_scale) : 1.f;
   // bf16-in / bf16-out products and sums are done with packed HMUL2/HADD2.BF16: for bf16 operands they round the
   // exact result once, which equals the reference's fp32 op followed by a bf16 rounding (the fp32 intermediate is
@@ -154,9 +169,12 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
   const __nv_bfloat162 s2 = __floats2bfloat162_rn(s, s);
   const uint4* shp = reinterpret_cast<const uint4*>(shift + static_cast<int64_t>(b) * mod_stride);
   const uint4* scp = reinterpret_cast<const uint4*>(scale + static_cast<int64_t>(b) * mod_stride);
+  // one top-level branch on the scale's representability -> two straight-line copies of the loop
+  auto apply = [&](auto packed_tag) {
+  constexpr bool kPacked = decltype(packed_tag)::value;
 #pragma unroll
-  for (int i = 0; i < kLnMaxIter; ++i) {
-    if (i < ni) {
+  for (int i = 0; i < kIter; ++i) {
+    if (NI || i < ni) {
       uint4 sh = __ldg(shp + i * 32 + lane);
       uint4 sc = __ldg(scp + i * 32 + lane);
       const uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
@@ -174,7 +192,7 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
         // (_rn forms: no contraction of the product and the sum into one HFMA2 -- each op rounds, as eager torch does)
         const __nv_bfloat162 m2 = __hadd2_rn(__hmul2_rn(__hadd2_rn(one2, sc2), n2), sh2);
         mb[t] = *reinterpret_cast<const uint32_t*>(&m2);
-        if (s_is_bf16) {
+        if (kPacked) {
           const __nv_bfloat162 p2 = __hmul2_rn(m2, s2);
           const float2 pf = __bfloat1622float2(p2);
           q[t * 2] = pf.x, q[t * 2 + 1] = pf.y;
@@ -184,8 +202,8 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
         }
       }
       const int64_t col = static_cast<int64_t>(i * 32 + lane) * 8;
-      if (yb) *reinterpret_cast<uint4*>(yb + static_cast<int64_t>(row) * ldyb + col) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
-      if (yq) {
+      if (NI == 0 && yb) *reinterpret_cast<uint4*>(yb + static_cast<int64_t>(row) * ldyb + col) = make_uint4(mb[0], mb[1], mb[2], mb[3]);
+      if (NI || yq) {
         // clamp(+-max) then cast == saturating cast
         uint2 o;
         o.x = to_fp8x2<FMT>(q[0], q[1]) | (static_cast<uint32_t>(to_fp8x2<FMT>(q[2], q[3])) << 16);
@@ -194,6 +212,9 @@ __global__ void __launch_bounds__(256) ln_mod_quant_kernel(const __nv_bfloat16* 
       }
     }
   }
+  };
+  if (s_is_bf16) apply(std::true_type{});
+  else apply(std::false_type{});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -519,7 +540,10 @@ extern "C" int fluxb200_ln_mod_quant(const void* x, int64_t ldx, const void* shi
   FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_ln_mod_quant: bad fp8 format %d", fmt);
   const int rows = B * L;
   const int grid = (rows + 7) / 8;
-  FB_CUDA_OK(launch_kernel(fmt == 0 ? ln_mod_quant_kernel<0> : ln_mod_quant_kernel<1>, dim3(grid), dim3(256), 0, stream, 1,
+  // the specialised form is the steady-state one: fp8 output only
+  auto kern = (D == 3072 && y_fp8 && !y_bf16) ? (fmt == 0 ? ln_mod_quant_kernel<0, 12> : ln_mod_quant_kernel<1, 12>)
+                        : (fmt == 0 ? ln_mod_quant_kernel<0, 0> : ln_mod_quant_kernel<1, 0>);
+  FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(256), 0, stream, 1,
                            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(shift),
                            static_cast<const __nv_bfloat16*>(scale), mod_batch_stride, static_cast<uint8_t*>(y_fp8), ldy,
                            static_cast<__nv_bfloat16*>(y_bf16), ldy_bf16, in_scale, rows, L, D, eps));
