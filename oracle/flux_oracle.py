@@ -58,10 +58,19 @@ def quantize_weight(w: Tensor, dtype: torch.dtype = E4M3) -> Tuple[Tensor, Tenso
     return quantize(w, scale, dtype), scale, scale.reciprocal()
 
 
+#: "restated": the arithmetic below.  "library": call the same PyTorch entry points the reference calls
+#: (torch._scaled_mm with use_fast_accum, F.scaled_dot_product_attention) -- CUDA only; used by
+#: tests/ref_gpu_timing.py to time / cross-check "the reference's eager fp8 path" on the B200 itself.
+BACKEND = "restated"
+
+
 def scaled_mm(xq: Tensor, wq: Tensor, sa_recip: Tensor, sw_recip: Tensor, bias: Optional[Tensor],
               out_dtype: torch.dtype = torch.bfloat16) -> Tensor:
     """torch._scaled_mm as called at float8_quantize.py:284-292: fp8 x fp8 products are exact in fp32,
     fp32 accumulation, then * scale_a * scale_b + bias, cast to out_dtype."""
+    if BACKEND == "library":
+        return torch._scaled_mm(xq, wq.T, scale_a=sa_recip, scale_b=sw_recip, bias=bias, out_dtype=out_dtype,
+                                use_fast_accum=True)
     acc = xq.float() @ wq.float().t()
     out = acc * (sa_recip.float() * sw_recip.float())
     if bias is not None:
@@ -165,6 +174,8 @@ SDPA_P_DTYPE = "fp32"
 def sdpa(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
     """F.scaled_dot_product_attention(q,k,v) (modules/flux_model.py:43): scale 1/sqrt(d), no mask.
     Restated with fp32 scores and softmax; output in the input dtype."""
+    if BACKEND == "library":
+        return F.scaled_dot_product_attention(q, k, v)
     scale = 1.0 / math.sqrt(q.shape[-1])
     s = (q.float() @ k.float().transpose(-1, -2)) * scale
     p = torch.softmax(s, dim=-1)
