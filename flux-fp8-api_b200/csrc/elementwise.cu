@@ -3,6 +3,7 @@
 // All reproduce the reference's eager bf16 rounding points.
 #include "flux_b200.h"
 #include "host_util.h"
+#include <cstdlib>
 #include <type_traits>
 
 #include "ptx.cuh"
@@ -476,6 +477,140 @@ __global__ void __launch_bounds__(256, 2) gemv_layers_kernel(const fluxb200_gemv
   }
 }
 
+// Tensor-core form of the batched modulation GEMV (the default when K % 64 == 0).  The CUDA-core form above spends
+// ~45 instructions per 16 weight bytes on fp8->fp32 conversion and FMAs and tops out near 3 TB/s.  Here the
+// WEIGHTS are the 16-row A operand of mma.sync.m16n8k16 (f16 operands, fp32 accumulate) and the batch (<= 8 rows
+// per pass, zero padded) is the 8-column B operand: a lane loads 16 bytes from weight row g and 16 from row g+8,
+// F2FP-unpacks them (exact: every e4m3 value is an f16 value, and products of two fp8 values are exact in fp32)
+// straight into the a0..a3 registers of four MMAs, and reads the matching activations (converted to f16 once per
+// block in shared memory) as two 16-byte pieces that are the b0/b1 pairs of those MMAs: ~12 instructions per 16
+// weight bytes, no register shuffling.  (mma.sync with fp8 operand TYPES is not native on sm_100a: ptxas expands
+// it into conversions + HMMA + FADDs.)
+// K order inside a dot product is free, so K is consumed in 64-byte chunks permuted so that every lane's load is
+// one contiguous 16-byte piece: quad lane t owns bytes [16t, 16t+16) of the chunk, word j of it feeds MMA j (low
+// half = k-slots 2t,2t+1, high half = k-slots 8+2t,8+2t+1), and the activation fragment is read from the same k's.
+// One warp = 16 output columns over the whole K; a block of 4 warps = 64 columns (same block->layer table).
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int FMT>
+__device__ __forceinline__ uint32_t fp8x2_to_f16x2(uint16_t two) {
+  __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2(two, FMT == 0 ? __NV_E4M3 : __NV_E5M2);
+  return *reinterpret_cast<uint32_t*>(&hr);
+}
+
+constexpr int kModAPad = 32;     // smem row pitch 2K + 32 bytes: the 8 batch rows of a quad-column land in distinct banks
+constexpr int kModMmaWarps = 4;  // 4 warps x 16 weight rows = kModColsPerBlock
+constexpr int kModU = 4;         // chunks per pipeline group
+
+template <int AFMT>
+__global__ void __launch_bounds__(kModMmaWarps * 32, 4) gemv_layers_mma_kernel(
+    const fluxb200_gemv_layer* __restrict__ layers, int num_layers, const uint8_t* __restrict__ aq,
+    __nv_bfloat16* __restrict__ out, int64_t ld_out, int B, int K) {
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t a_sm8[];
+  __shared__ int s_layer;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // block -> layer: every thread tests a few table entries, one barrier-wide count (a serial scan by one thread
+  // costs one dependent L2 round trip per layer: ~20 us for the last of 76 layers)
+  if (threadIdx.x == 0) s_layer = 0;
+  __syncthreads();
+  {
+    int mine = 0;
+    for (int i = threadIdx.x; i < num_layers; i += blockDim.x)
+      mine += layers[i].block_start <= static_cast<int>(blockIdx.x) ? 1 : 0;
+    if (mine) atomicAdd(&s_layer, mine);
+  }
+  __syncthreads();
+  const int l = s_layer - 1;
+  const fluxb200_gemv_layer L = layers[l];
+  const int pitch = 2 * K + kModAPad;
+  const int n0 = (static_cast<int>(blockIdx.x) - L.block_start) * kModColsPerBlock + warp * 16;
+  const int g = lane >> 2, t = lane & 3;
+  // weight rows beyond N re-read row N-1 (valid memory); their results are never stored
+  const uint8_t* wbase = static_cast<const uint8_t*>(L.w) + t * 16;
+  const uint8_t* wr0 = wbase + static_cast<int64_t>(min(n0 + g, L.N - 1)) * K;
+  const uint8_t* wr1 = wbase + static_cast<int64_t>(min(n0 + g + 8, L.N - 1)) * K;
+  const float s = __ldg(L.a_scale_recip) * __ldg(L.w_scale_recip);
+  const __nv_bfloat16* bias = static_cast<const __nv_bfloat16*>(L.bias);
+  const int chunks = K / 64;
+
+  for (int m0 = 0; m0 < B; m0 += 8) {
+    const int mt = min(8, B - m0);
+    __syncthreads();
+    {  // rows m0..m0+mt-1 of this layer's quantised activations -> f16; row `mt` of the buffer is all zeros
+      const uint8_t* src = aq + (static_cast<int64_t>(l) * B + m0) * K;
+      const int per_row = K / 16;  // 16 fp8 values in, 32 bytes of f16 out per item; rows are contiguous in aq
+      for (int i = threadIdx.x; i < mt * per_row; i += blockDim.x) {
+        const int r = i / per_row, c = i - r * per_row;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        uint4 lo, hi;
+        lo.x = fp8x2_to_f16x2<AFMT>(v.x & 0xffffu), lo.y = fp8x2_to_f16x2<AFMT>(v.x >> 16);
+        lo.z = fp8x2_to_f16x2<AFMT>(v.y & 0xffffu), lo.w = fp8x2_to_f16x2<AFMT>(v.y >> 16);
+        hi.x = fp8x2_to_f16x2<AFMT>(v.z & 0xffffu), hi.y = fp8x2_to_f16x2<AFMT>(v.z >> 16);
+        hi.z = fp8x2_to_f16x2<AFMT>(v.w & 0xffffu), hi.w = fp8x2_to_f16x2<AFMT>(v.w >> 16);
+        uint4* dst = reinterpret_cast<uint4*>(a_sm8 + r * pitch + c * 32);
+        dst[0] = lo, dst[1] = hi;
+      }
+      for (int i = threadIdx.x; i < pitch / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_sm8 + mt * pitch)[i] = 0u;
+    }
+    __syncthreads();
+    if (n0 < L.N) {
+      const uint8_t* ab = a_sm8 + (g < mt ? g : mt) * pitch + t * 32;
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+      auto consume = [&](const uint4& w0, const uint4& w1, int kc) {
+        const uint4 b01 = *reinterpret_cast<const uint4*>(ab + kc * 128);
+        const uint4 b23 = *reinterpret_cast<const uint4*>(ab + kc * 128 + 16);
+        mma_m16n8k16_f16(c0, fp8x2_to_f16x2<0>(w0.x & 0xffffu), fp8x2_to_f16x2<0>(w1.x & 0xffffu),
+                         fp8x2_to_f16x2<0>(w0.x >> 16), fp8x2_to_f16x2<0>(w1.x >> 16), b01.x, b01.y);
+        mma_m16n8k16_f16(c1, fp8x2_to_f16x2<0>(w0.y & 0xffffu), fp8x2_to_f16x2<0>(w1.y & 0xffffu),
+                         fp8x2_to_f16x2<0>(w0.y >> 16), fp8x2_to_f16x2<0>(w1.y >> 16), b01.z, b01.w);
+        mma_m16n8k16_f16(c0, fp8x2_to_f16x2<0>(w0.z & 0xffffu), fp8x2_to_f16x2<0>(w1.z & 0xffffu),
+                         fp8x2_to_f16x2<0>(w0.z >> 16), fp8x2_to_f16x2<0>(w1.z >> 16), b23.x, b23.y);
+        mma_m16n8k16_f16(c1, fp8x2_to_f16x2<0>(w0.w & 0xffffu), fp8x2_to_f16x2<0>(w1.w & 0xffffu),
+                         fp8x2_to_f16x2<0>(w0.w >> 16), fp8x2_to_f16x2<0>(w1.w >> 16), b23.z, b23.w);
+      };
+      // software pipeline over groups of kModU chunks, two register buffers: the loads of group i+1 are in flight
+      // while group i is consumed (8..16 outstanding 16-byte loads per lane; the kernel is latency/MLP bound)
+      uint4 bufA[kModU][2], bufB[kModU][2];
+      auto fetch = [&](uint4 (&buf)[kModU][2], int kc0) {
+#pragma unroll
+        for (int u = 0; u < kModU; ++u) {
+          buf[u][0] = __ldg(reinterpret_cast<const uint4*>(wr0 + (kc0 + u) * 64));
+          buf[u][1] = __ldg(reinterpret_cast<const uint4*>(wr1 + (kc0 + u) * 64));
+        }
+      };
+      const int full = chunks / (2 * kModU) * (2 * kModU);
+      if (full > 0) fetch(bufA, 0);
+      for (int kc0 = 0; kc0 < full; kc0 += 2 * kModU) {
+        fetch(bufB, kc0 + kModU);
+#pragma unroll
+        for (int u = 0; u < kModU; ++u) consume(bufA[u][0], bufA[u][1], kc0 + u);
+        if (kc0 + 2 * kModU < full) fetch(bufA, kc0 + 2 * kModU);
+#pragma unroll
+        for (int u = 0; u < kModU; ++u) consume(bufB[u][0], bufB[u][1], kc0 + kModU + u);
+      }
+      for (int kc = full; kc < chunks; ++kc) {
+        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(wr0 + kc * 64));
+        const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(wr1 + kc * 64));
+        consume(w0, w1, kc);
+      }
+      // D fragment: c[0],c[1] -> weight row n0+g, batch rows 2t, 2t+1;  c[2],c[3] -> weight row n0+g+8
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = n0 + g + (j >> 1) * 8, row = t * 2 + (j & 1);
+        if (row < mt && col < L.N) {
+          const float bb = bias ? __bfloat162float(bias[col]) : 0.f;
+          out[static_cast<int64_t>(m0 + row) * ld_out + L.out_offset + col] = __float2bfloat16_rn(fmaf(c0[j] + c1[j], s, bb));
+        }
+      }
+    }
+  }
+}
+
 static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
   int64_t blocks = (work_items + threads - 1) / threads;
   int64_t cap = static_cast<int64_t>(sm_count()) * max_blocks_per_sm;
@@ -613,6 +748,21 @@ extern "C" int fluxb200_modulation_batched(const void* vec, const fluxb200_gemv_
     FB_CUDA_OK(launch_kernel(gemv_layers_kernel<AF, 0, NK_>, dim3(total_blocks), dim3(256), 0, stream, 1, layers, num_layers, \
                              static_cast<const uint8_t*>(a8), o, ld_out, B, K));                                          \
   } while (0)
+  static const bool use_mma = [] {
+    const char* e = getenv("FLUXB200_GEMV_MMA");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (use_mma && K % 64 == 0) {
+    const size_t smem = static_cast<size_t>((B < 8 ? B : 8) + 1) * (2 * K + kModAPad);
+    auto kern = a_fmt == 0 ? gemv_layers_mma_kernel<0> : gemv_layers_mma_kernel<1>;
+    if (smem > 48 * 1024) FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB_CUDA_OK(launch_kernel(a_fmt == 0 ? silu_quant_layers_kernel<0> : silu_quant_layers_kernel<1>, dim3(num_layers),
+                             dim3(256), 0, stream, 1, v, layers, a8, B * K));
+    FB_CUDA_OK(launch_kernel(kern, dim3(total_blocks), dim3(kModMmaWarps * 32), smem, stream, 1, layers, num_layers,
+                             static_cast<const uint8_t*>(a8), o, ld_out, B, K));
+    FB_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const int nk = (K + 511) / 512;
   if (a_fmt == 0) {
     if (nk <= 1) FB_MOD(0, 1); else if (nk <= 2) FB_MOD(0, 2); else if (nk <= 6) FB_MOD(0, 6); else FB_MOD(0, 8);

@@ -358,6 +358,56 @@ def group_model():
                         cmp(f"ModulationBank B{B} (second half)", a_, b_, 2 ** -7 * max(1, b_.abs().max().item()), 0.01)
 
 
+def group_modbank():
+    """Full-width batched modulation (K = 3072; 4 double-type + 8 single-type layers) against the per-layer GEMV path,
+    batch 1 / 3 / 8 / 11, and its weight-streaming rate.  FLUXB200_GEMV_MMA=0 selects the CUDA-core kernel."""
+    from flux_fp8_api_b200 import blocks
+    from flux_fp8_api_b200.f8linear import F8Linear
+    torch.manual_seed(5)
+    mods = []
+    for i in range(12):
+        m = blocks.Modulation(3072, double=i < 4).to(DEV).to(BF16)
+        torch.nn.init.normal_(m.lin.weight, std=0.01)
+        torch.nn.init.normal_(m.lin.bias, std=0.02)
+        m.lin = F8Linear.from_linear(m.lin, input_float8_dtype=torch.float8_e4m3fn if i % 2 else torch.float8_e5m2)
+        mods.append(m)
+    with torch.inference_mode():
+        cal = torch.randn(1, 3072, device=DEV).to(BF16)
+        for _ in range(13):
+            for m in mods:
+                m(cal)
+        for dt in (torch.float8_e5m2, torch.float8_e4m3fn):
+            sel = [m for m in mods if m.lin.input_float8_dtype == dt]
+            bank = blocks.ModulationBank(sel)
+            for B in (1, 3, 8, 11):
+                vec = torch.randn(B, 3072, device=DEV).to(BF16)
+                got = bank(vec)
+                for m, (o1, o2) in zip(sel, got):
+                    r1, r2 = m(vec)
+                    a_ = torch.cat(tuple(o1) + (tuple(o2) if o2 else ()), -1)
+                    b_ = torch.cat(tuple(r1) + (tuple(r2) if r2 else ()), -1)
+                    cmp(f"bank {str(dt)[-4:]} B{B} N{m.lin.out_features}", a_, b_, 2 ** -7 * max(1, b_.abs().max().item()), 0.01)
+        bank = blocks.ModulationBank([m for m in mods if m.lin.input_float8_dtype == torch.float8_e5m2])
+        vec = torch.randn(1, 3072, device=DEV).to(BF16)
+        nbytes = bank.total_n * bank.K
+        for _ in range(3):
+            bank(vec)
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # stream more than L2 between repeats: 6 layers x ~40 MB = 240 MB per call, still flush explicitly
+        flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=DEV)
+        tot = 0.0
+        for _ in range(10):
+            flush.zero_()
+            s_.record()
+            bank(vec)
+            e_.record()
+            torch.cuda.synchronize()
+            tot += s_.elapsed_time(e_)
+        print(f"  batched modulation {nbytes/1e6:.0f} MB: {tot/10*1e3:.1f} us ({nbytes/(tot/10*1e-3)/1e9:.0f} GB/s) "
+              f"[FLUXB200_GEMV_MMA={os.environ.get('FLUXB200_GEMV_MMA', '1')}]")
+
+
 def group_flux():
     """Full-size Flux-dev 1024x1024: synthetic weights -> quantise -> calibrate (eager) -> fused denoise timing."""
     from flux_fp8_api_b200 import model as M, pipeline as PL
@@ -450,7 +500,7 @@ def group_fullwidth():
                 stats("ours vs bf16-P oracle: forward", ours, n_ref)
 
 
-GROUPS = {"elementwise": group_elementwise, "fullwidth": group_fullwidth, "model": group_model, "flux": group_flux, "gemm": group_gemm, "epilogue": group_epilogue,
+GROUPS = {"elementwise": group_elementwise, "fullwidth": group_fullwidth, "modbank": group_modbank, "model": group_model, "flux": group_flux, "gemm": group_gemm, "epilogue": group_epilogue,
           "attention": group_attention}
 
 
