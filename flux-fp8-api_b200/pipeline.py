@@ -122,6 +122,67 @@ def build_synthetic_flux(spec: FluxSpec, device, seed: int = 1234, quantize: boo
     return model
 
 
+# ------------------------------------------------------------------------------------------------
+# prequantised checkpoints.  The reference can LOAD a prequantised flow
+# (`prequantized_flow: true` + F8Linear._load_from_state_dict, float8_quantize.py:91-193) but has no
+# writer; this is the writer, and the artefact `parallel.broadcast_state` ships to the other ranks.
+# ------------------------------------------------------------------------------------------------
+PREQUANTIZED_FORMAT = "flux-fp8-b200/prequantized"
+PREQUANTIZED_VERSION = 1
+
+
+def _spec_to_dict(spec: FluxSpec) -> dict:
+    import dataclasses
+
+    d = dataclasses.asdict(spec)
+    d["params"] = {k: (list(v) if isinstance(v, tuple) else v) for k, v in d["params"].items()}
+    return d
+
+
+def save_prequantized(model: Flux, path: str, spec: Optional[FluxSpec] = None) -> dict:
+    """Write the quantised state (e4m3 `float8_data`, the four 0-dim fp32 scales, bf16 biases / norms / embedders,
+    zeros[1] `weight` placeholders) exactly as `state_dict()` names it -- the reference's own key layout, so the
+    file also loads into the reference's Flux built with prequantized_flow=True.  Returns the header."""
+    if not all_frozen(model):
+        raise RuntimeError("save_prequantized: input scales are not frozen yet (run calibrate() first); a checkpoint "
+                           "without them would silently re-calibrate on its first 12 steps")
+    state = {k: v.detach().to("cpu") for k, v in model.state_dict().items() if v is not None}
+    n_f8 = sum(1 for k in state if k.endswith(".float8_data"))
+    header = {"format": PREQUANTIZED_FORMAT, "version": PREQUANTIZED_VERSION, "f8_layers": n_f8,
+              "bytes": int(sum(v.numel() * v.element_size() for v in state.values())),
+              "spec": _spec_to_dict(spec) if spec is not None else None}
+    torch.save({"header": header, "state": state}, path)
+    return header
+
+
+def load_prequantized(path: str, device, spec: Optional[FluxSpec] = None) -> Flux:
+    """Build a Flux with F8Linear layers in place (prequantized_flow) and load a `save_prequantized` file: no master
+    weights, no quantisation pass, no calibration -- the model is frozen and graph-capturable straight away."""
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    header = blob.get("header", {})
+    if header.get("format") != PREQUANTIZED_FORMAT:
+        raise RuntimeError(f"{path}: not a {PREQUANTIZED_FORMAT} file")
+    if header.get("version", 0) > PREQUANTIZED_VERSION:
+        raise RuntimeError(f"{path}: format version {header.get('version')} is newer than this build ({PREQUANTIZED_VERSION})")
+    if spec is None:
+        sd = header.get("spec")
+        if sd is None:
+            raise ValueError("load_prequantized: the file carries no model spec; pass spec=")
+        from .model import FluxParams
+        pd = dict(sd["params"])
+        pd["axes_dim"] = list(pd["axes_dim"])
+        spec = FluxSpec(**{**sd, "params": FluxParams(**pd)})
+    spec = FluxSpec(**{**spec.__dict__, "prequantized_flow": True})
+    with torch.device(device):
+        model = Flux(spec, dtype=BF16)
+    state = {k: v.to(device) for k, v in blob["state"].items()}
+    model.load_state_dict(state, strict=True, assign=True)
+    model.eval()
+    if not all_frozen(model):
+        raise RuntimeError(f"{path}: some F8Linear layers came back without frozen scales")
+    return model
+
+
 def all_frozen(model: nn.Module) -> bool:
     return all(m.frozen for m in model.modules() if isinstance(m, F8Linear))
 

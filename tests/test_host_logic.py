@@ -70,6 +70,36 @@ def test_f8linear_load_cases(tiny):
         F8Linear(256, 256, dtype=BF16).load_state_dict(bad)
 
 
+def test_prequantized_checkpoint_round_trip(tiny, tmp_path):
+    """save_prequantized -> load_prequantized reproduces every tensor bit for bit (fp8 bytes, scales, biases),
+    carries the model spec in its header, and refuses un-calibrated models / foreign files."""
+    spec = tiny_spec(tiny, prequantized_flow=True)
+    net = M.Flux(spec, dtype=BF16)
+    net.load_state_dict(tiny["state"], strict=True)
+    path = str(tmp_path / "tiny.f8.pt")
+    header = PL.save_prequantized(net, path, spec)
+    assert header["format"] == PL.PREQUANTIZED_FORMAT and header["f8_layers"] == 13
+    back = PL.load_prequantized(path, "cpu")
+    assert PL.all_frozen(back)
+    a, b = net.state_dict(), back.state_dict()
+    assert set(a) == set(b)
+    for k in a:
+        if a[k] is None:
+            assert b[k] is None
+            continue
+        assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, k
+        assert torch.equal(a[k].view(torch.uint8) if a[k].dtype == torch.float8_e4m3fn else a[k],
+                           b[k].view(torch.uint8) if b[k].dtype == torch.float8_e4m3fn else b[k]), k
+    assert back.params.depth == net.params.depth and isinstance(back.double_blocks[0].img_mod.lin, F8Linear)
+    # an un-calibrated model must not be written
+    fresh = M.Flux(spec, dtype=BF16)
+    with pytest.raises(RuntimeError):
+        PL.save_prequantized(fresh, str(tmp_path / "x.pt"), spec)
+    torch.save({"header": {"format": "something-else"}, "state": {}}, str(tmp_path / "y.pt"))
+    with pytest.raises(RuntimeError):
+        PL.load_prequantized(str(tmp_path / "y.pt"), "cpu")
+
+
 def test_flux_constructor_errors():
     with pytest.raises(ValueError):
         M.Flux(M.FluxSpec(params=M.FluxParams(hidden_size=250, num_heads=4)))
