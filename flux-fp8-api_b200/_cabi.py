@@ -35,6 +35,7 @@ EXPORTS = (
     "fluxb200_ln_mod_quant",
     "fluxb200_qknorm_rope",
     "fluxb200_attention",
+    "fluxb200_lora_fuse",
     "fluxb200_debug_counters",
 )
 
@@ -164,6 +165,10 @@ def load() -> C.CDLL:
         C.c_float, C.c_void_p,
     ]
     lib.fluxb200_attention.argtypes = [C.POINTER(AttentionArgs), C.c_void_p]
+    lib.fluxb200_lora_fuse.argtypes = [
+        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+    ]
     lib.fluxb200_debug_counters.argtypes = [C.POINTER(C.c_ulonglong)]
     for name in EXPORTS:
         if name != "fluxb200_last_error":

@@ -63,6 +63,29 @@ def amax(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     return out
 
 
+def lora_fuse(w_fp8: Tensor, w_scale_recip: Tensor, lora_down: Tensor, lora_up: Tensor, coeff: float,
+              unfuse: bool = False, chunks: int = 1):
+    """Dequantise + rank-R update + bf16 rounding + amax in one pass (fluxb200_lora_fuse; reference
+    lora_loading.py:615-626, 509-577 and the amax of float8_quantize.py:196-198).
+    lora_down [N, R] fp32, lora_up [chunks*R, K] fp32.  Returns (W' bf16 [N, K], amax 0-dim fp32)."""
+    cabi.require_cuda(w_fp8, w_scale_recip, lora_down, lora_up)
+    N, K = w_fp8.shape
+    R = lora_down.shape[1]
+    if lora_down.dtype != torch.float32 or lora_up.dtype != torch.float32:
+        raise ValueError("lora_fuse expects fp32 LoRA factors (the reference computes the delta in fp32)")
+    if lora_down.shape != (N, R) or lora_up.shape != (chunks * R, K):
+        raise ValueError(f"lora_fuse: factors {tuple(lora_down.shape)} x {tuple(lora_up.shape)} do not match a "
+                         f"[{N}, {K}] weight with {chunks} chunk(s)")
+    w_fp8, lora_down, lora_up = w_fp8.contiguous(), lora_down.contiguous(), lora_up.contiguous()
+    out = torch.empty((N, K), dtype=BF16, device=w_fp8.device)
+    amax = torch.empty((), dtype=torch.float32, device=w_fp8.device)
+    cabi.check(cabi.load().fluxb200_lora_fuse(w_fp8.data_ptr(), cabi.fp8_fmt(w_fp8.dtype), w_scale_recip.data_ptr(),
+                                              lora_down.data_ptr(), lora_up.data_ptr(), N, K, R, chunks, float(coeff),
+                                              1 if unfuse else 0, out.data_ptr(), amax.data_ptr(), cabi.stream_ptr()),
+               "fluxb200_lora_fuse")
+    return out, amax
+
+
 def silu_quant(x: Tensor, scale: Optional[Tensor], dtype: Optional[torch.dtype], want_bf16: bool = False):
     """Modulation prologue: (fp8 quantised silu(x), bf16 silu(x))."""
     cabi.require_cuda(x)

@@ -209,6 +209,21 @@ typedef struct fluxb200_attention_args {
 
 int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * LoRA fuse / unfuse into one quantised layer, on the device.  Replaces the per-layer body of
+ * apply_lora_to_model / remove_lora_from_module (lora_loading.py:679-687, 742-749):
+ *   extract_weight_from_linear (:615-626)            W  = float(w_fp8) * (*w_scale_recip)
+ *   calculate_lora_weight (:509-547)                 D  = sum_c coeff * (lora_down @ lora_up[c*R:(c+1)*R])     (fp32)
+ *   apply_lora_weight_to_module (:566-577) / unfuse (:549-563)   W' = bf16(W + D)  /  bf16(W - D)
+ *   first half of F8Linear.quantize_weight (float8_quantize.py:196-198)   *amax_out = max|W'|
+ * lora_down = lora_B as fp32 [N, R]; lora_up = lora_A as fp32 [chunks*R, K], already multiplied by alpha/rank by the
+ * caller when alpha != rank (:530-531); chunks > 1 is the reference's "uneven rank" case (:532-541); coeff = lora_scale.
+ * The caller turns *amax_out into the new scale (amax_to_scale) and requantises w_out_bf16 with fluxb200_quantize --
+ * typically over the old w_fp8 buffer, which this call has finished reading.  amax_out is zeroed by the call. */
+int fluxb200_lora_fuse(const void* w_fp8, int w_fmt, const float* w_scale_recip, const float* lora_down,
+                       const float* lora_up, int N, int K, int R, int chunks, float coeff, int unfuse,
+                       void* w_out_bf16, float* amax_out, fluxb200_stream_t stream);
+
 /* Diagnostics: cycle counters of the last attention launch's CTA 0 (host pointer to 16 x uint64):
  * [0..5] softmax warp: wait-S, tmem load, max, exp, wait-O, store-P; [6] half-steps;
  * [8..10] MMA issuer: wait-P, wait-KV, issue.  Synchronises the device. */

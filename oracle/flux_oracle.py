@@ -302,6 +302,45 @@ def flux_forward(p: Dict[str, Tensor], cfg: dict, img: Tensor, img_ids: Tensor, 
 
 
 # --------------------------------------------------------------------------------------------
+# LoRA fuse / unfuse into an F8Linear (lora_loading.py)
+# --------------------------------------------------------------------------------------------
+def lora_delta(lora_A: Tensor, lora_B: Tensor, alpha, rank: Optional[int] = None, lora_scale: float = 1.0) -> Tensor:
+    """calculate_lora_weight (lora_loading.py:509-547): fp32 `lora_scale * (lora_B @ lora_A)`, with lora_A scaled by
+    alpha / rank when they differ, and an "uneven rank" lora_A ([c*r, K] against lora_B [N, r]) fused chunk by chunk."""
+    uneven = lora_B.shape[1] != lora_A.shape[0]
+    rank_diff = lora_A.shape[0] / lora_B.shape[1]
+    if rank is None:
+        rank = lora_B.shape[1]
+    if alpha is None:
+        alpha = rank
+    up = lora_A.to(torch.float32)
+    down = lora_B.to(torch.float32)
+    if alpha != rank:
+        up = up * alpha / rank
+    if uneven:
+        fused = torch.zeros((lora_B.shape[0], lora_A.shape[1]), dtype=torch.float32, device=up.device)
+        for chunk in up.chunk(int(rank_diff), dim=0):
+            fused = fused + (lora_scale * torch.mm(down, chunk))
+        return fused
+    return lora_scale * torch.mm(down, up)
+
+
+def lora_fuse_f8(float8_data: Tensor, scale_reciprocal: Tensor, lora_A: Tensor, lora_B: Tensor, alpha,
+                 lora_scale: float = 1.0, unfuse: bool = False, w_dtype: torch.dtype = torch.bfloat16,
+                 f8_dtype: torch.dtype = E4M3) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """One F8Linear through apply_lora_to_model / remove_lora_from_module (lora_loading.py:679-687, 742-749):
+    dequantise `float8_data.float() * scale_reciprocal` (:615-626), add (or subtract) the fp32 delta (:566-577,
+    :549-563), cast to the layer's weight dtype, then set_weight_tensor -> quantize_weight
+    (float8_quantize.py:209-212, 195-207).  Returns (fused weight in w_dtype, float8_data, scale, scale_reciprocal)."""
+    w = float8_data.float().mul(scale_reciprocal)
+    delta = lora_delta(lora_A, lora_B, alpha, None, lora_scale)
+    fused = (w - delta) if unfuse else (w + delta)
+    fused = fused.to(w_dtype)
+    q, s, sr = quantize_weight(fused, f8_dtype)
+    return fused, q, s, sr
+
+
+# --------------------------------------------------------------------------------------------
 # denoise-loop glue used by tests and the CPU baseline (flux_pipeline.py:315-344, 627-651)
 # --------------------------------------------------------------------------------------------
 def time_shift(mu: float, sigma: float, t: Tensor) -> Tensor:

@@ -249,6 +249,53 @@ def golden_flux():
                 "mod1": [mod1.shift, mod1.scale, mod1.gate]}, os.path.join(OUT, "flux_tiny.pt"))
 
 
+def golden_lora():
+    """LoRA fuse / unfuse through the reference's lora_loading functions on reference F8Linear layers."""
+    import lora_loading as ref_lora  # reference
+
+    print("lora fuse (reference lora_loading.py)")
+    g = torch.Generator().manual_seed(77)
+    cases = []
+    # (N, K, rank of lora_B, rows of lora_A, alpha, lora_scale)
+    for name, N, K, r, ra, alpha, ls in [("even", 384, 256, 16, 16, None, 1.0),
+                                          ("alpha", 256, 512, 8, 8, 4.0, 0.75),
+                                          ("uneven", 768, 256, 4, 12, None, 1.25),
+                                          ("big-delta", 256, 256, 32, 32, 16.0, 3.0)]:
+        lin = torch.nn.Linear(K, N, bias=True).to(BF16)
+        lin.weight.data = (torch.randn(N, K, generator=g) * 0.02).to(BF16)
+        mod = ref_f8.F8Linear.from_linear(lin)
+        mod.quantize_weight()
+        before = dict(float8_data=mod.float8_data.clone(), scale=mod.scale.clone(),
+                      scale_reciprocal=mod.scale_reciprocal.clone())
+        lora_A = (torch.randn(ra, K, generator=g) * 0.05).to(BF16)
+        lora_B = (torch.randn(N, r, generator=g) * 0.05).to(BF16)
+        lora_sd = (lora_A, lora_B, alpha)
+        # exactly the loop body of apply_lora_to_model (lora_loading.py:679-687)
+        weight, is_f8, dtype = ref_lora.extract_weight_from_linear(mod)
+        assert is_f8 and dtype == BF16
+        weight = ref_lora.apply_lora_weight_to_module(weight, lora_sd, lora_scale=ls)
+        mod.set_weight_tensor(weight.type(dtype))
+        fused = dict(weight=weight.type(dtype).clone(), float8_data=mod.float8_data.clone(), scale=mod.scale.clone(),
+                     scale_reciprocal=mod.scale_reciprocal.clone())
+        # ... and of remove_lora_from_module (:742-749) on the fused layer
+        weight, _, _ = ref_lora.extract_weight_from_linear(mod)
+        weight = ref_lora.unfuse_lora_weight_from_module(weight, lora_sd, lora_scale=ls)
+        mod.set_weight_tensor(weight.type(dtype))
+        unfused = dict(weight=weight.type(dtype).clone(), float8_data=mod.float8_data.clone(), scale=mod.scale.clone(),
+                       scale_reciprocal=mod.scale_reciprocal.clone())
+        ow, oq, os_, osr = O.lora_fuse_f8(before["float8_data"], before["scale_reciprocal"], lora_A, lora_B, alpha, ls)
+        report(f"{name}: fused weight", fused["weight"], ow, 0, exact=True)
+        report(f"{name}: fused float8_data", fused["float8_data"], oq, 0, exact=True)
+        report(f"{name}: fused scale", fused["scale"], os_, 0, exact=True)
+        uw, uq, us, usr = O.lora_fuse_f8(fused["float8_data"], fused["scale_reciprocal"], lora_A, lora_B, alpha, ls,
+                                         unfuse=True)
+        report(f"{name}: unfused weight", unfused["weight"], uw, 0, exact=True)
+        report(f"{name}: unfused float8_data", unfused["float8_data"], uq, 0, exact=True)
+        cases.append(dict(name=name, lora_A=lora_A, lora_B=lora_B, alpha=alpha, lora_scale=ls, before=before,
+                          fused=fused, unfused=unfused))
+    torch.save(cases, os.path.join(OUT, "lora.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -257,4 +304,5 @@ if __name__ == "__main__":
     golden_f8linear()
     golden_ops()
     golden_flux()
+    golden_lora()
     print("golden fixtures written to", OUT)

@@ -122,3 +122,25 @@ def test_schedule_matches_reference_formula():
     assert all(a > b for a, b in zip(ts[:-1], ts[1:]))
     lin = O.get_schedule(4, 4096, shift=False)
     assert lin == pytest.approx([1.0, 0.75, 0.5, 0.25, 0.0])
+
+
+def test_lora_fuse_and_unfuse_are_bit_exact(golden_dir):
+    """oracle.lora_fuse_f8 against the reference's extract_weight_from_linear -> apply / unfuse ->
+    set_weight_tensor chain (lora_loading.py), incl. alpha != rank and the uneven-rank chunked fuse."""
+    cases = load(golden_dir, "lora.pt")
+    assert [c["name"] for c in cases] == ["even", "alpha", "uneven", "big-delta"]
+    for c in cases:
+        w, q, s, sr = O.lora_fuse_f8(c["before"]["float8_data"], c["before"]["scale_reciprocal"], c["lora_A"],
+                                     c["lora_B"], c["alpha"], c["lora_scale"])
+        assert torch.equal(w, c["fused"]["weight"]), c["name"]
+        assert torch.equal(q.view(torch.uint8), c["fused"]["float8_data"].view(torch.uint8)), c["name"]
+        assert torch.equal(s, c["fused"]["scale"]) and torch.equal(sr, c["fused"]["scale_reciprocal"])
+        w, q, s, sr = O.lora_fuse_f8(c["fused"]["float8_data"], c["fused"]["scale_reciprocal"], c["lora_A"],
+                                     c["lora_B"], c["alpha"], c["lora_scale"], unfuse=True)
+        assert torch.equal(w, c["unfused"]["weight"]), c["name"]
+        assert torch.equal(q.view(torch.uint8), c["unfused"]["float8_data"].view(torch.uint8)), c["name"]
+        # the LoRA really changed the layer, and un-fusing brings it back to within the e4m3 requantisation step
+        assert not torch.equal(c["fused"]["float8_data"].view(torch.uint8), c["before"]["float8_data"].view(torch.uint8))
+        w0 = c["before"]["float8_data"].float() * c["before"]["scale_reciprocal"]
+        w2 = c["unfused"]["float8_data"].float() * c["unfused"]["scale_reciprocal"]
+        assert (w0 - w2).abs().max() <= 0.13 * w0.abs().max()
