@@ -298,7 +298,7 @@ def main():
         torch.cuda.synchronize()
         tl, ops.KERNEL_TIMELINE = ops.KERNEL_TIMELINE, None
         agg = {}
-        for kind, flops, s, e in tl:
+        for kind, flops, s, e, *_ in tl:
             a = agg.setdefault(kind, [0.0, 0.0, 0])
             a[0] += flops
             a[1] += s.elapsed_time(e)

@@ -13,8 +13,12 @@
 //   warp 1      MMA issuer:   tcgen05.mma.kind::f8f6f4 (M=128, N=BN, K=32), fp32 accumulators in TMEM,
 //               two accumulator buffers so tile i+1's MMAs overlap tile i's epilogue
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue: tcgen05.ld (thread == output row), dequant scale + bias -> bf16 rounding ->
-//               fused op -> vectorised global stores.  Warps 4-7 own columns [0,BN/2), 8-11 the rest.
+//   warps 4-19  epilogue: tcgen05.ld (thread == output row), dequant scale + bias -> bf16 rounding ->
+//               fused op -> vectorised global stores.  Warp w owns TMEM lanes 32*(w%4).. and the column quarter
+//               (w-4)/4 of the tile.  Sixteen warps, not eight: the epilogue is latency-bound (TMEM load -> math ->
+//               L2 round trips), and with K = 3072 a tile's mainloop is only ~9 us, so eight warps (two per
+//               scheduler) took longer than the MMAs they hide behind (profiles/r1_gemm_epilogue.md).  Registers
+//               are re-partitioned with setmaxnreg: 56 for the producer / issuer warpgroup, 104 for the epilogue.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -27,8 +31,9 @@ namespace fb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 128;  // bytes == fp8 elements: one SWIZZLE_128B span
-constexpr int kGemmThreads = 384;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 16;
+constexpr int kGemmThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 640 -> 96 registers per thread at launch
 constexpr int kHeadDim = 128;
 
 template <int BN, int CG>
@@ -39,9 +44,11 @@ struct GemmSmem {
   static constexpr int kB = kBRows * kBK;
   static constexpr int kStage = kA + kB;
   static constexpr int kBarOff = kStages * kStage;
-  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr, norm weights (2*128 fp32)
+  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr, norm weights (2 problems * 2*128 fp32),
+  // partial sums of squares exchanged between the two warps that share a head row (2 buffers * 4 parts * 128 rows)
   static constexpr int kNormOff = kBarOff + 256;
-  static constexpr int kTotal = kNormOff + 2 * 2 * kHeadDim * 4 + 1024 /*alignment slack*/;
+  static constexpr int kSsOff = kNormOff + 2 * 2 * kHeadDim * 4;
+  static constexpr int kTotal = kSsOff + 2 * 4 * kBM * 4 + 1024 /*alignment slack*/;
 };
 
 // Up to two problems that share N, K, formats and epilogue (the txt and img streams of a DoubleStreamBlock) run
@@ -183,18 +190,23 @@ __device__ __forceinline__ void epi_gelu_quant(const fluxb200_gemm_args& g, cons
   }
 }
 
-// One thread owns one (row, head): 128 accumulator columns starting at TMEM address `taddr`.
-// which: 0 = q, 1 = k (RMSNorm + RoPE), 2 = v (copy).
+// One thread owns one row and HALF a head: 64 accumulator columns starting at TMEM address `taddr` (tile column
+// `col0`); the warp `part ^ 1` of the same lane group owns the other half.  which: 0 = q, 1 = k (RMSNorm + RoPE),
+// 2 = v (copy).  The RMS statistic is the sum of the two threads' partial sums, exchanged through `ss_sm`
+// ([4 parts][128 rows], double-buffered by the caller) and a 64-thread named barrier `bar_id`.
 __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const RowInfo& ri, uint32_t taddr, int col0,
-                                             float s, const float* norm_smem) {
+                                             float s, const float* norm_smem, float* ss_sm, int part, int row_in_cta,
+                                             uint32_t bar_id) {
   const int hd = g.num_heads * kHeadDim;
   const int which = col0 / hd;
-  const int head = (col0 - which * hd) / kHeadDim;
+  const int within = col0 - which * hd;
+  const int head = within / kHeadDim;
+  const int hoff = within - head * kHeadDim;  // 0 or 64
   const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? g.q : (which == 1 ? g.k : g.v));
   const int64_t spos = static_cast<int64_t>(g.seq_offset) + ri.pos;
   __nv_bfloat16* dst =
-      base + ((static_cast<int64_t>(ri.b) * g.num_heads + head) * g.seq_total + spos) * kHeadDim;
+      base + ((static_cast<int64_t>(ri.b) * g.num_heads + head) * g.seq_total + spos) * kHeadDim + hoff;
 
   uint32_t v[32];
   float y[32];
@@ -203,22 +215,27 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
     // pass 1: fp32 sum of squares of the bf16-rounded linear output (F.rms_norm on x.float())
     float ss = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       tmem_ld32(taddr + c * 32, v);
       tmem_ld_wait();
       dequant_bias(v, s, bias, col0 + c * 32, y);
 #pragma unroll
       for (int j = 0; j < 32; ++j) ss = fmaf(y[j], y[j], ss);
     }
+    ss_sm[part * kBM + row_in_cta] = ss;
+    named_bar_sync(bar_id, 64);
+    const float other = ss_sm[(part ^ 1) * kBM + row_in_cta];
+    // both threads form the same sum: lower half + upper half
+    ss = (part & 1) ? other + ss : ss + other;
     rinv = rsqrtf(ss * (1.f / kHeadDim) + 1e-6f);
   }
-  const float* nw = norm_smem + which * kHeadDim;  // only read when which < 2
+  const float* nw = norm_smem + which * kHeadDim + hoff;  // only read when which < 2
   const __nv_bfloat16* cosp = reinterpret_cast<const __nv_bfloat16*>(g.rope_cos) +
-                              static_cast<int64_t>(ri.b) * g.rope_batch_stride + spos * (kHeadDim / 2);
+                              static_cast<int64_t>(ri.b) * g.rope_batch_stride + spos * (kHeadDim / 2) + hoff / 2;
   const __nv_bfloat16* sinp = reinterpret_cast<const __nv_bfloat16*>(g.rope_sin) +
-                              static_cast<int64_t>(ri.b) * g.rope_batch_stride + spos * (kHeadDim / 2);
+                              static_cast<int64_t>(ri.b) * g.rope_batch_stride + spos * (kHeadDim / 2) + hoff / 2;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     tmem_ld32(taddr + c * 32, v);
     tmem_ld_wait();
     dequant_bias(v, s, bias, col0 + c * 32, y);
@@ -268,6 +285,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* norm_smem = reinterpret_cast<float*>(smem + S::kNormOff);
+  float* ss_smem = reinterpret_cast<float*>(smem + S::kSsOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -287,7 +305,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8 * CG);  // one arrive per epilogue warp (of both CTAs for CG == 2)
+      mbar_init(&tempty_bar[i], kEpiWarps * CG);  // one arrive per epilogue warp (of both CTAs for CG == 2)
     }
     fence_mbar_init();
   }
@@ -322,6 +340,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   // Producer and issuer run their loops warp-uniformly; only the TMA / MMA / commit instructions are predicated on
   // one elected lane, so descriptors and addresses stay in uniform registers (a `lane == 0` loop makes ptxas wrap
   // every UTMALDG / UTCQMMA in a vector->uniform waterfall loop).
+  // 640 threads launch with 96 registers each; the producer / issuer warpgroup needs few, the epilogue many
+  if (warp < kEpiWarp0) {
+  setmaxnreg_dec<56>();
   if (warp == 0) {
     // ---- TMA producer (both CTAs of a pair: each loads its own A rows and its half of the W rows) ----
     int stage = 0;
@@ -401,10 +422,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
         }
       }
     }
-  } else if (warp >= kEpiWarp0) {
-    const int lg = warp & 3;                 // TMEM lane group of this warp
-    const int half = (warp - kEpiWarp0) >> 2;  // which half of the BN columns
-    constexpr int kHalfCols = BN / 2;
+  }
+  } else {
+    setmaxnreg_inc<104>();
+    const int lg = warp & 3;                   // TMEM lane group of this warp
+    const int part = (warp - kEpiWarp0) >> 2;  // which quarter of the BN columns
+    constexpr int kPartCols = BN / 4;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
@@ -418,26 +441,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
       const int n0 = tc.n_blk * BN;
       RowInfo ri;
       ri.row = m0 + lg * 32 + lane;
-      ri.valid = ri.row < g.M;
+      ri.valid = ri.row < g.M && P.debug != 4;  // debug 4: TMEM loads + dequant only, no epilogue math / stores
       ri.b = ri.row / rpb;
       ri.pos = ri.row - ri.b * rpb;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN + half * kHalfCols;
-      const int col0 = n0 + half * kHalfCols;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN + part * kPartCols;
+      const int col0 = n0 + part * kPartCols;
 
       bool qkv_path = (EPI == FLUXB200_EPI_QKV_ROPE);
       if constexpr (EPI == FLUXB200_EPI_LINEAR1) qkv_path = col0 < 3 * g.num_heads * kHeadDim;
-      if (qkv_path) {
+      if (P.debug == 3) {
+        // debug 3: no epilogue at all (accumulator released at once): isolates the TMA + MMA pipeline
+      } else if (qkv_path) {
         if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
-          static_assert(kHalfCols == kHeadDim || (EPI != FLUXB200_EPI_QKV_ROPE && EPI != FLUXB200_EPI_LINEAR1),
+          static_assert(2 * kPartCols == kHeadDim || (EPI != FLUXB200_EPI_QKV_ROPE && EPI != FLUXB200_EPI_LINEAR1),
                         "QKV epilogues need BN == 256");
-          epi_qkv_head(g, ri, taddr, col0, s, norm_smem + tc.pi * 2 * kHeadDim);
+          epi_qkv_head(g, ri, taddr, col0, s, norm_smem + tc.pi * 2 * kHeadDim, ss_smem + as * 4 * kBM, part,
+                       lg * 32 + lane, 1 + lg * 2 + (part >> 1));
         }
       } else {
         const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
 #pragma unroll 1
-        for (int c = 0; c < kHalfCols / 32; ++c) {
+        for (int c = 0; c < kPartCols / 32; ++c) {
           uint32_t v[32];
           float y[32];
           const int col = col0 + c * 32;
@@ -466,7 +492,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_remote(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
+        if constexpr (CG == 2) mbar_arrive_remote_relaxed(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
       }
       if (++as == 2) {
         as = 0;

@@ -39,6 +39,16 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// Register re-partitioning between warpgroups (all four warps of a warpgroup execute it together).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -169,6 +179,20 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
+}
+
+// Same, without release semantics.  `.release.cluster` compiles to MEMBAR.ALL.GPU in front of the arrive: the warp
+// then sits until every global store it has issued is acknowledged by L2.  Handing a TMEM accumulator back needs no
+// memory ordering at all (tcgen05.wait::ld has already put the data in registers; tcgen05.fence::before_thread_sync
+// orders the tensor-memory reads), so the GEMM epilogue uses this form and lets its stores drain in the background.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta));
 }
 
 // ---------------------------------------------------------------------------------------------

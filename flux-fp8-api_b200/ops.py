@@ -170,7 +170,7 @@ def gemm_args(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tenso
     return g
 
 
-def _timed(kind: str, flops: float, launch) -> None:
+def _timed(kind: str, flops: float, launch, detail: str = "") -> None:
     if KERNEL_TIMELINE is None:
         launch()
         return
@@ -178,12 +178,20 @@ def _timed(kind: str, flops: float, launch) -> None:
     s.record()
     launch()
     e.record()
-    KERNEL_TIMELINE.append((kind, flops, s, e))
+    KERNEL_TIMELINE.append((kind, flops, s, e, detail))
+
+
+_EPI_NAMES = {0: "plain", 1: "gate_residual", 2: "gelu_quant", 3: "qkv_rope", 4: "linear1"}
+
+
+def _gemm_detail(gs) -> str:
+    return _EPI_NAMES.get(gs[0].epilogue, "?") + " " + " + ".join(f"{g.M}x{g.N}x{g.K}" for g in gs)
 
 
 def run_gemm(g: cabi.GemmArgs) -> None:
     _timed("f8_gemm", 2.0 * g.M * g.N * g.K,
-           lambda: cabi.check(cabi.load().fluxb200_f8_gemm(C.byref(g), cabi.stream_ptr()), "fluxb200_f8_gemm"))
+           lambda: cabi.check(cabi.load().fluxb200_f8_gemm(C.byref(g), cabi.stream_ptr()), "fluxb200_f8_gemm"),
+           _gemm_detail([g]) if KERNEL_TIMELINE is not None else "")
 
 
 def run_gemm_group(gs) -> None:
@@ -194,7 +202,8 @@ def run_gemm_group(gs) -> None:
     arr = (cabi.GemmArgs * len(gs))(*gs)
     _timed("f8_gemm", sum(2.0 * g.M * g.N * g.K for g in gs),
            lambda: cabi.check(cabi.load().fluxb200_f8_gemm_grouped(arr, len(gs), cabi.stream_ptr()),
-                              "fluxb200_f8_gemm_grouped"))
+                              "fluxb200_f8_gemm_grouped"),
+           _gemm_detail(gs) if KERNEL_TIMELINE is not None else "")
 
 
 def f8_gemm(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tensor, w_scale_recip: Tensor,
