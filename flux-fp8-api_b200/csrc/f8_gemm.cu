@@ -112,6 +112,35 @@ __device__ __forceinline__ void dequant_bias(const uint32_t (&v)[32], float s, c
   }
 }
 
+// Same, leaving the 32 results as 16 packed bf16 pairs: one F2FP per two values does the rounding AND the packing
+// (the float form above pays one conversion per value plus the packing at the store).
+__device__ __forceinline__ void dequant_bias_packed(const uint32_t (&v)[32], float s, const __nv_bfloat16* bias, int col,
+                                                    uint32_t (&yp)[16]) {
+  if (bias != nullptr) {
+    const uint4* bp = reinterpret_cast<const uint4*>(bias + col);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 bb = __ldg(bp + q);
+      uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 bf = unpack_bf16x2(w[t]);
+        yp[q * 4 + t] = pack_bf16x2(fmaf(__uint_as_float(v[q * 8 + t * 2 + 0]), s, bf.x),
+                                    fmaf(__uint_as_float(v[q * 8 + t * 2 + 1]), s, bf.y));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) yp[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * s, __uint_as_float(v[2 * j + 1]) * s);
+  }
+}
+
+__device__ __forceinline__ void store_packed_bf16x32(__nv_bfloat16* dst, const uint32_t (&yp)[16]) {
+  uint4* op = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) op[q] = make_uint4(yp[q * 4], yp[q * 4 + 1], yp[q * 4 + 2], yp[q * 4 + 3]);
+}
+
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&y)[32]) {
   uint4* op = reinterpret_cast<uint4*>(dst);
 #pragma unroll
@@ -152,8 +181,11 @@ __device__ __forceinline__ void epi_plain(const fluxb200_gemm_args& g, const Row
   }
 }
 
+// x + gate * y on packed bf16 pairs: HMUL2 rounds the exact product once (== fp32 multiply of two bf16 values, which is
+// exact, then the bf16 rounding of the eager op); HADD2 rounds the exact sum once (the eager op adds in fp32 and rounds:
+// identical unless the fp32 add itself had to round, i.e. operands > 2^16 apart, and then only on a tie).
 __device__ __forceinline__ void epi_gate_residual(const fluxb200_gemm_args& g, const RowInfo& ri, int col,
-                                                  float (&y)[32]) {
+                                                  uint32_t (&yp)[16]) {
   const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.gate) +
                                                    static_cast<int64_t>(ri.b) * g.gate_batch_stride + col);
   const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.resid) +
@@ -166,28 +198,45 @@ __device__ __forceinline__ void epi_gate_residual(const fluxb200_gemm_args& g, c
     uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      float2 gf = unpack_bf16x2(gw[t]);
-      float2 rf = unpack_bf16x2(rw[t]);
-      int j = q * 8 + t * 2;
-      y[j] = rf.x + bf16r(gf.x * y[j]);  // rounded to bf16 by the store
-      y[j + 1] = rf.y + bf16r(gf.y * y[j + 1]);
+      const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yp[q * 4 + t]);
+      const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[t]);
+      const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[t]);
+      const __nv_bfloat162 o2 = __hadd2_rn(r2, __hmul2_rn(g2, y2));
+      yp[q * 4 + t] = *reinterpret_cast<const uint32_t*>(&o2);
     }
   }
-  store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, y);
+  store_packed_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, yp);
+}
+
+template <int FMT>
+__device__ __forceinline__ void gelu_quant_store(uint8_t* dst, float oscale, bool scale_is_bf16, float (&y)[32]) {
+  if (scale_is_bf16) {
+    // bf16(gelu) * scale -> bf16 -> fp8 on packed pairs (quant_pair_bf16scale)
+    const __nv_bfloat162 s2 = __floats2bfloat162_rn(oscale, oscale);
+    uint4* op = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = q * 16 + t * 4;
+        w[t] = static_cast<uint32_t>(quant_pair_bf16scale<FMT>(gelu_tanh_fast(y[j]), gelu_tanh_fast(y[j + 1]), s2)) |
+               (static_cast<uint32_t>(quant_pair_bf16scale<FMT>(gelu_tanh_fast(y[j + 2]), gelu_tanh_fast(y[j + 3]), s2)) << 16);
+      }
+      op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = quant_pre<FMT>(bf16r(gelu_tanh_fast(y[j])), oscale);
+    store_fp8x32<FMT>(dst, y);
+  }
 }
 
 __device__ __forceinline__ void epi_gelu_quant(const fluxb200_gemm_args& g, const RowInfo& ri, int out_col, float oscale,
-                                               float (&y)[32]) {
+                                               bool scale_is_bf16, float (&y)[32]) {
   uint8_t* dst = reinterpret_cast<uint8_t*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + out_col;
-  if (g.out_fmt == FLUXB200_E5M2) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = quant_pre<1>(bf16r(gelu_tanh(y[j])), oscale);
-    store_fp8x32<1>(dst, y);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = quant_pre<0>(bf16r(gelu_tanh(y[j])), oscale);
-    store_fp8x32<0>(dst, y);
-  }
+  if (g.out_fmt == FLUXB200_E5M2) gelu_quant_store<1>(dst, oscale, scale_is_bf16, y);
+  else gelu_quant_store<0>(dst, oscale, scale_is_bf16, y);
 }
 
 // One thread owns one row and HALF a head: 64 accumulator columns starting at TMEM address `taddr` (tile column
@@ -240,7 +289,9 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
     tmem_ld_wait();
     dequant_bias(v, s, bias, col0 + c * 32, y);
     if (which < 2 && ri.valid) {
-      // RMSNorm (fp32) -> bf16, then RoPE on interleaved pairs with bf16 products and sum
+      // RMSNorm (fp32) -> bf16, then RoPE on interleaved pairs with bf16 products and sum, on packed pairs:
+      //   X = (x0, x1), Xs = (x1, x0);  out = HADD2( HMUL2(X, (cos, cos)), HMUL2(Xs, (-sin, sin)) )
+      //       = ( bf16(cos x0) + bf16(-sin x1),  bf16(cos x1) + bf16(sin x0) )        (modules/flux_model.py:60-65)
       uint4 cw[2], sw[2];
       const uint4* cp = reinterpret_cast<const uint4*>(cosp + c * 16);
       const uint4* sp = reinterpret_cast<const uint4*>(sinp + c * 16);
@@ -250,22 +301,26 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
       sw[1] = __ldg(sp + 1);
       const uint32_t* cu = reinterpret_cast<const uint32_t*>(cw);
       const uint32_t* su = reinterpret_cast<const uint32_t*>(sw);
+      uint32_t op[16];
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        float2 cf = unpack_bf16x2(cu[t]);
-        float2 sf = unpack_bf16x2(su[t]);
-        float cc[2] = {cf.x, cf.y};
-        float sn[2] = {sf.x, sf.y};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          int j = t * 4 + u * 2;
-          float x0 = bf16r(y[j] * rinv * nw[c * 32 + j]);
-          float x1 = bf16r(y[j + 1] * rinv * nw[c * 32 + j + 1]);
-          // out0 = cos*x0 + (-sin)*x1 ; out1 = sin*x0 + cos*x1   (modules/flux_model.py:60-65)
-          y[j] = bf16r(cc[u] * x0) + bf16r(-sn[u] * x1);
-          y[j + 1] = bf16r(sn[u] * x0) + bf16r(cc[u] * x1);
+          const int j = t * 4 + u * 2;
+          const uint32_t x = pack_bf16x2(y[j] * rinv * nw[c * 32 + j], y[j + 1] * rinv * nw[c * 32 + j + 1]);
+          const uint32_t xs = __byte_perm(x, x, 0x1032);
+          // word t of the tables holds pair 2t (low half) and pair 2t+1 (high half)
+          const uint32_t c2 = __byte_perm(cu[t], cu[t], u ? 0x3232 : 0x1010);
+          const uint32_t s2 = __byte_perm(su[t], su[t], u ? 0x3232 : 0x1010) ^ 0x00008000u;  // (-sin, sin)
+          const __nv_bfloat162 o = __hadd2_rn(__hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&x),
+                                                         *reinterpret_cast<const __nv_bfloat162*>(&c2)),
+                                              __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&xs),
+                                                         *reinterpret_cast<const __nv_bfloat162*>(&s2)));
+          op[t * 2 + u] = *reinterpret_cast<const uint32_t*>(&o);
         }
       }
+      store_packed_bf16x32(dst + c * 32, op);
+      continue;
     }
     if (ri.valid) store_bf16x32(dst + c * 32, y);
   }
@@ -436,6 +491,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
       const float s = __ldg(g.a_scale_recip) * __ldg(g.w_scale_recip);
       float oscale = 0.f;
       if constexpr (EPI == FLUXB200_EPI_GELU_QUANT || EPI == FLUXB200_EPI_LINEAR1) oscale = __ldg(g.out_scale);
+      const bool oscale_is_bf16 = bf16r(oscale) == oscale;
       const int rpb = g.rows_per_batch > 0 ? g.rows_per_batch : g.M;
       const int m0 = tc.m_blk * kTileM + cta_rank * kBM;
       const int n0 = tc.n_blk * BN;
@@ -465,27 +521,37 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
 #pragma unroll 1
         for (int c = 0; c < kPartCols / 32; ++c) {
           uint32_t v[32];
-          float y[32];
           const int col = col0 + c * 32;
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
           if (col >= g.N) continue;  // warp-uniform
           const bool full_cols = col + 32 <= g.N;
-          dequant_bias(v, s, full_cols ? bias : nullptr, col, y);
-          if (!full_cols && bias != nullptr) {
+          if constexpr (EPI == FLUXB200_EPI_GATE_RESIDUAL) {
+            // (N % 32 == 0 is validated on the host for this epilogue)
+            uint32_t yp[16];
+            dequant_bias_packed(v, s, bias, col, yp);
+            if (ri.valid) epi_gate_residual(g, ri, col, yp);
+          } else if (EPI == FLUXB200_EPI_PLAIN && full_cols) {
+            uint32_t yp[16];
+            dequant_bias_packed(v, s, bias, col, yp);
+            if (ri.valid)
+              store_packed_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, yp);
+          } else {
+            float y[32];
+            dequant_bias(v, s, full_cols ? bias : nullptr, col, y);
+            if (!full_cols && bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col + j < g.N) y[j] = bf16r(fmaf(__uint_as_float(v[j]), s, __bfloat162float(bias[col + j])));
-          }
-          if (!ri.valid) continue;
-          if constexpr (EPI == FLUXB200_EPI_PLAIN) {
-            epi_plain(g, ri, col, y);
-          } else if constexpr (EPI == FLUXB200_EPI_GATE_RESIDUAL) {
-            epi_gate_residual(g, ri, col, y);
-          } else if constexpr (EPI == FLUXB200_EPI_GELU_QUANT) {
-            epi_gelu_quant(g, ri, g.out_col_offset + col, oscale, y);
-          } else if constexpr (EPI == FLUXB200_EPI_LINEAR1) {
-            epi_gelu_quant(g, ri, g.out_col_offset + col - 3 * g.num_heads * kHeadDim, oscale, y);
+              for (int j = 0; j < 32; ++j)
+                if (col + j < g.N) y[j] = bf16r(fmaf(__uint_as_float(v[j]), s, __bfloat162float(bias[col + j])));
+            }
+            if (!ri.valid) continue;
+            if constexpr (EPI == FLUXB200_EPI_PLAIN) {
+              epi_plain(g, ri, col, y);
+            } else if constexpr (EPI == FLUXB200_EPI_GELU_QUANT) {
+              epi_gelu_quant(g, ri, g.out_col_offset + col, oscale, oscale_is_bf16, y);
+            } else if constexpr (EPI == FLUXB200_EPI_LINEAR1) {
+              epi_gelu_quant(g, ri, g.out_col_offset + col - 3 * g.num_heads * kHeadDim, oscale, oscale_is_bf16, y);
+            }
           }
         }
       }

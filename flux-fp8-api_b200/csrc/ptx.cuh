@@ -411,6 +411,35 @@ __device__ __forceinline__ float quant_pre(float x_bf16_exact, float scale) {
   float p = bf16r(x_bf16_exact * scale);
   return fminf(fmaxf(p, -kMax), kMax);
 }
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// The same quantiser on a PAIR, for a scale that is itself a bf16 value (always true under torch's CUDA scalar
+// semantics): bf16(x*s) is one packed HMUL2 (the fp32 product of two bf16 values is exact, so
+// rounding it once equals the reference's fp32 multiply + bf16 rounding), and the saturating fp8 conversion
+// subsumes the clamp.  x pair given as fp32 values still to be rounded to bf16.
+template <int FMT>
+__device__ __forceinline__ uint16_t quant_pair_bf16scale(float x0, float x1, __nv_bfloat162 s2) {
+  const __nv_bfloat162 p = __hmul2_rn(__floats2bfloat162_rn(x0, x1), s2);
+  const float2 pf = __bfloat1622float2(p);
+  return to_fp8x2<FMT>(pf.x, pf.y);
+}
+// 0.5 x (1 + tanh(u)) == x * sigmoid(2u) == x / (1 + 2^(-2 u log2 e)):  8 instructions instead of 12.
+// u = sqrt(2/pi) (x + 0.044715 x^3).  Saturates cleanly: 2^(+big) = inf -> x * 0, 2^(-big) = 0 -> x * 1.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  constexpr float kC0 = -2.f * 1.4426950408889634f * 0.7978845608028654f;            // -2 log2(e) sqrt(2/pi)
+  constexpr float kC1 = kC0 * 0.044715f;
+  const float w = fmaf(x * x, kC1, kC0);
+  const float e = exp2f_approx(x * w);
+  return x * rcp_approx(1.f + e);
+}
 // nn.GELU(approximate="tanh") evaluated in fp32 (ATen opmath) on a bf16-exact input.
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float kBeta = 0.7978845608028654f;  // sqrt(2/pi)
