@@ -244,7 +244,7 @@ __device__ __forceinline__ void epi_gelu_quant(const fluxb200_gemm_args& g, cons
 // 2 = v (copy).  The RMS statistic is the sum of the two threads' partial sums, exchanged through `ss_sm`
 // ([4 parts][128 rows], double-buffered by the caller) and a 64-thread named barrier `bar_id`.
 __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const RowInfo& ri, uint32_t taddr, int col0,
-                                             float s, const float* norm_smem, float* ss_sm, int part, int row_in_cta,
+                                             float s, uint32_t norm_saddr, uint32_t ss_saddr, int part, int row_in_cta,
                                              uint32_t bar_id) {
   const int hd = g.num_heads * kHeadDim;
   const int which = col0 / hd;
@@ -257,72 +257,90 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
   __nv_bfloat16* dst =
       base + ((static_cast<int64_t>(ri.b) * g.num_heads + head) * g.seq_total + spos) * kHeadDim + hoff;
 
-  uint32_t v[32];
-  float y[32];
-  float rinv = 1.f;
-  if (which < 2) {
-    // pass 1: fp32 sum of squares of the bf16-rounded linear output (F.rms_norm on x.float())
-    float ss = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      tmem_ld32(taddr + c * 32, v);
-      tmem_ld_wait();
-      dequant_bias(v, s, bias, col0 + c * 32, y);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) ss = fmaf(y[j], y[j], ss);
-    }
-    ss_sm[part * kBM + row_in_cta] = ss;
-    named_bar_sync(bar_id, 64);
-    const float other = ss_sm[(part ^ 1) * kBM + row_in_cta];
-    // both threads form the same sum: lower half + upper half
-    ss = (part & 1) ? other + ss : ss + other;
-    rinv = rsqrtf(ss * (1.f / kHeadDim) + 1e-6f);
-  }
-  const float* nw = norm_smem + which * kHeadDim + hoff;  // only read when which < 2
+  // The thread's 64 linear outputs, bf16-rounded, stay packed in registers between the statistic and the rotation
+  // (one TMEM read and one de-quantisation instead of two of each).
+  uint32_t yp[2][16];
   const __nv_bfloat16* cosp = reinterpret_cast<const __nv_bfloat16*>(g.rope_cos) +
                               static_cast<int64_t>(ri.b) * g.rope_batch_stride + spos * (kHeadDim / 2) + hoff / 2;
   const __nv_bfloat16* sinp = reinterpret_cast<const __nv_bfloat16*>(g.rope_sin) +
                               static_cast<int64_t>(ri.b) * g.rope_batch_stride + spos * (kHeadDim / 2) + hoff / 2;
-#pragma unroll 1
+  if (which < 2 && ri.valid) {
+    // the row's 64 B of cos and of sin come from L2 (~1 us away): start them now, use them after the barrier
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(cosp));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(sinp));
+  }
+  float ss = 0.f;
+#pragma unroll
   for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
     tmem_ld32(taddr + c * 32, v);
     tmem_ld_wait();
-    dequant_bias(v, s, bias, col0 + c * 32, y);
-    if (which < 2 && ri.valid) {
-      // RMSNorm (fp32) -> bf16, then RoPE on interleaved pairs with bf16 products and sum, on packed pairs:
-      //   X = (x0, x1), Xs = (x1, x0);  out = HADD2( HMUL2(X, (cos, cos)), HMUL2(Xs, (-sin, sin)) )
-      //       = ( bf16(cos x0) + bf16(-sin x1),  bf16(cos x1) + bf16(sin x0) )        (modules/flux_model.py:60-65)
-      uint4 cw[2], sw[2];
-      const uint4* cp = reinterpret_cast<const uint4*>(cosp + c * 16);
-      const uint4* sp = reinterpret_cast<const uint4*>(sinp + c * 16);
-      cw[0] = __ldg(cp);
-      cw[1] = __ldg(cp + 1);
-      sw[0] = __ldg(sp);
-      sw[1] = __ldg(sp + 1);
-      const uint32_t* cu = reinterpret_cast<const uint32_t*>(cw);
-      const uint32_t* su = reinterpret_cast<const uint32_t*>(sw);
-      uint32_t op[16];
+    dequant_bias_packed(v, s, bias, col0 + c * 32, yp[c]);
+    if (which < 2) {
+      // fp32 sum of squares of the bf16-rounded linear output (F.rms_norm on x.float())
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int j = t * 4 + u * 2;
-          const uint32_t x = pack_bf16x2(y[j] * rinv * nw[c * 32 + j], y[j + 1] * rinv * nw[c * 32 + j + 1]);
-          const uint32_t xs = __byte_perm(x, x, 0x1032);
-          // word t of the tables holds pair 2t (low half) and pair 2t+1 (high half)
-          const uint32_t c2 = __byte_perm(cu[t], cu[t], u ? 0x3232 : 0x1010);
-          const uint32_t s2 = __byte_perm(su[t], su[t], u ? 0x3232 : 0x1010) ^ 0x00008000u;  // (-sin, sin)
-          const __nv_bfloat162 o = __hadd2_rn(__hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&x),
-                                                         *reinterpret_cast<const __nv_bfloat162*>(&c2)),
-                                              __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&xs),
-                                                         *reinterpret_cast<const __nv_bfloat162*>(&s2)));
-          op[t * 2 + u] = *reinterpret_cast<const uint32_t*>(&o);
-        }
+      for (int j = 0; j < 16; ++j) {
+        const float2 f = unpack_bf16x2(yp[c][j]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
       }
-      store_packed_bf16x32(dst + c * 32, op);
-      continue;
     }
-    if (ri.valid) store_bf16x32(dst + c * 32, y);
+  }
+  if (which == 2) {
+    if (ri.valid) {
+      store_packed_bf16x32(dst, yp[0]);
+      store_packed_bf16x32(dst + 32, yp[1]);
+    }
+    return;
+  }
+  sts_f32(ss_saddr + (part * kBM + row_in_cta) * 4, ss);
+  named_bar_sync(bar_id, 64);
+  const float other = lds_f32(ss_saddr + ((part ^ 1) * kBM + row_in_cta) * 4);
+  // both threads form the same sum: lower half + upper half
+  ss = (part & 1) ? other + ss : ss + other;
+  const float rinv = rsqrtf(ss * (1.f / kHeadDim) + 1e-6f);
+  if (!ri.valid) return;
+  const uint32_t nw_saddr = norm_saddr + (which * kHeadDim + hoff) * 4;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float nw[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 w4 = lds_f32x4(nw_saddr + (c * 32 + q * 4) * 4);
+      nw[q * 4 + 0] = w4.x, nw[q * 4 + 1] = w4.y, nw[q * 4 + 2] = w4.z, nw[q * 4 + 3] = w4.w;
+    }
+    // RMSNorm (fp32) -> bf16, then RoPE on interleaved pairs with bf16 products and sum, on packed pairs:
+    //   X = (x0, x1), Xs = (x1, x0);  out = HADD2( HMUL2(X, (cos, cos)), HMUL2(Xs, (-sin, sin)) )
+    //       = ( bf16(cos x0) + bf16(-sin x1),  bf16(cos x1) + bf16(sin x0) )        (modules/flux_model.py:60-65)
+    uint4 cw[2], sw[2];
+    const uint4* cp = reinterpret_cast<const uint4*>(cosp + c * 16);
+    const uint4* sp = reinterpret_cast<const uint4*>(sinp + c * 16);
+    cw[0] = __ldg(cp);
+    cw[1] = __ldg(cp + 1);
+    sw[0] = __ldg(sp);
+    sw[1] = __ldg(sp + 1);
+    const uint32_t* cu = reinterpret_cast<const uint32_t*>(cw);
+    const uint32_t* su = reinterpret_cast<const uint32_t*>(sw);
+    uint32_t op[16];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = t * 4 + u * 2;
+        const float2 yf = unpack_bf16x2(yp[c][t * 2 + u]);
+        const uint32_t x = pack_bf16x2(yf.x * rinv * nw[j], yf.y * rinv * nw[j + 1]);
+        const uint32_t xs = __byte_perm(x, x, 0x1032);
+        // word t of the tables holds pair 2t (low half) and pair 2t+1 (high half)
+        const uint32_t c2 = __byte_perm(cu[t], cu[t], u ? 0x3232 : 0x1010);
+        const uint32_t s2 = __byte_perm(su[t], su[t], u ? 0x3232 : 0x1010) ^ 0x00008000u;  // (-sin, sin)
+        const __nv_bfloat162 o = __hadd2_rn(__hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&x),
+                                                       *reinterpret_cast<const __nv_bfloat162*>(&c2)),
+                                            __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&xs),
+                                                       *reinterpret_cast<const __nv_bfloat162*>(&s2)));
+        op[t * 2 + u] = *reinterpret_cast<const uint32_t*>(&o);
+      }
+    }
+    store_packed_bf16x32(dst + c * 32, op);
   }
 }
 
@@ -513,8 +531,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
         if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
           static_assert(2 * kPartCols == kHeadDim || (EPI != FLUXB200_EPI_QKV_ROPE && EPI != FLUXB200_EPI_LINEAR1),
                         "QKV epilogues need BN == 256");
-          epi_qkv_head(g, ri, taddr, col0, s, norm_smem + tc.pi * 2 * kHeadDim, ss_smem + as * 4 * kBM, part,
-                       lg * 32 + lane, 1 + lg * 2 + (part >> 1));
+          epi_qkv_head(g, ri, taddr, col0, s, smem_u32(norm_smem) + tc.pi * 2 * kHeadDim * 4,
+                       smem_u32(ss_smem) + as * 4 * kBM * 4, part, lg * 32 + lane, 1 + lg * 2 + (part >> 1));
         }
       } else {
         const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);

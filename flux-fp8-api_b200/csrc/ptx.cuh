@@ -39,6 +39,23 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// Explicit shared-space accesses by 32-bit shared address.  The dynamic shared buffer is re-aligned with integer
+// arithmetic, after which the compiler only knows a GENERIC pointer and emits LD.E / ST.E through the global-memory
+// pipe (and its LG throttle) for what are shared-memory reads.
+__device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
 // Register re-partitioning between warpgroups (all four warps of a warpgroup execute it together).
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {

@@ -46,3 +46,21 @@ if which in ("gate", "all"):
     out = torch.empty(M, N, dtype=BF16, device=dev)
     ms = timed(lambda: ops.f8_gemm_gate_residual(a, w, bias, sa, sw, resid, gate, M, out=out))
     print(f"gate_residual {M}x{N}x{K}: {ms*1e3:.1f} us {2*M*N*K/ms/1e9:.0f} TFLOP/s")
+if which in ("qkv", "all"):
+    import math
+    from oracle import flux_oracle as O
+    B, L, T, H, K = 1, 4096, 512, 24, 3072
+    S, D = L + T, H * 128
+    N, M = 3 * D, B * L
+    a = (torch.randn(M, K, device=dev) * 4).to(BF16).to(E5M2)
+    w = (torch.randn(N, K, device=dev) * 0.5).to(BF16).to(E4M3)
+    bias = (torch.randn(N, device=dev) * 0.5).to(BF16)
+    qw = (1 + 0.05 * torch.randn(128, device=dev)).float()
+    kw = (1 + 0.05 * torch.randn(128, device=dev)).float()
+    ids = torch.cat((torch.zeros(1, T, 3), O.make_img_ids(1, 64, 64, torch.float32)), 1).to(BF16).to(dev)
+    pe = O.embed_nd(ids, [16, 56, 56], 10000, BF16)
+    cos, sin = pe[:, 0, :, :, 0, 0].contiguous(), pe[:, 0, :, :, 1, 0].contiguous()
+    q = torch.zeros(B, H, S, 128, dtype=BF16, device=dev)
+    k, v = torch.zeros_like(q), torch.zeros_like(q)
+    ms = timed(lambda: ops.f8_gemm_qkv_rope(a, w, bias, sa, sw, q, k, v, qw, kw, cos, sin, L, T))
+    print(f"qkv_rope {M}x{N}x{K}: {ms*1e3:.1f} us {2*M*N*K/ms/1e9:.0f} TFLOP/s")
