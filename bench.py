@@ -99,6 +99,18 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's bf16 path (reference flow_dtype=bfloat16, no quantisation) on host cores
 # ------------------------------------------------------------------------------------------------
+def gemm_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per f8_gemm_kernel launch, averaged over the GEMM launches of one
+    step, from the committed ncu capture (profiles/r1_gemm_traffic.json, written by tools/ncu_traffic.py from
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over tests/profile_step.py).  None if absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def cpu_block_sample(threads: int, seed: int = 0):
     """Build one double and one single bf16 block of Flux-dev and return a closure that runs both at the
     1024x1024 sequence length (L=4096, T=512) through the oracle; a step = 19 double + 38 single blocks."""
@@ -316,7 +328,7 @@ def main():
         achieved = gf / (gms * 1e-3) / 1e12
         roof = {
             "bound": "tensor", "kernel": "f8_gemm_kernel (tcgen05 kind::f8f6f4)", "achieved": achieved,
-            "peak": fp8_peak, "unit": "TFLOP/s", "frac": achieved / fp8_peak, "traffic": None,
+            "peak": fp8_peak, "unit": "TFLOP/s", "frac": achieved / fp8_peak, "traffic": gemm_traffic_per_launch(),
             "peak_source": f"2 x bf16_tflops_sustained, {peaks_src}; fp8 tensor rate is twice bf16",
             "launches_per_step": gn // 2, "gemm_ms_per_step": gms / 2, "gemm_share_of_step": (gms / 2) / ms_per_step,
             "attention": {"achieved": af / (ams * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",

@@ -320,6 +320,11 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       const int slot = NQ == 2 ? g : (j & 1);
       const uint32_t sph = NQ == 2 ? (j & 1) : ((j >> 1) & 1);
       if (dbg) tA = clk();
+      if constexpr (FAST && TS) {
+        // PV(j-1) was issued before QK(j): by the time S(j) can be ready this wait has long been satisfied, so taking
+        // it here (instead of between the exponentials and the P store) removes a barrier poll from the S -> P chain
+        if (j > 0) mbar_wait(&o_done[g], (j - 1) & 1);  // O stable, P buffer reusable
+      }
       mbar_wait(&s_ready[slot], sph);
       tc_fence_after();
       if (dbg) { tB = clk(); d_wait_s += tB - tA; tA = tB; }
@@ -339,6 +344,100 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
         for (int i = 0; i < 128; ++i)
           if (i >= kv_left) sv[i] = __float_as_uint(-INFINITY);
       }
+      float alpha = 1.f;
+      bool warp_grow = false;
+      float rs = 0.f;
+      if constexpr (FAST && TS) {
+        // One pass: 3 of 4 exponentials on the MUFU, 1 of 4 on the FMA pipe; bf16 pairs packed in place.  The fp32 work
+        // runs on packed pairs (FFMA2 / FADD2: two IEEE operations per issue slot).
+        // The pass exponentiates against the STALE running max and tracks the maximum exponent it met; only if
+        // some row of the warp ran more than 2^kRescaleThreshold above its stale max (or on the first tile, which
+        // has none) is the tile redone the classic way: max first, rescale, exponentiate.  The separate max pass
+        // was 9 % of the per-tile S -> P -> PV -> S chain that bounds the kernel (profiles/r1_attention_variants.md).
+        auto exp_pass = [&](float neg_m, float& tmax_out) {
+          const float2 sl2v = make_float2(sl2, sl2), negmv = make_float2(neg_m, neg_m);
+          const float2 magic = make_float2(12582912.f, 12582912.f);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+          float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 128; i += 8) {
+            const float2 t01 = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, negmv);
+            const float2 t23 = ffma2(make_float2(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2v, negmv);
+            const float2 t45 = ffma2(make_float2(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])), sl2v, negmv);
+            const float2 t67 = ffma2(make_float2(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])), sl2v, negmv);
+            tm0 = fmaxf(tm0, fmaxf(t01.x, t01.y));
+            tm1 = fmaxf(tm1, fmaxf(t23.x, t23.y));
+            tm0 = fmaxf(tm0, fmaxf(t45.x, t45.y));
+            tm1 = fmaxf(tm1, fmaxf(t67.x, t67.y));
+            const float p0 = fast_exp2_pinned(t01.x), p1 = fast_exp2_pinned(t01.y), p2 = fast_exp2_pinned(t23.x);
+            const float p4 = fast_exp2_pinned(t45.x), p5 = fast_exp2_pinned(t45.y), p6 = fast_exp2_pinned(t67.x);
+            // poly_exp2 on the pair (t23.y, t67.y)
+            const float2 x = make_float2(fmaxf(t23.y, -126.f), fmaxf(t67.y, -126.f));
+            const float2 rr = fadd2(x, magic);
+            const float2 f = fsub2(x, fsub2(rr, magic));
+            float2 pp = ffma2(make_float2(0.05500892f, 0.05500892f), f, make_float2(0.24221096f, 0.24221096f));
+            pp = ffma2(pp, f, make_float2(0.69328293f, 0.69328293f));
+            pp = ffma2(pp, f, make_float2(1.f, 1.f));
+            const float p3 = __int_as_float(__float_as_int(pp.x) + (__float_as_int(rr.x) << 23));
+            const float p7 = __int_as_float(__float_as_int(pp.y) + (__float_as_int(rr.y) << 23));
+            acc0 = fadd2(acc0, make_float2(p0, p1));
+            acc1 = fadd2(acc1, make_float2(p2, p3));
+            acc0 = fadd2(acc0, make_float2(p4, p5));
+            acc1 = fadd2(acc1, make_float2(p6, p7));
+            sv[i >> 1] = pack_bf16x2(p0, p1);
+            sv[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+            sv[(i >> 1) + 2] = pack_bf16x2(p4, p5);
+            sv[(i >> 1) + 3] = pack_bf16x2(p6, p7);
+          }
+          const float2 acc = fadd2(acc0, acc1);
+          tmax_out = fmaxf(tm0, tm1);
+          return acc.x + acc.y;
+        };
+        if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
+        if (NQ == 2 && P.debug != 4) named_bar_sync(1 + g, 256);  // wait for our turn
+        bool redo = j == 0;
+        if (!redo) {
+          float tmax;
+          rs = exp_pass(-m_used, tmax);
+          redo = __any_sync(0xffffffffu, tmax > kRescaleThreshold);
+          if (redo) {  // rare: S is still intact in TMEM (P has not been stored yet)
+            uint32_t(*sv4)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+            tmem_ld32(lane_base + slot * 128 + 0, sv4[0]);
+            tmem_ld32(lane_base + slot * 128 + 32, sv4[1]);
+            tmem_ld32(lane_base + slot * 128 + 64, sv4[2]);
+            tmem_ld32(lane_base + slot * 128 + 96, sv4[3]);
+            tmem_ld_wait();
+            if (kv_left < kBKV) {
+#pragma unroll
+              for (int i = 0; i < 128; ++i)
+                if (i >= kv_left) sv[i] = __float_as_uint(-INFINITY);
+            }
+          }
+        }
+        if (redo) {
+          float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]);
+          float m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
+#pragma unroll
+          for (int i = 4; i < 128; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(sv[i]));
+            m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(sv[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
+          }
+          const float m_cand = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+          // Lazy rescale: keep the stale max unless it is more than 2^8 below the new one.
+          const bool grow = m_cand > m_used + kRescaleThreshold;
+          warp_grow = __any_sync(0xffffffffu, grow);
+          if (warp_grow) {
+            const float m_new = fmaxf(m_used, m_cand);
+            alpha = fast_exp2(m_used - m_new);  // exp2(-inf) = 0 on the first tile
+            m_used = m_new;
+            l *= alpha;
+          }
+          float tmax;
+          rs = exp_pass(-m_used, tmax);
+        }
+      } else {
       float mx;
       if constexpr (FAST) {  // four independent chains instead of one 128-deep dependency chain
         float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]);
@@ -359,34 +458,16 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       const float m_cand = mx * sl2;
       // Lazy rescale: keep the stale max unless it is more than 2^8 below the new one.
       const bool grow = m_cand > m_used + kRescaleThreshold;
-      const bool warp_grow = __any_sync(0xffffffffu, grow);
-      float alpha = 1.f;
+      warp_grow = __any_sync(0xffffffffu, grow);
       if (warp_grow) {
         const float m_new = fmaxf(m_used, m_cand);
         alpha = fast_exp2(m_used - m_new);  // exp2(-inf) = 0 on the first tile
         m_used = m_new;
         l *= alpha;
       }
-      float rs = 0.f;
       const float neg_m = -m_used;
       if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
       if (NQ == 2 && P.debug != 4) named_bar_sync(1 + g, 256);  // wait for our turn
-      if constexpr (FAST && TS) {
-        // one pass: 3 of 4 exponentials on the MUFU, 1 of 4 on the FMA pipe; bf16 pairs packed in place
-        float rs1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          const float p0 = fast_exp2_pinned(fmaf(__uint_as_float(sv[i]), sl2, neg_m));
-          const float p1 = fast_exp2_pinned(fmaf(__uint_as_float(sv[i + 1]), sl2, neg_m));
-          const float p2 = fast_exp2_pinned(fmaf(__uint_as_float(sv[i + 2]), sl2, neg_m));
-          const float p3 = poly_exp2(fmaf(__uint_as_float(sv[i + 3]), sl2, neg_m));
-          rs += p0 + p1;
-          rs1 += p2 + p3;
-          sv[i >> 1] = pack_bf16x2(p0, p1);
-          sv[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-        }
-        rs += rs1;
-      } else {
 #pragma unroll
         for (int i = 0; i < 128; ++i) {
           float p = fast_exp2_pinned(fmaf(__uint_as_float(sv[i]), sl2, neg_m));
@@ -399,8 +480,10 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
 
       if (j > 0) {
-        mbar_wait(&o_done[g], (j - 1) & 1);  // PV(j-1) finished: O stable, P buffer reusable
-        tc_fence_after();
+        if constexpr (!(FAST && TS)) {
+          mbar_wait(&o_done[g], (j - 1) & 1);  // PV(j-1) finished: O stable, P buffer reusable
+          tc_fence_after();
+        }
         if (dbg) { tB = clk(); d_wait_o += tB - tA; tA = tB; }
         if (warp_grow) {
 #pragma unroll 1
