@@ -89,7 +89,11 @@ __device__ __forceinline__ void reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
 }
 
-template <int NQ, bool TS, bool FAST = false>
+// CHUNK (with FAST && TS && NQ == 2): P is handed to the MMA issuer in two 64-column halves.  The PV product is
+// K-split over the KV columns (MMA kk reads P[:, 16kk .. 16kk+16)), so PV over the first half runs on the tensor
+// pipe while the softmax warps still exponentiate the second half: ~350 cycles of MMA and the first P store leave
+// the strictly serial S -> softmax -> P -> PV -> next S chain that bounds this kernel.
+template <int NQ, bool TS, bool FAST = false, bool CHUNK = false>
 __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams P) {
   using C = AttnCfg<NQ, TS>;
   constexpr int KS = C::kStages;
@@ -104,7 +108,8 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
   uint64_t* s_ready = v_empty + KS;        // 2 (per S slot)
   uint64_t* p_ready = s_ready + 2;         // NQ
   uint64_t* o_done = p_ready + NQ;         // NQ
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + NQ);
+  uint64_t* p_lo = o_done + NQ;            // NQ (CHUNK: first half of P stored)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_lo + NQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,6 +138,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
     for (int g = 0; g < NQ; ++g) {
       mbar_init(&p_ready[g], 4);  // one arrive per softmax warp
       mbar_init(&o_done[g], 1);
+      mbar_init(&p_lo[g], 4);
     }
     fence_mbar_init();
   }
@@ -215,12 +221,12 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int g, int pslot, int st, bool first) {
+      auto issue_pv = [&](int g, int pslot, int st, bool first, int kk0 = 0, int kk1 = kBKV / 16) {
         const uint32_t d = tmem_base + 256 + g * 128;
         const uint64_t bd0 = v_desc[st];
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kBKV / 16; ++kk) {
+          for (int kk = kk0; kk < kk1; ++kk) {
             // V tile: [2 d-chunks][kv rows][128 B]; 16 kv rows per MMA = 2048 B; next d-chunk at kChunkBytes
             const uint32_t acc = (!first || kk != 0) ? 1u : 0u;
             if constexpr (TS) {
@@ -247,9 +253,18 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
           const int st = j % KS;
           mbar_wait(&v_full[st], (j / KS) & 1);
           for (int g = 0; g < 2; ++g) {
-            if (P.debug != 1) mbar_wait(&p_ready[g], j & 1);
-            tc_fence_after();
-            issue_pv(g, g, st, j == 0);
+            if constexpr (CHUNK) {
+              if (P.debug != 1) mbar_wait(&p_lo[g], j & 1);
+              tc_fence_after();
+              issue_pv(g, g, st, j == 0, 0, kBKV / 32);
+              if (P.debug != 1) mbar_wait(&p_ready[g], j & 1);
+              tc_fence_after();
+              issue_pv(g, g, st, j == 0, kBKV / 32, kBKV / 16);
+            } else {
+              if (P.debug != 1) mbar_wait(&p_ready[g], j & 1);
+              tc_fence_after();
+              issue_pv(g, g, st, j == 0);
+            }
             commit(&o_done[g]);
             if (g == 1) commit(&v_empty[st]);
             if (j + 1 < n) {
@@ -347,7 +362,86 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       float alpha = 1.f;
       bool warp_grow = false;
       float rs = 0.f;
-      if constexpr (FAST && TS) {
+      if constexpr (FAST && TS && CHUNK) {
+        // classic order (max -> lazy rescale -> exponentials), the exponentials in two halves with a P hand-off each
+        float m0 = fmax3(__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]));
+        float m1 = fmax3(__uint_as_float(sv[3]), __uint_as_float(sv[4]), __uint_as_float(sv[5]));
+        float m2 = fmaxf(__uint_as_float(sv[6]), __uint_as_float(sv[7]));
+        float m3 = -INFINITY;
+#pragma unroll
+        for (int i = 8; i < 128; i += 8) {
+          m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+          m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+          m2 = fmax3(m2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+          m3 = fmax3(m3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+        }
+        const float m_cand = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+        const bool grow = m_cand > m_used + kRescaleThreshold;
+        warp_grow = __any_sync(0xffffffffu, grow);
+        if (warp_grow) {
+          const float m_new = fmaxf(m_used, m_cand);
+          alpha = fast_exp2(m_used - m_new);  // exp2(-inf) = 0 on the first tile
+          m_used = m_new;
+          l *= alpha;
+          if (j > 0) {  // o_done(j-1) was awaited at the top of the step
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t ov[32];
+              tmem_ld32(o_taddr + c * 32, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(o_taddr + c * 32, ov);
+            }
+            tmem_st_wait();
+          }
+        }
+        if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
+        if (P.debug != 4) named_bar_sync(1 + g, 256);  // wait for our turn
+        const float2 sl2v = make_float2(sl2, sl2), negmv = make_float2(-m_used, -m_used);
+        const float2 magic = make_float2(12582912.f, 12582912.f);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+          for (int i = hh * 64; i < hh * 64 + 64; i += 8) {
+            const float2 t01 = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, negmv);
+            const float2 t23 = ffma2(make_float2(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2v, negmv);
+            const float2 t45 = ffma2(make_float2(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])), sl2v, negmv);
+            const float2 t67 = ffma2(make_float2(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])), sl2v, negmv);
+            const float p0 = fast_exp2_pinned(t01.x), p1 = fast_exp2_pinned(t01.y), p2 = fast_exp2_pinned(t23.x);
+            const float p4 = fast_exp2_pinned(t45.x), p5 = fast_exp2_pinned(t45.y), p6 = fast_exp2_pinned(t67.x);
+            const float2 x = make_float2(fmaxf(t23.y, -126.f), fmaxf(t67.y, -126.f));
+            const float2 rr = fadd2(x, magic);
+            const float2 f = fsub2(x, fsub2(rr, magic));
+            float2 pp = ffma2(make_float2(0.05500892f, 0.05500892f), f, make_float2(0.24221096f, 0.24221096f));
+            pp = ffma2(pp, f, make_float2(0.69328293f, 0.69328293f));
+            pp = ffma2(pp, f, make_float2(1.f, 1.f));
+            const float p3 = __int_as_float(__float_as_int(pp.x) + (__float_as_int(rr.x) << 23));
+            const float p7 = __int_as_float(__float_as_int(pp.y) + (__float_as_int(rr.y) << 23));
+            acc0 = fadd2(acc0, make_float2(p0, p1));
+            acc1 = fadd2(acc1, make_float2(p2, p3));
+            acc0 = fadd2(acc0, make_float2(p4, p5));
+            acc1 = fadd2(acc1, make_float2(p6, p7));
+            sv[i >> 1] = pack_bf16x2(p0, p1);
+            sv[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+            sv[(i >> 1) + 2] = pack_bf16x2(p4, p5);
+            sv[(i >> 1) + 3] = pack_bf16x2(p6, p7);
+          }
+          // hand this half of P (32 packed columns) to the issuer
+          uint32_t(*pk)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+          tmem_st32(lane_base + slot * 128 + hh * 32, pk[hh]);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(hh == 0 ? &p_lo[g] : &p_ready[g]);
+        }
+        if (P.debug != 4) named_bar_arrive(1 + (g ^ 1), 256);  // pass the turn
+        const float2 acc = fadd2(acc0, acc1);
+        l += acc.x + acc.y;
+        if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
+        continue;
+      } else if constexpr (FAST && TS) {
         // One pass: 3 of 4 exponentials on the MUFU, 1 of 4 on the FMA pipe; bf16 pairs packed in place.  The fp32 work
         // runs on packed pairs (FFMA2 / FADD2: two IEEE operations per issue slot).
         // The pass exponentiates against the STALE running max and tracks the maximum exponent it met; only if
@@ -1416,12 +1510,12 @@ static int launch_attention_events(const AttnParams& P, cudaStream_t stream) {
   return 0;
 }
 
-template <int NQ, bool TS, bool FAST = false>
+template <int NQ, bool TS, bool FAST = false, bool CHUNK = false>
 static int launch_attention(const AttnParams& P, cudaStream_t stream) {
   using C = AttnCfg<NQ, TS>;
   static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
   static bool attr_set = false;
-  auto kern = attention_kernel<NQ, TS, FAST>;
+  auto kern = attention_kernel<NQ, TS, FAST, CHUNK>;
   if (!attr_set) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     attr_set = true;
@@ -1474,6 +1568,7 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
   switch (a.variant) {
     case 0: return launch_attention<2, true, true>(P, stream);  // default: variant 1 + tightened softmax (4-way max,
                                                                 // 1/4 of the exponentials on the FMA pipe, in-loop packing)
+    case 7: return launch_attention<2, true, true, true>(P, stream);  // variant 0 + P handed over in two halves
     case 1: return launch_attention<2, true>(P, stream);   // 2 query tiles, whole KV tiles, P through TMEM
     case 5: return launch_attention_halves(P, stream);     // 2 query tiles x 2 KV halves in flight, explicit PV->QK waits
     case 6: return launch_attention_events(P, stream);     // event-driven issuer + fused single-pass softmax

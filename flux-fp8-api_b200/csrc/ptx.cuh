@@ -56,6 +56,11 @@ __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // one FMNMX3
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 // Packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 issue two IEEE fp32 operations per lane per instruction; each half
 // rounds exactly like the scalar instruction).
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
