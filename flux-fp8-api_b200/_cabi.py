@@ -33,11 +33,29 @@ EXPORTS = (
     "fluxb200_modulation_batched",
     "fluxb200_silu_quant",
     "fluxb200_ln_mod_quant",
+    "fluxb200_ln_mod_quant_grouped",
     "fluxb200_qknorm_rope",
     "fluxb200_attention",
     "fluxb200_lora_fuse",
     "fluxb200_debug_counters",
 )
+
+
+class LnArgs(C.Structure):
+    """struct fluxb200_ln_args"""
+
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("shift", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("y_fp8", C.c_void_p),
+        ("in_scale", C.c_void_p),
+        ("ldx", C.c_int64),
+        ("ldy", C.c_int64),
+        ("mod_batch_stride", C.c_int64),
+        ("B", C.c_int32),
+        ("L", C.c_int32),
+    ]
 
 
 class GemmArgs(C.Structure):
@@ -160,6 +178,7 @@ def load() -> C.CDLL:
         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
     ]
+    lib.fluxb200_ln_mod_quant_grouped.argtypes = [C.POINTER(LnArgs), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
     lib.fluxb200_qknorm_rope.argtypes = [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
         C.c_float, C.c_void_p,

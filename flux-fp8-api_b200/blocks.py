@@ -316,9 +316,9 @@ class DoubleStreamBlock(nn.Module):
         streams = ((txt, txt_mod1, txt_mod2, self.txt_attn, self.txt_mlp, T, 0),
                    (img, img_mod1, img_mod2, self.img_attn, self.img_mlp, L, T))
         group = []
-        for x, mod1, _, attn, _, rows, off in streams:
+        a8s = self._ln_pair([(x, mod1, attn.qkv) for x, mod1, _, attn, _, _, _ in streams])
+        for (x, mod1, _, attn, _, rows, off), a8 in zip(streams, a8s):
             lin = attn.qkv
-            a8, _ = ops.ln_mod_quant(x, mod1.shift, mod1.scale, lin.qscale, lin.input_float8_dtype)
             ops.f8_gemm_qkv_rope(a8.view(-1, D), lin.float8_data, lin.bias, lin.input_scale_reciprocal,
                                  lin.scale_reciprocal, q, k, v, attn.norm.query_norm.weight_fp32(),
                                  attn.norm.key_norm.weight_fp32(), cos, sin, rows_per_batch=rows, seq_offset=off,
@@ -343,9 +343,9 @@ class DoubleStreamBlock(nn.Module):
         self._launch(group)
         # x = x + gate2 * mlp((1 + scale2) * LN(x) + shift2)
         hs, group = [], []
-        for (x, _, mod2, _, mlp, rows, _), y in zip(streams, ys):
+        m8s = self._ln_pair([(y.view(B, rows, D), mod2, mlp[0]) for (_, _, mod2, _, mlp, rows, _), y in zip(streams, ys)])
+        for (x, _, mod2, _, mlp, rows, _), y, m8 in zip(streams, ys, m8s):
             up, down = mlp[0], mlp[2]
-            m8, _ = ops.ln_mod_quant(y.view(B, rows, D), mod2.shift, mod2.scale, up.qscale, up.input_float8_dtype)
             hs.append(ops.f8_gemm_gelu_quant(m8.view(-1, D), up.float8_data, up.bias, up.input_scale_reciprocal,
                                              up.scale_reciprocal, down.qscale, down.input_float8_dtype, defer=group))
         self._launch(group)
@@ -357,6 +357,16 @@ class DoubleStreamBlock(nn.Module):
         self._launch(group)
         txt_out, img_out = ys[0].view(B, T, D), ys[1].view(B, L, D)
         return img_out, txt_out
+
+    @staticmethod
+    def _ln_pair(items):
+        """LN -> modulate -> quantise for the txt and img streams: one grouped launch when both consumers take the same
+        fp8 input format, else one launch each.  items: [(x, ModulationOut, consuming F8Linear)] * 2."""
+        (x0, m0, l0), (x1, m1, l1) = items
+        if l0.input_float8_dtype == l1.input_float8_dtype:
+            return ops.ln_mod_quant_pair([(x0, m0.shift, m0.scale, l0.qscale), (x1, m1.shift, m1.scale, l1.qscale)],
+                                         l0.input_float8_dtype)
+        return [ops.ln_mod_quant(x, m.shift, m.scale, l.qscale, l.input_float8_dtype)[0] for x, m, l in items]
 
     @staticmethod
     def _launch(group):

@@ -1566,9 +1566,11 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
   if ((rc = make_tmap_3d(&P.tmap_v, a.v, 2, kD, a.S, bhn, row_bytes, row_bytes * a.S, 64, kBKV, 1))) return rc;
 
   switch (a.variant) {
-    case 0: return launch_attention<2, true, true>(P, stream);  // default: variant 1 + tightened softmax (4-way max,
-                                                                // 1/4 of the exponentials on the FMA pipe, in-loop packing)
-    case 7: return launch_attention<2, true, true, true>(P, stream);  // variant 0 + P handed over in two halves
+    case 0: return launch_attention<2, true, true, true>(P, stream);  // default: 2 query tiles, P through TMEM, packed-fp32
+                                                                      // softmax with 1/4 of the exponentials on the FMA
+                                                                      // pipe, P handed to the issuer in two halves
+    case 7: return launch_attention<2, true, true>(P, stream);  // the same with one whole-tile P hand-off, max fused
+                                                                // into the exp pass (stale max + rare redo)
     case 1: return launch_attention<2, true>(P, stream);   // 2 query tiles, whole KV tiles, P through TMEM
     case 5: return launch_attention_halves(P, stream);     // 2 query tiles x 2 KV halves in flight, explicit PV->QK waits
     case 6: return launch_attention_events(P, stream);     // event-driven issuer + fused single-pass softmax

@@ -100,18 +100,41 @@ constexpr int kLnMaxIter = 16;  // D <= 16*256 = 4096
 
 // NI = D/256 when known at compile time (12 for hidden 3072: the row lives in 48 registers and four 256-thread
 // blocks fit per SM, so the 4608-row launch is a single wave); NI = 0 is the generic predicated form.
+struct LnSeg {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* shift;
+  const __nv_bfloat16* scale;
+  uint8_t* yq;
+  __nv_bfloat16* yb;
+  const float* in_scale;
+  int64_t ldx, ldy, ldyb, mod_stride;
+  int rows, L;
+};
+struct LnParams {
+  LnSeg seg[2];  // rows of seg[0] come first
+  int D;
+  float eps;
+};
+
 template <int FMT, int NI>
-__global__ void __launch_bounds__(256, NI == 0 ? 2 : 4) ln_mod_quant_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
-                                                           const __nv_bfloat16* __restrict__ shift,
-                                                           const __nv_bfloat16* __restrict__ scale,
-                                                           int64_t mod_stride, uint8_t* __restrict__ yq, int64_t ldy,
-                                                           __nv_bfloat16* __restrict__ yb, int64_t ldyb,
-                                                           const float* __restrict__ in_scale, int rows, int L, int D,
-                                                           float eps) {
+__global__ void __launch_bounds__(256, NI == 0 ? 2 : 4) ln_mod_quant_kernel(const __grid_constant__ LnParams P) {
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= rows) return;
+  // the second row set starts on a block boundary (the grid is padded, not the rows)
+  const int blocks0 = (P.seg[0].rows + 7) >> 3;
+  const bool second = static_cast<int>(blockIdx.x) >= blocks0;
+  const LnSeg& G = second ? P.seg[1] : P.seg[0];
+  const int row = (static_cast<int>(blockIdx.x) - (second ? blocks0 : 0)) * 8 + warp;
+  if (row >= G.rows) return;
+  const __nv_bfloat16* __restrict__ x = G.x;
+  const __nv_bfloat16* __restrict__ shift = G.shift;
+  const __nv_bfloat16* __restrict__ scale = G.scale;
+  uint8_t* __restrict__ yq = G.yq;
+  __nv_bfloat16* __restrict__ yb = G.yb;
+  const float* __restrict__ in_scale = G.in_scale;
+  const int64_t ldx = G.ldx, ldy = G.ldy, ldyb = G.ldyb, mod_stride = G.mod_stride;
+  const int L = G.L, D = P.D;
+  const float eps = P.eps;
   const int b = row / L;
   const int ni = NI ? NI : D / 256;
   constexpr int kIter = NI ? NI : kLnMaxIter;
@@ -673,15 +696,53 @@ extern "C" int fluxb200_ln_mod_quant(const void* x, int64_t ldx, const void* shi
   FB_REQUIRE(ldx % 8 == 0 && mod_batch_stride % 8 == 0 && (!y_fp8 || ldy % 8 == 0) && (!y_bf16 || ldy_bf16 % 8 == 0),
              "fluxb200_ln_mod_quant: strides must keep 16-byte (bf16) / 8-byte (fp8) alignment");
   FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_ln_mod_quant: bad fp8 format %d", fmt);
-  const int rows = B * L;
-  const int grid = (rows + 7) / 8;
+  fb::LnParams P{};
+  P.seg[0] = fb::LnSeg{static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(shift),
+                       static_cast<const __nv_bfloat16*>(scale), static_cast<uint8_t*>(y_fp8),
+                       static_cast<__nv_bfloat16*>(y_bf16), in_scale, ldx, ldy, ldy_bf16, mod_batch_stride, B * L, L};
+  P.seg[1] = P.seg[0];
+  P.seg[1].rows = 0;
+  P.D = D;
+  P.eps = eps;
+  const int grid = (B * L + 7) / 8;
   // the specialised form is the steady-state one: fp8 output only
   auto kern = (D == 3072 && y_fp8 && !y_bf16) ? (fmt == 0 ? ln_mod_quant_kernel<0, 12> : ln_mod_quant_kernel<1, 12>)
+                                              : (fmt == 0 ? ln_mod_quant_kernel<0, 0> : ln_mod_quant_kernel<1, 0>);
+  FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(256), 0, stream, 1, P));
+  return 0;
+}
+
+extern "C" int fluxb200_ln_mod_quant_grouped(const fluxb200_ln_args* args, int count, int fmt, int D, float eps,
+                                             fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(args && (count == 1 || count == 2), "fluxb200_ln_mod_quant_grouped: 1 or 2 row sets");
+  FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_ln_mod_quant_grouped: bad fp8 format %d", fmt);
+  FB_REQUIRE(D > 0 && D % 256 == 0 && D <= kLnMaxIter * 256, "fluxb200_ln_mod_quant_grouped: D=%d must be a multiple of 256, <= %d",
+             D, kLnMaxIter * 256);
+  fb::LnParams P{};
+  int total = 0;
+  for (int i = 0; i < count; ++i) {
+    const fluxb200_ln_args& a = args[i];
+    FB_REQUIRE(a.x && a.shift && a.scale && a.y_fp8 && a.B > 0 && a.L > 0, "fluxb200_ln_mod_quant_grouped: bad row set %d", i);
+    FB_REQUIRE(a.ldx % 8 == 0 && a.mod_batch_stride % 8 == 0 && a.ldy % 8 == 0,
+               "fluxb200_ln_mod_quant_grouped: strides must keep 16-byte (bf16) / 8-byte (fp8) alignment");
+    P.seg[i] = fb::LnSeg{static_cast<const __nv_bfloat16*>(a.x), static_cast<const __nv_bfloat16*>(a.shift),
+                         static_cast<const __nv_bfloat16*>(a.scale), static_cast<uint8_t*>(a.y_fp8), nullptr, a.in_scale,
+                         a.ldx, a.ldy, 0, a.mod_batch_stride, a.B * a.L, a.L};
+    total += a.B * a.L;
+  }
+  if (count == 1) {
+    P.seg[1] = P.seg[0];
+    P.seg[1].rows = 0;
+  }
+  P.D = D;
+  P.eps = eps;
+  // rows of the second set start on a block boundary only if the first count is a multiple of 8: pad the grid instead
+  const int grid = (P.seg[0].rows + 7) / 8 + (P.seg[1].rows + 7) / 8;
+  auto kern = D == 3072 ? (fmt == 0 ? ln_mod_quant_kernel<0, 12> : ln_mod_quant_kernel<1, 12>)
                         : (fmt == 0 ? ln_mod_quant_kernel<0, 0> : ln_mod_quant_kernel<1, 0>);
-  FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(256), 0, stream, 1,
-                           static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(shift),
-                           static_cast<const __nv_bfloat16*>(scale), mod_batch_stride, static_cast<uint8_t*>(y_fp8), ldy,
-                           static_cast<__nv_bfloat16*>(y_bf16), ldy_bf16, in_scale, rows, L, D, eps));
+  (void)total;
+  FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(256), 0, stream, 1, P));
   return 0;
 }
 

@@ -123,6 +123,38 @@ def ln_mod_quant(x: Tensor, shift: Tensor, scale: Tensor, in_scale: Optional[Ten
     return yq, yb
 
 
+def ln_mod_quant_pair(items, dtype: torch.dtype, eps: float = 1e-6):
+    """Two independent LN-modulate-quantise problems (the txt and img streams of a DoubleStreamBlock) in ONE launch.
+    items: [(x [B,L,D], shift, scale, in_scale)] * 2 with the same D; returns the two fp8 tensors."""
+    args = (cabi.LnArgs * len(items))()
+    outs, keep = [], []
+    D = items[0][0].shape[-1]
+    total = 0.0
+    for i, (x, shift, scale, in_scale) in enumerate(items):
+        cabi.require_cuda(x, shift, scale, in_scale)
+        B, L, Dx = x.shape
+        if Dx != D:
+            raise ValueError("ln_mod_quant_pair: both streams must share the hidden size")
+        if x.stride(-1) != 1 or x.stride(0) != L * x.stride(1):
+            x = x.contiguous()
+        sh = shift.reshape(B, D) if shift.dim() == 3 else shift
+        sc = scale.reshape(B, D) if scale.dim() == 3 else scale
+        if sh.stride(-1) != 1 or sc.stride(-1) != 1 or sh.stride(0) != sc.stride(0):
+            sh, sc = sh.contiguous(), sc.contiguous()
+        yq = torch.empty((B, L, D), dtype=dtype, device=x.device)
+        a = args[i]
+        a.x, a.shift, a.scale, a.y_fp8, a.in_scale = x.data_ptr(), sh.data_ptr(), sc.data_ptr(), yq.data_ptr(), in_scale.data_ptr()
+        a.ldx, a.ldy, a.mod_batch_stride, a.B, a.L = x.stride(1), D, (sh.stride(0) if B > 1 else D), B, L
+        outs.append(yq)
+        keep += [x, sh, sc]
+        total += B * L * D * 3.0
+    _timed("ln_mod_quant", total,
+           lambda: cabi.check(cabi.load().fluxb200_ln_mod_quant_grouped(args, len(items), cabi.fp8_fmt(dtype), D, eps,
+                                                                        cabi.stream_ptr()),
+                              "fluxb200_ln_mod_quant_grouped"))
+    return outs
+
+
 def qknorm_rope(x: Tensor, norm_w: Optional[Tensor], cos: Optional[Tensor], sin: Optional[Tensor]) -> Tensor:
     """Stand-alone QKNorm + RoPE on [B,H,S,128] (cos/sin: bf16 [Bp,S,64], Bp in {1,B})."""
     cabi.require_cuda(x)

@@ -169,6 +169,20 @@ int fluxb200_ln_mod_quant(const void* x, int64_t ldx, const void* shift, const v
                           const float* in_scale, int fmt, int B, int L, int D, float eps,
                           fluxb200_stream_t stream);
 
+/* The same for up to two independent row sets in ONE launch (the txt and img streams of a DoubleStreamBlock,
+ * modules/flux_model.py:367-368 / 374-375 and :389 / :395): fp8 output only, same D / fmt / eps. */
+typedef struct fluxb200_ln_args {
+  const void* x;       /* bf16 [B*L, D], row stride ldx */
+  const void* shift;   /* bf16 [B][D], sample stride mod_batch_stride */
+  const void* scale;
+  void* y_fp8;         /* [B*L, ldy] */
+  const float* in_scale;
+  int64_t ldx, ldy, mod_batch_stride;
+  int32_t B, L;
+} fluxb200_ln_args;
+int fluxb200_ln_mod_quant_grouped(const fluxb200_ln_args* args, int count, int fmt, int D, float eps,
+                                  fluxb200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stand-alone QKNorm + apply_rope on [B,H,S,128] tensors (modules/flux_model.py:164, 60-65).
  * norm_w may be NULL (skip RMSNorm); cos/sin may be NULL (skip RoPE).  In-place allowed.

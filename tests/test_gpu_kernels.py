@@ -99,6 +99,23 @@ def test_ln_modulate_quantise(ops, O, B, L, D):
     assert mism < 0.001
 
 
+@pytest.mark.parametrize("B,L0,L1,D", [(1, 512, 4096, 3072), (2, 37, 100, 256), (1, 8, 3, 3072)])
+def test_ln_pair_equals_two_single_launches(ops, B, L0, L1, D):
+    """The grouped launch (txt + img rows of a DoubleStreamBlock) is bit-identical to one launch per stream, including
+    row counts that do not fill the last block of the first set."""
+    g = gen(5)
+    items, singles = [], []
+    for L in (L0, L1):
+        x = (torch.randn(B, L, D, device=DEV, generator=g) * 2 + 0.3).to(BF16)
+        mod = (torch.randn(B, 1, 6 * D, device=DEV, generator=g) * 0.3).to(BF16)
+        s = torch.tensor(48.0 + L % 7, device=DEV)
+        items.append((x, mod[..., :D], mod[..., D:2 * D], s))
+        singles.append(ops.ln_mod_quant(x, mod[..., :D], mod[..., D:2 * D], s, E5M2)[0])
+    pair = ops.ln_mod_quant_pair(items, E5M2)
+    for a, b in zip(pair, singles):
+        assert a.shape == b.shape and torch.equal(a.view(torch.uint8), b.view(torch.uint8))
+
+
 def test_silu_qknorm_rope_against_reference_golden(ops, O, golden_dir):
     g = torch.load(os.path.join(golden_dir, "ops.pt"))
     pe = g["pe"].to(DEV)
