@@ -89,12 +89,15 @@ __device__ __forceinline__ void reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
 }
 
-// CHUNK (with FAST && TS && NQ == 2): P is handed to the MMA issuer in two 64-column halves.  The PV product is
+// SPLIT = 64 or 96 (with FAST && TS && NQ == 2; "CHUNK"): P is handed to the MMA issuer in two pieces, the first
+// SPLIT KV columns and the rest.  The PV product is
 // K-split over the KV columns (MMA kk reads P[:, 16kk .. 16kk+16)), so PV over the first half runs on the tensor
 // pipe while the softmax warps still exponentiate the second half: ~350 cycles of MMA and the first P store leave
 // the strictly serial S -> softmax -> P -> PV -> next S chain that bounds this kernel.
-template <int NQ, bool TS, bool FAST = false, bool CHUNK = false>
+template <int NQ, bool TS, bool FAST = false, int SPLIT = 0>
 __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams P) {
+  constexpr bool CHUNK = SPLIT != 0;
+  static_assert(SPLIT == 0 || SPLIT == 64 || SPLIT == 96, "first hand-off: 64 or 96 KV columns");
   using C = AttnCfg<NQ, TS>;
   constexpr int KS = C::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -256,10 +259,10 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
             if constexpr (CHUNK) {
               if (P.debug != 1) mbar_wait(&p_lo[g], j & 1);
               tc_fence_after();
-              issue_pv(g, g, st, j == 0, 0, kBKV / 32);
+              issue_pv(g, g, st, j == 0, 0, SPLIT / 16);
               if (P.debug != 1) mbar_wait(&p_ready[g], j & 1);
               tc_fence_after();
-              issue_pv(g, g, st, j == 0, kBKV / 32, kBKV / 16);
+              issue_pv(g, g, st, j == 0, SPLIT / 16, kBKV / 16);
             } else {
               if (P.debug != 1) mbar_wait(&p_ready[g], j & 1);
               tc_fence_after();
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-          for (int i = hh * 64; i < hh * 64 + 64; i += 8) {
+          for (int i = hh * SPLIT; i < (hh == 0 ? SPLIT : 128); i += 8) {
             const float2 t01 = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, negmv);
             const float2 t23 = ffma2(make_float2(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2v, negmv);
             const float2 t45 = ffma2(make_float2(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])), sl2v, negmv);
@@ -428,9 +431,16 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
             sv[(i >> 1) + 2] = pack_bf16x2(p4, p5);
             sv[(i >> 1) + 3] = pack_bf16x2(p6, p7);
           }
-          // hand this half of P (32 packed columns) to the issuer
+          // hand this piece of P (packed: 2 KV columns per TMEM column) to the issuer
           uint32_t(*pk)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
-          tmem_st32(lane_base + slot * 128 + hh * 32, pk[hh]);
+          if constexpr (SPLIT == 64) {
+            tmem_st32(lane_base + slot * 128 + hh * 32, pk[hh]);
+          } else if (hh == 0) {
+            tmem_st32(lane_base + slot * 128, pk[0]);
+            tmem_st16(lane_base + slot * 128 + 32, sv + 32);
+          } else {
+            tmem_st16(lane_base + slot * 128 + 48, sv + 48);
+          }
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -1510,12 +1520,12 @@ static int launch_attention_events(const AttnParams& P, cudaStream_t stream) {
   return 0;
 }
 
-template <int NQ, bool TS, bool FAST = false, bool CHUNK = false>
+template <int NQ, bool TS, bool FAST = false, int SPLIT = 0>
 static int launch_attention(const AttnParams& P, cudaStream_t stream) {
   using C = AttnCfg<NQ, TS>;
   static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
   static bool attr_set = false;
-  auto kern = attention_kernel<NQ, TS, FAST, CHUNK>;
+  auto kern = attention_kernel<NQ, TS, FAST, SPLIT>;
   if (!attr_set) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     attr_set = true;
@@ -1566,11 +1576,12 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
   if ((rc = make_tmap_3d(&P.tmap_v, a.v, 2, kD, a.S, bhn, row_bytes, row_bytes * a.S, 64, kBKV, 1))) return rc;
 
   switch (a.variant) {
-    case 0: return launch_attention<2, true, true, true>(P, stream);  // default: 2 query tiles, P through TMEM, packed-fp32
+    case 0: return launch_attention<2, true, true, 64>(P, stream);  // default: 2 query tiles, P through TMEM, packed-fp32
                                                                       // softmax with 1/4 of the exponentials on the FMA
                                                                       // pipe, P handed to the issuer in two halves
     case 7: return launch_attention<2, true, true>(P, stream);  // the same with one whole-tile P hand-off, max fused
                                                                 // into the exp pass (stale max + rare redo)
+    case 8: return launch_attention<2, true, true, 96>(P, stream);  // default with a 3/4 + 1/4 split of the hand-off
     case 1: return launch_attention<2, true>(P, stream);   // 2 query tiles, whole KV tiles, P through TMEM
     case 5: return launch_attention_halves(P, stream);     // 2 query tiles x 2 KV halves in flight, explicit PV->QK waits
     case 6: return launch_attention_events(P, stream);     // event-driven issuer + fused single-pass softmax
