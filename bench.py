@@ -325,15 +325,30 @@ def main():
                              "frac": bts / (ms_ * 1e-3) / 1e9 / peaks["hbm_gbs"], "launches_per_step": cnt // 2,
                              "ms_per_step": ms_ / 2}
         fp8_peak = 2.0 * peaks["bf16_tflops_sustained"]
-        achieved = gf / (gms * 1e-3) / 1e12
+        # The event-timed pass launches eagerly: the host-side gaps between its launches let the power-capped GPU
+        # clock higher than it does inside the back-to-back CUDA-graph step.  `achieved` therefore charges the kernel
+        # its SHARE of the event-timed launches applied to the timed graph step (the in-step rate); the raw
+        # event-timed rate is reported beside it.
+        timed_ms = sum(a[1] for a in agg.values()) / 2
+        gemm_share = (gms / 2) / timed_ms
+        attn_share = (ams / 2) / timed_ms
+        gemm_ms_in_step = gemm_share * ms_per_step
+        attn_ms_in_step = attn_share * ms_per_step
+        achieved = (gf / 2) / (gemm_ms_in_step * 1e-3) / 1e12
+        attn_achieved = (af / 2) / (attn_ms_in_step * 1e-3) / 1e12
         roof = {
             "bound": "tensor", "kernel": "f8_gemm_kernel (tcgen05 kind::f8f6f4)", "achieved": achieved,
             "peak": fp8_peak, "unit": "TFLOP/s", "frac": achieved / fp8_peak, "traffic": gemm_traffic_per_launch(),
             "peak_source": f"2 x bf16_tflops_sustained, {peaks_src}; fp8 tensor rate is twice bf16",
-            "launches_per_step": gn // 2, "gemm_ms_per_step": gms / 2, "gemm_share_of_step": (gms / 2) / ms_per_step,
-            "attention": {"achieved": af / (ams * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                          "frac": af / (ams * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
-                          "launches_per_step": an // 2, "ms_per_step": ams / 2},
+            "method": "algorithmic flops of all GEMM launches of a step / (share of the CUDA-event-timed launch time "
+                      "x graph-replay ms per step)",
+            "achieved_event_timed_eager": gf / (gms * 1e-3) / 1e12,
+            "launches_per_step": gn // 2, "gemm_ms_per_step": gemm_ms_in_step, "gemm_share_of_step": gemm_share,
+            "gemm_ms_per_step_event_timed_eager": gms / 2,
+            "attention": {"achieved": attn_achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                          "frac": attn_achieved / peaks["bf16_tflops_sustained"],
+                          "achieved_event_timed_eager": af / (ams * 1e-3) / 1e12,
+                          "launches_per_step": an // 2, "ms_per_step": attn_ms_in_step, "share_of_step": attn_share},
             "hbm_kernels": hbm,
             "step_tensor_frac": (F8_FLOPS / (fp8_peak * 1e12) + ATTN_FLOPS / (peaks["bf16_tflops_sustained"] * 1e12))
                                 / (ms_per_step * 1e-3),
