@@ -508,7 +508,8 @@ def main():
     if len(sys.argv) > 1:
         name = sys.argv[1]
         if name.startswith("attention") and len(name) > len("attention"):
-            group_attention(tuple(int(c) for c in name[len("attention"):]))
+            tail = name[len("attention"):]
+            group_attention(tuple(int(c) for c in tail[1:].split(",")) if tail[0] == ":" else tuple(int(c) for c in tail))
         else:
             GROUPS[name]()
         print(f"== {name}: {'OK' if not FAILS else 'FAILED: ' + ', '.join(FAILS)}")
