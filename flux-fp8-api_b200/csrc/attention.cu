@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
   pdl_wait();  // q, k, v come from the preceding QKV GEMMs
 
   if (warp < 4) {
-    if constexpr (NQ == 2) reg_dec<56>();
+    if constexpr (NQ == 2) reg_dec<88>();  // 128 x 88 + 256 x 208 = 64512 = the whole launch allocation (384 x 168)
     if (warp == 0) {
       // ---------------- TMA producer (warp-uniform loop, one elected lane issues) ----------------
       if (elect_one()) {
@@ -198,20 +198,19 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       const uint32_t v_addr = smem_u32(smem + C::kVOff);
       const uint32_t p_addr = smem_u32(smem + C::kPOff);
 
-      uint64_t q_desc[NQ], k_desc[KS], v_desc[KS], p_desc[2];
-      for (int g = 0; g < NQ; ++g) q_desc[g] = make_desc_sw128(q_addr + g * kTileBytes, 16, 1024);
-      for (int i = 0; i < KS; ++i) {
-        k_desc[i] = make_desc_sw128(k_addr + i * kTileBytes, 16, 1024);
-        v_desc[i] = make_desc_sw128(v_addr + i * kTileBytes, kChunkBytes, 1024);
-      }
-      for (int i = 0; i < 2; ++i) p_desc[i] = make_desc_sw128(p_addr + i * kTileBytes, 16, 1024);
+      // descriptors of stage / tile i are base + i * tile bytes: derived arithmetically (arrays indexed by a run-time
+      // stage number live in local memory, and the issuer would fetch every descriptor through LDL)
+      const uint64_t q_desc0 = make_desc_sw128(q_addr, 16, 1024);
+      const uint64_t k_desc0 = make_desc_sw128(k_addr, 16, 1024);
+      const uint64_t v_desc0 = make_desc_sw128(v_addr, kChunkBytes, 1024);
+      const uint64_t p_desc0 = make_desc_sw128(p_addr, 16, 1024);
       auto commit = [&](uint64_t* bar) {
         if (elect_one()) tc_commit(bar);
         __syncwarp();
       };
       auto issue_qk = [&](int g, int slot, int st) {
         const uint32_t d = tmem_base + slot * 128;
-        const uint64_t ad0 = q_desc[g], bd0 = k_desc[st];
+        const uint64_t ad0 = desc_advance(q_desc0, g * kTileBytes), bd0 = desc_advance(k_desc0, st * kTileBytes);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kD / 16; ++kk) {
@@ -227,7 +226,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       };
       auto issue_pv = [&](int g, int pslot, int st, bool first, int kk0 = 0, int kk1 = kBKV / 16) {
         const uint32_t d = tmem_base + 256 + g * 128;
-        const uint64_t bd0 = v_desc[st];
+        const uint64_t bd0 = desc_advance(v_desc0, st * kTileBytes);
         if (elect_one()) {
 #pragma unroll
           for (int kk = kk0; kk < kk1; ++kk) {
@@ -237,7 +236,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
               mma_f16_ts(d, tmem_base + pslot * 128 + kk * 8, desc_advance(bd0, kk * 2048), idesc_pv, acc);
             } else {
               const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
-              mma_f16_ss(d, desc_advance(p_desc[pslot], off), desc_advance(bd0, kk * 2048), idesc_pv, acc);
+              mma_f16_ss(d, desc_advance(desc_advance(p_desc0, pslot * kTileBytes), off), desc_advance(bd0, kk * 2048), idesc_pv, acc);
             }
           }
         }
