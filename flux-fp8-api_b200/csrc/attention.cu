@@ -1656,19 +1656,16 @@ __global__ void __launch_bounds__(AttnWCfg::kThreads, 1) attention_kernel_wide(c
       const uint32_t q_addr = smem_u32(smem + C::kQOff);
       const uint32_t k_addr = smem_u32(smem + C::kKOff);
       const uint32_t v_addr = smem_u32(smem + C::kVOff);
-      uint64_t q_desc[2], k_desc[KS], v_desc[KS];
-      for (int g = 0; g < 2; ++g) q_desc[g] = make_desc_sw128(q_addr + g * kTileBytes, 16, 1024);
-      for (int i = 0; i < KS; ++i) {
-        k_desc[i] = make_desc_sw128(k_addr + i * kTileBytes, 16, 1024);
-        v_desc[i] = make_desc_sw128(v_addr + i * kTileBytes, kChunkBytes, 1024);
-      }
+      const uint64_t q_desc0 = make_desc_sw128(q_addr, 16, 1024);
+      const uint64_t k_desc0 = make_desc_sw128(k_addr, 16, 1024);
+      const uint64_t v_desc0 = make_desc_sw128(v_addr, kChunkBytes, 1024);
       auto commit = [&](uint64_t* bar) {
         if (elect_one()) tc_commit(bar);
         __syncwarp();
       };
       auto issue_qk = [&](int g, int st) {
         const uint32_t d = tmem_base + g * 128;
-        const uint64_t ad0 = q_desc[g], bd0 = k_desc[st];
+        const uint64_t ad0 = desc_advance(q_desc0, g * kTileBytes), bd0 = desc_advance(k_desc0, st * kTileBytes);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kD / 16; ++kk) {
@@ -1680,7 +1677,7 @@ __global__ void __launch_bounds__(AttnWCfg::kThreads, 1) attention_kernel_wide(c
       };
       auto issue_pv = [&](int g, int st, bool first, int kk0, int kk1) {
         const uint32_t d = tmem_base + 256 + g * 128;
-        const uint64_t bd0 = v_desc[st];
+        const uint64_t bd0 = desc_advance(v_desc0, st * kTileBytes);
         if (elect_one()) {
 #pragma unroll
           for (int kk = kk0; kk < kk1; ++kk) {
@@ -1725,7 +1722,7 @@ __global__ void __launch_bounds__(AttnWCfg::kThreads, 1) attention_kernel_wide(c
     }
   } else {
     // ---------------- softmax: 8 warps per query tile ----------------
-    reg_inc<104>();
+    reg_inc<104>();  // (88 / 96 instead spills 500 bytes per softmax thread: 593 us)
     const int g = (warp - 4) >> 3;          // query tile
     const int hc = ((warp - 4) >> 2) & 1;   // column half of the KV tile: [64*hc, 64*hc + 64)
     const int lg = warp & 3;                // TMEM lane group
