@@ -161,3 +161,28 @@ def test_shard_ranges_partition_the_batch():
     req = {"img": torch.arange(8)[:, None], "txt": torch.arange(8)[:, None] * 10, "note": 3}
     got = torch.cat([PAR.shard_request(req, r, 4)["img"] for r in range(4)])
     assert torch.equal(got, req["img"]) and PAR.shard_request(req, 1, 4)["note"] == 3
+
+
+def test_lora_operands_reproduce_the_reference_delta(golden_dir):
+    """lora.lora_operands (the factors handed to fluxb200_lora_fuse) multiplied out on the CPU equal the oracle's
+    calculate_lora_weight restatement for every golden case (alpha scaling, uneven-rank chunking), and the host
+    mirror keeps the reference's key helpers' behaviour."""
+    from flux_fp8_api_b200 import lora
+
+    cases = torch.load(os.path.join(golden_dir, "lora.pt"))
+    for c in cases:
+        down, up, chunks = lora.lora_operands((c["lora_A"], c["lora_B"], c["alpha"]), None, "cpu")
+        assert down.dtype == torch.float32 and up.dtype == torch.float32
+        delta = torch.zeros(down.shape[0], up.shape[1])
+        for part in up.chunk(chunks, dim=0):
+            delta = delta + (c["lora_scale"] * torch.mm(down, part))
+        assert torch.equal(delta, O.lora_delta(c["lora_A"], c["lora_B"], c["alpha"], None, c["lora_scale"])), c["name"]
+    w = {"a.b.lora_A.weight": torch.ones(2, 4), "a.b.lora_B.weight": torch.ones(3, 2), "a.b.alpha": 2.0,
+         "c.lora_A.weight": torch.ones(2, 4)}
+    assert lora.get_lora_for_key("a.b", w)[2] == 2.0
+    assert lora.get_lora_for_key("c", w) is None          # lora_B missing -> skipped, as in the reference
+    assert sorted(lora._keys_without_ab(w)) == ["a.b", "c"]
+    with pytest.raises(ValueError):
+        lora.lora_operands((torch.ones(5, 4), torch.ones(3, 2), None), None, "cpu")   # 5 rows do not chain with rank 2
+    with pytest.raises(NotImplementedError):
+        lora.apply_lora_to_model(torch.nn.Linear(2, 2), "some/file.safetensors")
