@@ -425,7 +425,10 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
             };
             float p0, p1, p2, p3, p4, p5, p6, p7;
             p0 = fast_exp2_pinned(t01.x), p1 = fast_exp2_pinned(t01.y);
-            if constexpr (POLY == 2) {
+            if constexpr (POLY == 0) {
+              p2 = fast_exp2_pinned(t23.x), p3 = fast_exp2_pinned(t23.y), p4 = fast_exp2_pinned(t45.x);
+              p5 = fast_exp2_pinned(t45.y), p6 = fast_exp2_pinned(t67.x), p7 = fast_exp2_pinned(t67.y);
+            } else if constexpr (POLY == 2) {
               p2 = fast_exp2_pinned(t23.x), p4 = fast_exp2_pinned(t45.x), p5 = fast_exp2_pinned(t45.y);
               p6 = fast_exp2_pinned(t67.x);
               const float2 q = poly2(make_float2(t23.y, t67.y));
@@ -2347,11 +2350,12 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
   if ((rc = make_tmap_3d(&P.tmap_v, a.v, 2, kD, a.S, bhn, row_bytes, row_bytes * a.S, 64, kBKV, 1))) return rc;
 
   switch (a.variant) {
-    case 0: return launch_attention<2, true, true, 64>(P, stream);  // default: 2 query tiles, P through TMEM, packed-fp32
-                                                                      // softmax with 1/4 of the exponentials on the FMA
-                                                                      // pipe, P handed to the issuer in two halves
+    case 0: return launch_attention<2, true, true, 64, 0>(P, stream);  // default: 2 query tiles, P through TMEM, packed-fp32
+                                                                         // softmax, every exponential on the MUFU, P
+                                                                         // handed to the issuer in two halves
     case 7: return launch_attention<2, true, true>(P, stream);  // the same with one whole-tile P hand-off, max fused
                                                                 // into the exp pass (stale max + rare redo)
+    case 13: return launch_attention<2, true, true, 64, 2>(P, stream);  // default with 2 of 8 exponentials on the FMA pipe
     case 10: return launch_attention<2, true, true, 64, 4>(P, stream);  // default with 1/2 of the exponentials on the FMA pipe
     case 11: return launch_attention<2, true, true, 64, 6>(P, stream);  // ... 3/4
     case 12: return launch_attention_one(P, stream);                // 1 query tile, 8 softmax warps, S double-buffered

@@ -27,6 +27,9 @@ __global__ void k(float* out, long long* cyc, float seed) {
       if (OP == 4) { unsigned u; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(u) : "f"(v[i])); v[i] = __uint_as_float(u); }
       if (OP == 5) { int x = __float_as_int(v[i]); asm volatile("shl.b32 %0, %0, 1;" : "+r"(x)); asm volatile("add.s32 %0, %0, 3;" : "+r"(x)); v[i] = __int_as_float(x); }
       if (OP == 6) asm volatile("max.f32 %0, %0, %1;" : "+f"(v[i]) : "f"(0.5f));
+      if (OP == 8) { unsigned u = __float_as_uint(v[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u)); v[i] = __uint_as_float(u); }
+      if (OP == 9) { unsigned u = __float_as_uint(v[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u)); v[i] = __uint_as_float(u); }
+      if (OP == 10) { unsigned u = __float_as_uint(v[i]); asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(u)); v[i] = __uint_as_float(u); }
     }
     if (OP == 2) {
 #pragma unroll
@@ -64,6 +67,9 @@ void run(const char* name, int warps, int instr_per_iter) {
 }
 
 int main() {
+  run<8>("ex2.approx.f16x2 (per PTX instr)", 4, CHAINS); run<8>("ex2.approx.f16x2 (per PTX instr)", 16, CHAINS);
+  run<9>("ex2.approx.ftz.bf16x2 (per PTX instr)", 4, CHAINS); run<9>("ex2.approx.ftz.bf16x2 (per PTX instr)", 16, CHAINS);
+  run<10>("tanh.approx.bf16x2 (per PTX instr)", 4, CHAINS); run<10>("tanh.approx.bf16x2 (per PTX instr)", 16, CHAINS);
   for (int w : {4, 8, 16}) {
     if (w == 4) {
       run<0>("MUFU.EX2", 4, CHAINS); run<1>("FFMA", 4, CHAINS); run<2>("FFMA2 (fma.rn.f32x2)", 4, CHAINS / 2);
