@@ -1924,6 +1924,383 @@ static int launch_attention_wide(const AttnParams& P, cudaStream_t stream) {
 
 
 // =====================================================================================================
+// Cooperative-halves variant: the layout of the default kernel (two query tiles, 384 threads, K/V shared by 256 query
+// rows) with the softmax work of EVERY tile-step split over all eight softmax warps (see the comment at the softmax
+// section).  The per-tile chain S -> softmax -> P -> PV -> next S keeps its MMA half, its softmax half is cut in two.
+// =====================================================================================================
+struct AttnCCfg {
+  static constexpr int kStages = 2;
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = 2 * kTileBytes;
+  static constexpr int kVOff = kKOff + kStages * kTileBytes;
+  static constexpr int kBarOff = kVOff + kStages * kTileBytes;
+  static constexpr int kXchOff = kBarOff + 256;                 // [2 tiles][2 buffers][2 halves][128 rows] fp32
+  static constexpr int kTotal = kXchOff + 2 * 2 * 2 * kBQ * 4 + 1024;
+  static constexpr int kThreads = 128 + 256;
+};
+
+__global__ void __launch_bounds__(AttnCCfg::kThreads, 1) attention_kernel_coop(const __grid_constant__ AttnParams P) {
+  using C = AttnCCfg;
+  constexpr int KS = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = q_full + 1;           // KS
+  uint64_t* k_empty = k_full + KS;         // KS
+  uint64_t* v_full = k_empty + KS;         // KS
+  uint64_t* v_empty = v_full + KS;         // KS
+  uint64_t* s_ready = v_empty + KS;        // 2
+  uint64_t* p_lo = s_ready + 2;            // 2: columns [0,64) of P stored (4 warps)
+  uint64_t* p_hi = p_lo + 2;               // 2: columns [64,128)
+  uint64_t* o_done = p_hi + 2;             // 2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+  const uint32_t xch_saddr = smem_u32(smem + C::kXchOff);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const fluxb200_attention_args& a = P.a;
+  const int q0 = blockIdx.x * (2 * kBQ);
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * a.H + h;
+  const int n = P.num_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmap_q);
+    tma_prefetch_desc(&P.tmap_k);
+    tma_prefetch_desc(&P.tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_ready[g], 1);
+      mbar_init(&p_lo[g], 4);
+      mbar_init(&p_hi[g], 4);
+      mbar_init(&o_done[g], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // q, k, v come from the preceding QKV GEMMs
+
+  if (warp < 4) {
+    reg_dec<88>();
+    if (warp == 0) {
+      // ---------------- TMA producer ----------------
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        for (int g = 0; g < 2; ++g) {
+          uint8_t* dst = smem + C::kQOff + g * kTileBytes;
+          tma_load_3d(dst, &P.tmap_q, q_full, 0, q0 + g * kBQ, bh, kEvictFirst);
+          tma_load_3d(dst + kChunkBytes, &P.tmap_q, q_full, 64, q0 + g * kBQ, bh, kEvictFirst);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < n; ++j) {
+        const int st = j % KS;
+        const uint32_t ph = (j / KS) & 1;
+        uint8_t* kd = smem + C::kKOff + st * kTileBytes;
+        uint8_t* vd = smem + C::kVOff + st * kTileBytes;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+          tma_load_3d(kd, &P.tmap_k, &k_full[st], 0, j * kBKV, bh, kEvictLast);
+          tma_load_3d(kd + kChunkBytes, &P.tmap_k, &k_full[st], 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+          tma_load_3d(vd, &P.tmap_v, &v_full[st], 0, j * kBKV, bh, kEvictLast);
+          tma_load_3d(vd + kChunkBytes, &P.tmap_v, &v_full[st], 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kFmtBF16, kBQ, kBKV, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kFmtBF16, kBQ, kD, 0, 1);  // V is MN-major
+      const uint32_t q_addr = smem_u32(smem + C::kQOff);
+      const uint32_t k_addr = smem_u32(smem + C::kKOff);
+      const uint32_t v_addr = smem_u32(smem + C::kVOff);
+      const uint64_t q_desc0 = make_desc_sw128(q_addr, 16, 1024);
+      const uint64_t k_desc0 = make_desc_sw128(k_addr, 16, 1024);
+      const uint64_t v_desc0 = make_desc_sw128(v_addr, kChunkBytes, 1024);
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) tc_commit(bar);
+        __syncwarp();
+      };
+      auto issue_qk = [&](int g, int st) {
+        const uint32_t d = tmem_base + g * 128;
+        const uint64_t ad0 = desc_advance(q_desc0, g * kTileBytes), bd0 = desc_advance(k_desc0, st * kTileBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
+            mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk, kk != 0 ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int g, int st, bool first, int kk0, int kk1) {
+        const uint32_t d = tmem_base + 256 + g * 128;
+        const uint64_t bd0 = desc_advance(v_desc0, st * kTileBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = kk0; kk < kk1; ++kk) {
+            const uint32_t acc = (!first || kk != 0) ? 1u : 0u;
+            mma_f16_ts(d, tmem_base + g * 128 + kk * 8, desc_advance(bd0, kk * 2048), idesc_pv, acc);
+          }
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int g = 0; g < 2; ++g) {
+        issue_qk(g, 0);
+        commit(&s_ready[g]);
+      }
+      commit(&k_empty[0]);
+      for (int j = 0; j < n; ++j) {
+        const int st = j % KS;
+        mbar_wait(&v_full[st], (j / KS) & 1);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_lo[g], j & 1);
+          tc_fence_after();
+          issue_pv(g, st, j == 0, 0, 4);
+          mbar_wait(&p_hi[g], j & 1);
+          tc_fence_after();
+          issue_pv(g, st, j == 0, 4, 8);
+          commit(&o_done[g]);
+          if (g == 1) commit(&v_empty[st]);
+          if (j + 1 < n) {
+            const int st1 = (j + 1) % KS;
+            if (g == 0) {
+              mbar_wait(&k_full[st1], ((j + 1) / KS) & 1);
+              tc_fence_after();
+            }
+            issue_qk(g, st1);
+            commit(&s_ready[g]);
+            if (g == 1) commit(&k_empty[st1]);
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax: 8 warps, every one of them works on BOTH query tiles ----------------
+    // Warps 4-7 own KV columns [0,64) and warps 8-11 columns [64,128) of whichever tile's scores are ready; warp w and
+    // w+4 have the same w % 4, i.e. the same TMEM lanes (rows) AND the same SM sub-partition, so a tile's exponential
+    // pass runs as two concurrent warps per sub-partition (their FMA / ALU / MUFU work overlaps) and takes half as
+    // long, while the tensor pipe works on the other tile.  No extra threads or registers compared with one
+    // warpgroup per tile; a thread carries the running max / partial row sum of its row in both tiles.
+    reg_inc<208>();  // 128 x 88 + 256 x 208 = 64512 = 384 x 168
+    const int hc = (warp - 4) >> 2;         // column half of the KV tile: [64*hc, 64*hc + 64)
+    const int lg = warp & 3;                // TMEM lane group == SM sub-partition
+    const int r = lg * 32 + lane;           // row within either query tile
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    const uint32_t pair_bar = 3 + lg;       // named barrier of the two warps sharing my rows
+    const float sl2 = P.scale_log2;
+    float m_used[2] = {-INFINITY, -INFINITY};
+    float l[2] = {0.f, 0.f};
+
+    for (int j = 0; j < n; ++j) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const uint32_t s_taddr = lane_base + g * 128 + hc * 64;        // my 64 S columns of tile g
+        const uint32_t p_taddr = lane_base + g * 128 + hc * 32;        // my 32 packed P columns
+        const uint32_t o_taddr = lane_base + 256 + g * 128 + hc * 64;  // my 64 O columns
+        if (j > 0) mbar_wait(&o_done[g], (j - 1) & 1);  // PV(j-1) finished: O stable, P columns reusable
+        mbar_wait(&s_ready[g], j & 1);
+        tc_fence_after();
+        uint32_t sv[64];
+        {
+          uint32_t(*sv2)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+          tmem_ld32(s_taddr, sv2[0]);
+          tmem_ld32(s_taddr + 32, sv2[1]);
+          tmem_ld_wait();
+        }
+        const int kv_left = a.S - j * kBKV - hc * 64;  // my columns >= kv_left are out of range (last tile only)
+        if (kv_left < 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= kv_left) sv[i] = __float_as_uint(-INFINITY);
+        }
+        float m0 = fmax3(__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]));
+        float m1 = fmax3(__uint_as_float(sv[3]), __uint_as_float(sv[4]), __uint_as_float(sv[5]));
+        float m2 = fmaxf(__uint_as_float(sv[6]), __uint_as_float(sv[7]));
+        float m3 = -INFINITY;
+#pragma unroll
+        for (int i = 8; i < 64; i += 8) {
+          m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+          m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+          m2 = fmax3(m2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+          m3 = fmax3(m3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+        }
+        const float mx_half = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        // row max = max over the two half-row threads (exchange buffer double-buffered by step parity)
+        const uint32_t xb = xch_saddr + ((g * 2 + (j & 1)) * 2) * kBQ * 4;
+        sts_f32(xb + (hc * kBQ + r) * 4, mx_half);
+        named_bar_sync(pair_bar, 64);
+        const float m_cand = fmaxf(mx_half, lds_f32(xb + ((hc ^ 1) * kBQ + r) * 4)) * sl2;
+        // Lazy rescale: keep the stale max unless it is more than 2^8 below the new one (identical decision in both
+        // half-row threads: same rows, same m_used, same m_cand).
+        const bool grow = m_cand > m_used[g] + kRescaleThreshold;
+        const bool warp_grow = __any_sync(0xffffffffu, grow);
+        if (warp_grow) {
+          const float m_new = fmaxf(m_used[g], m_cand);
+          const float alpha = fast_exp2(m_used[g] - m_new);  // exp2(-inf) = 0 on the first tile
+          m_used[g] = m_new;
+          l[g] *= alpha;
+          if (j > 0) {
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t ov[32];
+              tmem_ld32(o_taddr + c * 32, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(o_taddr + c * 32, ov);
+            }
+            tmem_st_wait();
+          }
+        }
+        const float2 sl2v = make_float2(sl2, sl2), negmv = make_float2(-m_used[g], -m_used[g]);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+          const float2 t01 = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, negmv);
+          const float2 t23 = ffma2(make_float2(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2v, negmv);
+          const float2 t45 = ffma2(make_float2(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])), sl2v, negmv);
+          const float2 t67 = ffma2(make_float2(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])), sl2v, negmv);
+          const float p0 = fast_exp2_pinned(t01.x), p1 = fast_exp2_pinned(t01.y), p2 = fast_exp2_pinned(t23.x);
+          const float p3 = fast_exp2_pinned(t23.y), p4 = fast_exp2_pinned(t45.x), p5 = fast_exp2_pinned(t45.y);
+          const float p6 = fast_exp2_pinned(t67.x), p7 = fast_exp2_pinned(t67.y);
+          acc0 = fadd2(acc0, make_float2(p0, p1));
+          acc1 = fadd2(acc1, make_float2(p2, p3));
+          acc0 = fadd2(acc0, make_float2(p4, p5));
+          acc1 = fadd2(acc1, make_float2(p6, p7));
+          sv[i >> 1] = pack_bf16x2(p0, p1);
+          sv[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          sv[(i >> 1) + 2] = pack_bf16x2(p4, p5);
+          sv[(i >> 1) + 3] = pack_bf16x2(p6, p7);
+        }
+        {
+          uint32_t(*pk)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+          tmem_st32(p_taddr, pk[0]);
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hc == 0 ? &p_lo[g] : &p_hi[g]);
+        const float2 acc = fadd2(acc0, acc1);
+        l[g] += acc.x + acc.y;
+      }
+    }
+
+    // ---------------- epilogue: O / l -> bf16 -> (optional) fp8; this thread writes its 64 columns of both tiles ----------------
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+      const uint32_t o_taddr = lane_base + 256 + g * 128 + hc * 64;
+      const int qrow = q0 + g * kBQ + r;
+      mbar_wait(&o_done[g], (n - 1) & 1);
+      tc_fence_after();
+      // row sum = the two half-row partial sums (same stale-max history in both threads)
+      const uint32_t xb = xch_saddr + ((g * 2 + (n & 1)) * 2) * kBQ * 4;
+      sts_f32(xb + (hc * kBQ + r) * 4, l[g]);
+      named_bar_sync(pair_bar, 64);
+      const float l_other = lds_f32(xb + ((hc ^ 1) * kBQ + r) * 4);
+      const float inv_l = 1.f / (hc == 0 ? l[g] + l_other : l_other + l[g]);
+      const bool valid = qrow < a.S;
+      const bool second = a.out1 != nullptr && qrow >= a.split_row;
+      void* const outp = second ? a.out1 : a.out;
+      const int64_t obase = (second ? static_cast<int64_t>(b) * a.out1_batch_stride +
+                                          static_cast<int64_t>(qrow - a.split_row) * a.ldo1 + h * kD
+                                    : static_cast<int64_t>(b) * a.out_batch_stride + static_cast<int64_t>(qrow) * a.ldo + h * kD) +
+                            hc * 64;
+      float oscale = 1.f;
+      if (a.out_kind == 1) oscale = __ldg(qrow < a.split_row ? a.out_scale0 : a.out_scale1);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld32(o_taddr + c * 32, ov);
+        tmem_ld_wait();
+        if (!valid) continue;
+        if (a.out_kind == 0) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + obase + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(ov[q * 8 + 0]) * inv_l, __uint_as_float(ov[q * 8 + 1]) * inv_l);
+            o.y = pack_bf16x2(__uint_as_float(ov[q * 8 + 2]) * inv_l, __uint_as_float(ov[q * 8 + 3]) * inv_l);
+            o.z = pack_bf16x2(__uint_as_float(ov[q * 8 + 4]) * inv_l, __uint_as_float(ov[q * 8 + 5]) * inv_l);
+            o.w = pack_bf16x2(__uint_as_float(ov[q * 8 + 6]) * inv_l, __uint_as_float(ov[q * 8 + 7]) * inv_l);
+            dst[q] = o;
+          }
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(outp) + obase + c * 32);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float f[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float o = bf16r(__uint_as_float(ov[q * 16 + t * 4 + e]) * inv_l);
+                f[e] = a.out_fmt == FLUXB200_E5M2 ? quant_pre<1>(o, oscale) : quant_pre<0>(o, oscale);
+              }
+              if (a.out_fmt == FLUXB200_E5M2)
+                w[t] = to_fp8x2<1>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<1>(f[2], f[3])) << 16);
+              else
+                w[t] = to_fp8x2<0>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<0>(f[2], f[3])) << 16);
+            }
+            dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+  }
+
+  pdl_launch_dependents();  // multi-wave grid: let the next kernel in only when this CTA is done
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_attention_coop(const AttnParams& P, cudaStream_t stream) {
+  using C = AttnCCfg;
+  static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
+  static bool attr_set = false;
+  if (!attr_set) {
+    FB_CUDA_OK(cudaFuncSetAttribute(attention_kernel_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+    attr_set = true;
+  }
+  const fluxb200_attention_args& a = P.a;
+  dim3 grid((a.S + 2 * kBQ - 1) / (2 * kBQ), a.H, a.B);
+  FB_CUDA_OK(launch_kernel(attention_kernel_coop, grid, dim3(C::kThreads), C::kTotal, stream, 1, P));
+  return 0;
+}
+
+
+// =====================================================================================================
 // One query tile per CTA, EIGHT softmax warps on it (384 threads, 208 registers each for the softmax warps), S
 // double-buffered in TMEM: QK(j+1) is issued before the issuer waits for P(j), so the tensor pipe computes the next
 // scores while the softmax warps work -- the MMA and softmax halves of the per-tile chain of the two-tile kernels
@@ -2358,6 +2735,7 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
     case 13: return launch_attention<2, true, true, 64, 2>(P, stream);  // default with 2 of 8 exponentials on the FMA pipe
     case 10: return launch_attention<2, true, true, 64, 4>(P, stream);  // default with 1/2 of the exponentials on the FMA pipe
     case 11: return launch_attention<2, true, true, 64, 6>(P, stream);  // ... 3/4
+    case 14: return launch_attention_coop(P, stream);               // both tiles' softmax split over all 8 softmax warps
     case 12: return launch_attention_one(P, stream);                // 1 query tile, 8 softmax warps, S double-buffered
     case 9: return launch_attention_wide(P, stream);                // 8 softmax warps per query tile (640 threads)
     case 8: return launch_attention<2, true, true, 96>(P, stream);  // default with a 3/4 + 1/4 split of the hand-off
