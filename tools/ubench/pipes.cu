@@ -35,6 +35,19 @@ __global__ void k(float* out, long long* cyc, float seed) {
 #pragma unroll
       for (int i = 0; i < CHAINS / 2; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p[i]) : "l"(c2));
     }
+    if (OP == 11 || OP == 12 || OP == 13) {
+      // mixed stream: 8 MUFU.EX2 (OP 11, 12) and/or 16 FFMA2 (OP 11, 13) per iteration, independent chains
+      if (OP != 13) {
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+      }
+      if (OP != 12) {
+#pragma unroll
+        for (int r2 = 0; r2 < 4; ++r2)
+#pragma unroll
+          for (int i = 0; i < CHAINS / 2; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(p[i]) : "l"(c2));
+      }
+    }
     if (OP == 7) {
 #pragma unroll
       for (int i = 0; i < CHAINS / 2; ++i) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(c2));
@@ -70,6 +83,10 @@ int main() {
   run<8>("ex2.approx.f16x2 (per PTX instr)", 4, CHAINS); run<8>("ex2.approx.f16x2 (per PTX instr)", 16, CHAINS);
   run<9>("ex2.approx.ftz.bf16x2 (per PTX instr)", 4, CHAINS); run<9>("ex2.approx.ftz.bf16x2 (per PTX instr)", 16, CHAINS);
   run<10>("tanh.approx.bf16x2 (per PTX instr)", 4, CHAINS); run<10>("tanh.approx.bf16x2 (per PTX instr)", 16, CHAINS);
+  // does FMA-pipe work issue underneath MUFU work of the same warp(s)?  time per ITERATION, in cycles
+  for (int w : {4, 8}) {
+    run<12>("8 MUFU.EX2 per iteration", w, 1); run<13>("16 FFMA2 per iteration", w, 1); run<11>("8 MUFU.EX2 + 16 FFMA2 per iteration", w, 1);
+  }
   for (int w : {4, 8, 16}) {
     if (w == 4) {
       run<0>("MUFU.EX2", 4, CHAINS); run<1>("FFMA", 4, CHAINS); run<2>("FFMA2 (fma.rn.f32x2)", 4, CHAINS / 2);
