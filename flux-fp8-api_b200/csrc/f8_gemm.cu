@@ -60,6 +60,11 @@ struct GemmParams {
   int num_m_tiles[2];
   int tiles0, num_tiles;
   int num_n_tiles, num_k_blocks;
+  // LINEAR1 only: number of N tiles that take the heavy QKV epilogue (0 = no interleaving).  They are the FIRST
+  // q_n_tiles columns of the weight; processed in column order the kernel would run all heavy-epilogue tiles first
+  // (epilogue longer than a K = 3072 mainloop: the MMAs stall) and all light ones last.  decode_tile spreads them
+  // evenly through the schedule so the double-buffered accumulators average the two epilogue costs.
+  int q_n_tiles;
   uint32_t idesc;
   // Timing experiments only (env FLUXB200_GEMM_DEBUG; results are garbage): 1 = no TMA traffic after the ring is
   // first filled (pure MMA issue rate), 2 = no MMAs (pure TMA pipeline rate).
@@ -77,7 +82,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) 
   const int local = tile - (c.pi ? P.tiles0 : 0);
   const int nm = P.num_m_tiles[c.pi];
   c.m_blk = local % nm;
-  c.n_blk = local / nm;
+  int i = local / nm;
+  if (P.q_n_tiles > 0) {
+    // position i of the schedule is a QKV tile iff floor((i+1) q / N) > floor(i q / N)   (q of every N, evenly spaced)
+    const int q = P.q_n_tiles, N = P.num_n_tiles;
+    const int before = i * q / N, upto = (i + 1) * q / N;
+    i = upto > before ? before : q + (i - before);
+  }
+  c.n_blk = i;
   return c;
 }
 
@@ -709,6 +721,14 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
   }();
   P.debug = dbg;
   P.num_n_tiles = (g.N + bn - 1) / bn;
+  P.q_n_tiles = 0;
+  {
+    static const bool ilv = [] {
+      const char* e = getenv("FLUXB200_GEMM_INTERLEAVE");  // experiment, off by default: measured 235.8 us (on) against
+      return e != nullptr && atoi(e) != 0;                 // 233.9 us (off) per launch inside the step
+    }();
+    if (ilv && epi == FLUXB200_EPI_LINEAR1 && count == 1) P.q_n_tiles = (3 * g.num_heads * kHeadDim) / bn;
+  }
   P.num_k_blocks = (g.K + kBK - 1) / kBK;
   P.idesc = make_idesc(g.a_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3, g.w_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3,
                        kBM * cg, bn);
