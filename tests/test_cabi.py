@@ -37,11 +37,17 @@ def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / "layout.c"
     fields_g = [f[0] for f in _cabi.GemmArgs._fields_]
     fields_a = [f[0] for f in _cabi.AttentionArgs._fields_]
+    fields_l = [f[0] for f in _cabi.LnArgs._fields_]
+    fields_v = [f[0] for f in _cabi.GemvLayer._fields_]
     body = ['#include <stdio.h>', '#include <stddef.h>', '#include "flux_b200.h"', "int main(void){"]
     body.append('printf("%zu\\n", sizeof(fluxb200_gemm_args));')
     body += [f'printf("%zu\\n", offsetof(fluxb200_gemm_args, {f}));' for f in fields_g]
     body.append('printf("%zu\\n", sizeof(fluxb200_attention_args));')
     body += [f'printf("%zu\\n", offsetof(fluxb200_attention_args, {f}));' for f in fields_a]
+    body.append('printf("%zu\\n", sizeof(fluxb200_ln_args));')
+    body += [f'printf("%zu\\n", offsetof(fluxb200_ln_args, {f}));' for f in fields_l]
+    body.append('printf("%zu\\n", sizeof(fluxb200_gemv_layer));')
+    body += [f'printf("%zu\\n", offsetof(fluxb200_gemv_layer, {f}));' for f in fields_v]
     body.append("return 0;}")
     src.write_text("\n".join(body))
     exe = tmp_path / "layout"
@@ -51,7 +57,13 @@ def test_struct_layout_matches_c(tmp_path):
     assert nums[1:1 + len(fields_g)] == [getattr(_cabi.GemmArgs, f).offset for f in fields_g]
     rest = nums[1 + len(fields_g):]
     assert rest[0] == C.sizeof(_cabi.AttentionArgs)
-    assert rest[1:] == [getattr(_cabi.AttentionArgs, f).offset for f in fields_a]
+    assert rest[1:1 + len(fields_a)] == [getattr(_cabi.AttentionArgs, f).offset for f in fields_a]
+    rest = rest[1 + len(fields_a):]
+    assert rest[0] == C.sizeof(_cabi.LnArgs)
+    assert rest[1:1 + len(fields_l)] == [getattr(_cabi.LnArgs, f).offset for f in fields_l]
+    rest = rest[1 + len(fields_l):]
+    assert rest[0] == C.sizeof(_cabi.GemvLayer)
+    assert rest[1:] == [getattr(_cabi.GemvLayer, f).offset for f in fields_v]
 
 
 def test_invalid_arguments_fail_loudly(lib):
@@ -64,6 +76,13 @@ def test_invalid_arguments_fail_loudly(lib):
     assert lib.fluxb200_f8_gemm(C.byref(g), None) == _cabi.ERR_INVALID
     a = _cabi.AttentionArgs()
     assert lib.fluxb200_attention(C.byref(a), None) == _cabi.ERR_INVALID
+    assert lib.fluxb200_ln_mod_quant_grouped(None, 1, 1, 3072, 1e-6, None) == _cabi.ERR_INVALID
+    ln = (_cabi.LnArgs * 2)()
+    assert lib.fluxb200_ln_mod_quant_grouped(ln, 3, 1, 3072, 1e-6, None) == _cabi.ERR_INVALID      # at most two row sets
+    assert lib.fluxb200_ln_mod_quant_grouped(ln, 2, 1, 3000, 1e-6, None) == _cabi.ERR_INVALID      # D % 256
+    assert lib.fluxb200_lora_fuse(None, 0, None, None, None, 8, 8, 4, 1, 1.0, 0, None, None, None) == _cabi.ERR_INVALID
+    assert b"null" in lib.fluxb200_last_error()
+    assert lib.fluxb200_modulation_batched(None, None, 1, 1, None, None, 0, 1, 3072, 1, 0, None) == _cabi.ERR_INVALID
     with pytest.raises(ValueError):
         _cabi.check(_cabi.ERR_INVALID, "x")
     with pytest.raises(_cabi.FluxB200Error):
@@ -82,6 +101,11 @@ def test_cpu_tensors_are_rejected_not_computed():
         ops.quantize(x, torch.tensor(1.0), torch.float8_e5m2)
     with pytest.raises(_cabi.FluxB200Error):
         F8Linear.from_linear(torch.nn.Linear(16, 16).to(torch.bfloat16))
+    with pytest.raises(_cabi.FluxB200Error):
+        ops.ln_mod_quant_pair([(torch.zeros(1, 8, 256, dtype=torch.bfloat16), x[:1, :0], x[:1, :0], torch.tensor(1.0))] * 2,
+                              torch.float8_e5m2)
+    with pytest.raises(_cabi.FluxB200Error):
+        ops.lora_fuse(torch.zeros(8, 16, dtype=torch.float8_e4m3fn), torch.tensor(1.0), torch.zeros(8, 2), torch.zeros(2, 16), 1.0)
 
 
 def test_product_does_not_import_the_oracle():
