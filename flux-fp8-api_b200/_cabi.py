@@ -31,6 +31,7 @@ EXPORTS = (
     "fluxb200_f8_gemm_grouped",
     "fluxb200_f8_gemv",
     "fluxb200_modulation_batched",
+    "fluxb200_modulation_batched_bf16",
     "fluxb200_silu_quant",
     "fluxb200_ln_mod_quant",
     "fluxb200_ln_mod_quant_grouped",
@@ -172,6 +173,9 @@ def load() -> C.CDLL:
     lib.fluxb200_modulation_batched.argtypes = [
         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
         C.c_int, C.c_void_p,
+    ]
+    lib.fluxb200_modulation_batched_bf16.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
     ]
     lib.fluxb200_silu_quant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     lib.fluxb200_ln_mod_quant.argtypes = [

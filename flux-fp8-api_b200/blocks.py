@@ -13,6 +13,8 @@ Two execution modes per block, both entirely on the GPU through libflux_b200.so:
 """
 from __future__ import annotations
 
+import threading
+import weakref
 from collections import namedtuple
 from typing import Optional, Tuple
 
@@ -49,7 +51,16 @@ class EmbedND(nn.Module):
         return torch.cat(tables, dim=-3).unsqueeze(1)
 
 
-_rope_cache: dict = {}
+class _RopeCache(threading.local):
+    """Last (pe -> cos, sin) extraction of this thread.  The entry holds `pe` by WEAK reference and is a hit only
+    for the very same tensor object: a new `pe` allocated at a recycled address (same shape, and version 0 under
+    inference_mode) can never alias it -- the round-1 key (data_ptr, shape, version) could."""
+
+    def __init__(self):
+        self.entry = None
+
+
+_rope_cache = _RopeCache()
 
 
 def tensor_version(t: Tensor) -> int:
@@ -60,18 +71,22 @@ def tensor_version(t: Tensor) -> int:
         return 0
 
 
-def rope_cos_sin(pe: Tensor) -> Tuple[Tensor, Tensor]:
+def extract_cos_sin(pe: Tensor) -> Tuple[Tensor, Tensor]:
     """pe [B,1,S,64,2,2] -> (cos, sin) as contiguous bf16 [B,S,64]: the two table entries the kernels need
-    (pe[...,0,0] = cos, pe[...,1,0] = sin; the other two are their negation / copy).  Cached per pe tensor."""
-    key = (pe.data_ptr(), tuple(pe.shape), tensor_version(pe))
-    hit = _rope_cache.get("k")
-    if hit is not None and hit[0] == key:
-        return hit[1], hit[2]
+    (pe[...,0,0] = cos, pe[...,1,0] = sin; the other two are their negation / copy)."""
     if pe.dtype != BF16:
         raise ValueError(f"pe must be bfloat16 (EmbedND output), got {pe.dtype}")
-    cos = pe[:, 0, :, :, 0, 0].contiguous()
-    sin = pe[:, 0, :, :, 1, 0].contiguous()
-    _rope_cache["k"] = (key, cos, sin)
+    return pe[:, 0, :, :, 0, 0].contiguous(), pe[:, 0, :, :, 1, 0].contiguous()
+
+
+def rope_cos_sin(pe: Tensor) -> Tuple[Tensor, Tensor]:
+    """(cos, sin) of a `pe` table for callers that only hand over `pe` (the reference's block signature).  Flux.forward
+    computes the pair once next to `pe` and passes it down (`rope=`), so the steady-state path never comes here."""
+    hit = _rope_cache.entry
+    if hit is not None and hit[0]() is pe and hit[1] == tensor_version(pe):
+        return hit[2], hit[3]
+    cos, sin = extract_cos_sin(pe)
+    _rope_cache.entry = (weakref.ref(pe), tensor_version(pe), cos, sin)
     return cos, sin
 
 
@@ -94,18 +109,44 @@ class RMSNorm(nn.Module):
         super().__init__()
         self.scale = nn.Parameter(torch.ones(dim))
         self._w32: Optional[Tensor] = None
+        self._w32_key = None
 
     def weight_fp32(self) -> Tensor:
-        """The learned scale as the fp32 vector the kernels read (cached; refreshed if the parameter moves)."""
+        """The learned scale as the fp32 vector the kernels read.  Cached against the identity of the Parameter
+        object, its storage and (where tracked) its in-place version; load_state_dict / .to() / invalidate_derived()
+        drop it.  An in-place write into an *inference-mode* parameter is the one change this cannot see: call
+        invalidate_derived(model) after such a write (parallel.broadcast_state does)."""
         w = self.scale
-        key = (w.data_ptr(), w.device, tensor_version(w))
+        key = (id(w), w.data_ptr(), w.device, tensor_version(w))
         if self._w32 is None or self._w32_key != key:
             self._w32 = w.detach().float().contiguous()
             self._w32_key = key
         return self._w32
 
+    def invalidate_derived(self) -> None:
+        self._w32, self._w32_key = None, None
+
+    def _apply(self, fn, *a, **kw):
+        self.invalidate_derived()
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self.invalidate_derived()
+        return super()._load_from_state_dict(*a, **kw)
+
     def forward(self, x: Tensor):
         return ops.qknorm_rope(x, self.weight_fp32(), None, None)
+
+
+def invalidate_derived(model: nn.Module) -> None:
+    """Drop every value cached from a parameter / buffer (RMSNorm fp32 weights, F8Linear quantising scales, batched
+    modulation tables) after buffers were rewritten IN PLACE (e.g. parallel.broadcast_state's copy_)."""
+    for m in model.modules():
+        if isinstance(m, RMSNorm):
+            m.invalidate_derived()
+        elif isinstance(m, F8Linear):
+            m.__dict__.pop("_qscale_cache", None)
+    model.__dict__.pop("_mod_bank", None)
 
 
 class QKNorm(nn.Module):
@@ -180,64 +221,97 @@ class Modulation(nn.Module):
 
 
 class ModulationBank:
-    """Every Modulation.lin of a model as ONE batched launch pair (fluxb200_modulation_batched): all of them
-    consume the same `vec`, so a step needs one SiLU+quantise pass per layer scale and one weight-streaming
-    GEMV over the concatenated rows (3.2 GB of e4m3 per step for Flux-dev) instead of 76 x (silu, quantise,
-    GEMV) launches.  Results are views into one [B, sum(N)] buffer, chunked exactly like Modulation.forward."""
+    """Every Modulation.lin of a model as ONE batched launch: all of them consume the same `vec`, so a step needs one
+    weight-streaming GEMV over the concatenated rows instead of 76 x (silu [, quantise], GEMV) launches.
+
+    * F8Linear modulation (frozen): fluxb200_modulation_batched -- one SiLU+quantise pass per layer scale + the GEMV
+      over 3.2 GB of e4m3 per step for Flux-dev.
+    * nn.Linear modulation (quantize_modulation=False, BASELINE config c5): fluxb200_modulation_batched_bf16 -- the
+      same GEMV over 6.5 GB of bf16 weights, SiLU fused into the staging of `vec`.
+    Results are views into one [B, sum(N)] buffer, chunked exactly like Modulation.forward."""
 
     COLS_PER_BLOCK = 64
+    MAX_BATCH = 16
 
     def __init__(self, mods):
-        import ctypes as C
-
         self.mods = list(mods)
         lins = [m.lin for m in self.mods]
-        if not lins or not _frozen(*lins):
-            raise ValueError("ModulationBank needs frozen F8Linear modulation layers")
+        if not lins:
+            raise ValueError("ModulationBank needs at least one Modulation")
+        self.f8 = all(isinstance(l, F8Linear) for l in lins)
         self.K = lins[0].in_features
-        self.in_dtype = lins[0].input_float8_dtype
-        if any(l.in_features != self.K or l.input_float8_dtype != self.in_dtype or
-               l.float8_dtype != torch.float8_e4m3fn for l in lins):
-            raise ValueError("ModulationBank: heterogeneous modulation layers")
-        if self.K % 16 or self.K > 4096:
-            raise ValueError(f"ModulationBank: K={self.K} not supported by the batched kernel")
+        if self.f8:
+            if not _frozen(*lins):
+                raise ValueError("ModulationBank needs frozen F8Linear modulation layers")
+            self.in_dtype = lins[0].input_float8_dtype
+            if any(l.in_features != self.K or l.input_float8_dtype != self.in_dtype or
+                   l.float8_dtype != torch.float8_e4m3fn for l in lins):
+                raise ValueError("ModulationBank: heterogeneous modulation layers")
+            if self.K % 16 or self.K > 4096:
+                raise ValueError(f"ModulationBank: K={self.K} not supported by the batched kernel")
+        else:
+            if any(isinstance(l, F8Linear) or not isinstance(l, nn.Linear) for l in lins):
+                raise ValueError("ModulationBank: a mix of F8Linear and nn.Linear modulation layers")
+            if any(l.in_features != self.K or l.weight.dtype != BF16 or not l.weight.is_cuda or
+                   not l.weight.is_contiguous() or (l.bias is not None and l.bias.dtype != BF16) for l in lins):
+                raise ValueError("ModulationBank: bf16 modulation needs contiguous bfloat16 CUDA weights of one width")
+            if self.K % 32 or self.K > 4096:
+                raise ValueError(f"ModulationBank: K={self.K} not supported by the batched bf16 kernel")
         table = (cabi.GemvLayer * len(lins))()
         self._keep = []
         off = blocks = 0
         self.offsets = []
         for i, l in enumerate(lins):
-            q = l.qscale
-            self._keep += [l.float8_data, l.bias, q, l.input_scale_reciprocal, l.scale_reciprocal]
-            table[i].w, table[i].bias = l.float8_data.data_ptr(), cabi.ptr(l.bias)
-            table[i].in_qscale = q.data_ptr()
-            table[i].a_scale_recip, table[i].w_scale_recip = l.input_scale_reciprocal.data_ptr(), l.scale_reciprocal.data_ptr()
+            if self.f8:
+                q = l.qscale
+                self._keep += [l.float8_data, l.bias, q, l.input_scale_reciprocal, l.scale_reciprocal]
+                table[i].w, table[i].in_qscale = l.float8_data.data_ptr(), q.data_ptr()
+                table[i].a_scale_recip = l.input_scale_reciprocal.data_ptr()
+                table[i].w_scale_recip = l.scale_reciprocal.data_ptr()
+            else:
+                self._keep += [l.weight, l.bias]
+                table[i].w = l.weight.data_ptr()
+            table[i].bias = cabi.ptr(l.bias)
             table[i].N, table[i].out_offset, table[i].block_start = l.out_features, off, blocks
             self.offsets.append(off)
             off += l.out_features
             blocks += (l.out_features + self.COLS_PER_BLOCK - 1) // self.COLS_PER_BLOCK
         self.total_n, self.total_blocks = off, blocks
-        dev = lins[0].float8_data.device
+        dev = (lins[0].float8_data if self.f8 else lins[0].weight).device
         self.table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
         self.signature = self._signature()
 
     def _signature(self):
-        return tuple((m.lin.float8_data.data_ptr(), m.lin.input_scale.data_ptr(), m.lin.scale_reciprocal.data_ptr())
-                     for m in self.mods)
+        if self.f8:
+            return tuple((m.lin.float8_data.data_ptr(), m.lin.input_scale.data_ptr(), m.lin.scale_reciprocal.data_ptr(),
+                          id(m.lin.input_scale)) for m in self.mods)
+        return tuple((id(m.lin.weight), m.lin.weight.data_ptr(), cabi.ptr(m.lin.bias)) for m in self.mods)
 
     def stale(self) -> bool:
         """True when a layer's buffers were replaced (e.g. LoRA fuse through set_weight_tensor)."""
-        return self._signature() != self.signature
+        try:
+            return self._signature() != self.signature
+        except AttributeError:  # a layer changed type under us
+            return True
 
     def __call__(self, vec: Tensor):
         B = vec.shape[0]
+        if B > self.MAX_BATCH:
+            raise ValueError(f"ModulationBank: batch {B} > {self.MAX_BATCH} (use the per-block Modulation path)")
         vec = vec.contiguous()
         out = torch.empty((B, self.total_n), dtype=BF16, device=vec.device)
-        aq = torch.empty((len(self.mods), B, self.K), dtype=torch.uint8, device=vec.device)
-        ops._timed("modulation_batched", float(self.total_n) * self.K,
-                   lambda: cabi.check(cabi.load().fluxb200_modulation_batched(
-                       vec.data_ptr(), self.table.data_ptr(), len(self.mods), self.total_blocks, aq.data_ptr(),
-                       out.data_ptr(), out.stride(0), B, self.K, cabi.fp8_fmt(self.in_dtype), cabi.E4M3,
-                       cabi.stream_ptr()), "fluxb200_modulation_batched"))
+        if self.f8:
+            aq = torch.empty((len(self.mods), B, self.K), dtype=torch.uint8, device=vec.device)
+            ops._timed("modulation_batched", float(self.total_n) * self.K,
+                       lambda: cabi.check(cabi.load().fluxb200_modulation_batched(
+                           vec.data_ptr(), self.table.data_ptr(), len(self.mods), self.total_blocks, aq.data_ptr(),
+                           out.data_ptr(), out.stride(0), B, self.K, cabi.fp8_fmt(self.in_dtype), cabi.E4M3,
+                           cabi.stream_ptr()), "fluxb200_modulation_batched"))
+        else:
+            ops._timed("modulation_batched", 2.0 * self.total_n * self.K,
+                       lambda: cabi.check(cabi.load().fluxb200_modulation_batched_bf16(
+                           vec.data_ptr(), self.table.data_ptr(), len(self.mods), self.total_blocks, out.data_ptr(),
+                           out.stride(0), B, self.K, cabi.stream_ptr()), "fluxb200_modulation_batched_bf16"))
         res = []
         for m, off in zip(self.mods, self.offsets):
             chunks = out[:, None, off:off + m.lin.out_features].chunk(m.multiplier, dim=-1)
@@ -292,21 +366,23 @@ class DoubleStreamBlock(nn.Module):
         return (_frozen(*lins) and img.dtype == BF16 and txt.dtype == BF16 and self.hidden_size % 256 == 0
                 and self.hidden_size <= 4096 and self.hidden_size // self.num_heads == HEAD_DIM)
 
-    def forward(self, img: Tensor, txt: Tensor, vec: Tensor, pe: Tensor, mods=None) -> Tuple[Tensor, Tensor]:
+    def forward(self, img: Tensor, txt: Tensor, vec: Tensor, pe: Tensor, mods=None, rope=None) -> Tuple[Tensor, Tensor]:
+        """Reference signature (img, txt, vec, pe).  `mods` (this block's precomputed modulation outputs) and `rope`
+        (the (cos, sin) pair extracted from `pe`) are optional hand-downs from Flux.forward."""
         cabi.require_cuda(img, txt, vec, pe)
         if mods is None:
             mods = (self.img_mod(vec), self.txt_mod(vec))
         if self._fusable(img, txt):
-            return self._forward_fused(img, txt, pe, mods)
+            return self._forward_fused(img, txt, pe, mods, rope)
         return self._forward_eager(img, txt, pe, mods)
 
-    def _forward_fused(self, img, txt, pe, mods):
+    def _forward_fused(self, img, txt, pe, mods, rope=None):
         (img_mod1, img_mod2), (txt_mod1, txt_mod2) = mods
         B, L, D = img.shape
         T = txt.shape[1]
         S, H = L + T, self.num_heads
         img, txt = img.contiguous(), txt.contiguous()
-        cos, sin = rope_cos_sin(pe)
+        cos, sin = rope if rope is not None else rope_cos_sin(pe)
         dev = img.device
         q = torch.empty((B, H, S, HEAD_DIM), dtype=BF16, device=dev)
         k, v = torch.empty_like(q), torch.empty_like(q)
@@ -436,19 +512,19 @@ class SingleStreamBlock(nn.Module):
                 and self.mlp_hidden_dim % 128 == 0
                 and self.linear1.input_float8_dtype == self.linear2.input_float8_dtype)
 
-    def forward(self, x: Tensor, vec: Tensor, pe: Tensor, mod=None) -> Tensor:
+    def forward(self, x: Tensor, vec: Tensor, pe: Tensor, mod=None, rope=None) -> Tensor:
         cabi.require_cuda(x, vec, pe)
         if mod is None:
             mod = self.modulation(vec)[0]
         if self._fusable(x):
-            return self._forward_fused(x, pe, mod)
+            return self._forward_fused(x, pe, mod, rope)
         return self._forward_eager(x, pe, mod)
 
-    def _forward_fused(self, x, pe, mod):
+    def _forward_fused(self, x, pe, mod, rope=None):
         B, S, D = x.shape
         H, l1, l2 = self.num_heads, self.linear1, self.linear2
         x = x.contiguous()
-        cos, sin = rope_cos_sin(pe)
+        cos, sin = rope if rope is not None else rope_cos_sin(pe)
         dev = x.device
         a8, _ = ops.ln_mod_quant(x, mod.shift, mod.scale, l1.qscale, l1.input_float8_dtype)
         q = torch.empty((B, H, S, HEAD_DIM), dtype=BF16, device=dev)

@@ -634,6 +634,107 @@ __global__ void __launch_bounds__(kModMmaWarps * 32, 4) gemv_layers_mma_kernel(
   }
 }
 
+// bf16 form of the batched modulation GEMV: Modulation.lin left as nn.Linear (quantize_modulation = False, BASELINE
+// config c5; reference modules/flux_model.py:233-257 with float8_quantize.py:346 skipping the swap) =
+//   out[b, n] = bf16( sum_k bf16(silu(vec[b,k])) * W[n,k] + bias[n] )       (fp32 accumulate, as cuBLAS does)
+// Same structure as gemv_layers_mma_kernel: the bf16 WEIGHTS are the 16-row A operand of mma.sync.m16n8k16 (bf16
+// operands, fp32 accumulate), the batch (<= 8 rows per pass) the B operand.  K is consumed in 64-byte (32-element)
+// chunks permuted so that a lane's load is one contiguous 16 bytes: quad lane t owns elements [8t, 8t+8) of the chunk;
+// words (0,1) of it are the (k 2t.., k 2t+8..) slots of the chunk's first MMA, words (2,3) of the second, and the
+// activation fragment is read from the same elements.  silu is applied while the block stages vec into shared
+// memory (every layer consumes the same bf16(silu(vec)): there is no per-layer quantisation), so the whole step's
+// modulation is ONE launch streaming 6.46 GB of bf16 weights.
+__device__ __forceinline__ void mma_m16n8k16_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// row pitch 2K + 64 bytes: a quarter-warp (two batch rows x four 16-byte pieces) covers all 32 banks exactly once
+constexpr int kModBf16Pad = 64;
+
+__global__ void __launch_bounds__(kModMmaWarps * 32, 4) gemv_layers_bf16_kernel(
+    const fluxb200_gemv_layer* __restrict__ layers, int num_layers, const __nv_bfloat16* __restrict__ vec,
+    __nv_bfloat16* __restrict__ out, int64_t ld_out, int B, int K) {
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t a_sm8[];
+  __shared__ int s_layer;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_layer = 0;
+  __syncthreads();
+  {
+    int mine = 0;
+    for (int i = threadIdx.x; i < num_layers; i += blockDim.x)
+      mine += layers[i].block_start <= static_cast<int>(blockIdx.x) ? 1 : 0;
+    if (mine) atomicAdd(&s_layer, mine);
+  }
+  __syncthreads();
+  const int l = s_layer - 1;
+  const fluxb200_gemv_layer L = layers[l];
+  const int pitch = 2 * K + kModBf16Pad;
+  const int n0 = (static_cast<int>(blockIdx.x) - L.block_start) * kModColsPerBlock + warp * 16;
+  const int g = lane >> 2, t = lane & 3;
+  const uint8_t* wbase = static_cast<const uint8_t*>(L.w) + t * 16;
+  const uint8_t* wr0 = wbase + static_cast<int64_t>(min(n0 + g, L.N - 1)) * K * 2;
+  const uint8_t* wr1 = wbase + static_cast<int64_t>(min(n0 + g + 8, L.N - 1)) * K * 2;
+  const __nv_bfloat16* bias = static_cast<const __nv_bfloat16*>(L.bias);
+  const int chunks = K / 32;
+
+  for (int m0 = 0; m0 < B; m0 += 8) {
+    const int mt = min(8, B - m0);
+    __syncthreads();
+    {  // bf16(silu(vec)) rows m0..m0+mt-1; row `mt` of the buffer is all zeros (batch padding of the B operand)
+      for (int i = threadIdx.x; i < mt * K; i += blockDim.x) {
+        const int r = i / K, c = i - r * K;
+        const float v = __bfloat162float(vec[static_cast<int64_t>(m0 + r) * K + c]);
+        *reinterpret_cast<__nv_bfloat16*>(a_sm8 + r * pitch + c * 2) = __float2bfloat16_rn(v / (1.f + expf(-v)));
+      }
+      for (int i = threadIdx.x; i < pitch / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_sm8 + mt * pitch)[i] = 0u;
+    }
+    __syncthreads();
+    if (n0 < L.N) {
+      const uint8_t* ab = a_sm8 + (g < mt ? g : mt) * pitch + t * 16;
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+      auto consume = [&](const uint4& w0, const uint4& w1, int kc) {
+        const uint4 b = *reinterpret_cast<const uint4*>(ab + kc * 64);
+        mma_m16n8k16_bf16(c0, w0.x, w1.x, w0.y, w1.y, b.x, b.y);
+        mma_m16n8k16_bf16(c1, w0.z, w1.z, w0.w, w1.w, b.z, b.w);
+      };
+      uint4 bufA[kModU][2], bufB[kModU][2];
+      auto fetch = [&](uint4 (&buf)[kModU][2], int kc0) {
+#pragma unroll
+        for (int u = 0; u < kModU; ++u) {
+          buf[u][0] = __ldg(reinterpret_cast<const uint4*>(wr0 + (kc0 + u) * 64));
+          buf[u][1] = __ldg(reinterpret_cast<const uint4*>(wr1 + (kc0 + u) * 64));
+        }
+      };
+      const int full = chunks / (2 * kModU) * (2 * kModU);
+      if (full > 0) fetch(bufA, 0);
+      for (int kc0 = 0; kc0 < full; kc0 += 2 * kModU) {
+        fetch(bufB, kc0 + kModU);
+#pragma unroll
+        for (int u = 0; u < kModU; ++u) consume(bufA[u][0], bufA[u][1], kc0 + u);
+        if (kc0 + 2 * kModU < full) fetch(bufA, kc0 + 2 * kModU);
+#pragma unroll
+        for (int u = 0; u < kModU; ++u) consume(bufB[u][0], bufB[u][1], kc0 + kModU + u);
+      }
+      for (int kc = full; kc < chunks; ++kc) {
+        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(wr0 + kc * 64));
+        const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(wr1 + kc * 64));
+        consume(w0, w1, kc);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = n0 + g + (j >> 1) * 8, row = t * 2 + (j & 1);
+        if (row < mt && col < L.N) {
+          const float bb = bias ? __bfloat162float(bias[col]) : 0.f;
+          out[static_cast<int64_t>(m0 + row) * ld_out + L.out_offset + col] = __float2bfloat16_rn(c0[j] + c1[j] + bb);
+        }
+      }
+    }
+  }
+}
+
 static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
   int64_t blocks = (work_items + threads - 1) / threads;
   int64_t cap = static_cast<int64_t>(sm_count()) * max_blocks_per_sm;
@@ -831,6 +932,22 @@ extern "C" int fluxb200_modulation_batched(const void* vec, const fluxb200_gemv_
     if (nk <= 1) FB_MOD(1, 1); else if (nk <= 2) FB_MOD(1, 2); else if (nk <= 6) FB_MOD(1, 6); else FB_MOD(1, 8);
   }
 #undef FB_MOD
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_modulation_batched_bf16(const void* vec, const fluxb200_gemv_layer* layers, int num_layers,
+                                                int total_blocks, void* out, int64_t ld_out, int B, int K,
+                                                fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(vec && layers && out, "fluxb200_modulation_batched_bf16: null operand");
+  FB_REQUIRE(num_layers > 0 && total_blocks > 0 && B > 0 && B <= 16, "fluxb200_modulation_batched_bf16: bad sizes");
+  FB_REQUIRE(K % 32 == 0 && K <= 4096, "fluxb200_modulation_batched_bf16: K=%d must be a multiple of 32 and <= 4096", K);
+  const size_t smem = static_cast<size_t>((B < 8 ? B : 8) + 1) * (2 * K + kModBf16Pad);
+  auto kern = gemv_layers_bf16_kernel;
+  if (smem > 48 * 1024) FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FB_CUDA_OK(launch_kernel(kern, dim3(total_blocks), dim3(kModMmaWarps * 32), smem, stream, 1, layers, num_layers,
+                           static_cast<const __nv_bfloat16*>(vec), static_cast<__nv_bfloat16*>(out), ld_out, B, K));
   FB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -40,6 +40,13 @@ _SCALE_KEYS = ("scale", "input_scale", "scale_reciprocal", "input_scale_reciproc
 SCALE_SEMANTICS = "cuda"
 
 
+def _version(t: torch.Tensor) -> int:
+    try:
+        return t._version
+    except RuntimeError:  # inference tensors do not track versions
+        return 0
+
+
 def mul_scale(scale: torch.Tensor) -> torch.Tensor:
     """The value the quantisation kernels multiply by for a given F8Linear scale buffer."""
     if SCALE_SEMANTICS == "cuda":
@@ -137,13 +144,16 @@ class F8Linear(nn.Module):
 
     @property
     def qscale(self) -> torch.Tensor:
-        """input_scale as the quantising kernels consume it (see SCALE_SEMANTICS); cached once frozen."""
+        """input_scale as the quantising kernels consume it (see SCALE_SEMANTICS); cached once frozen.  The cache is
+        keyed on the identity of the `input_scale` buffer and, where the tensor tracks one, its in-place version; code
+        that rewrites the buffer in place under inference_mode calls blocks.invalidate_derived (broadcast_state does)."""
         if self.input_scale_initialized:
             c = self.__dict__.get("_qscale_cache")
-            if c is None or c[0] is not self.input_scale or c[1] != SCALE_SEMANTICS:
-                c = (self.input_scale, SCALE_SEMANTICS, mul_scale(self.input_scale))
+            key = (id(self.input_scale), self.input_scale.data_ptr(), _version(self.input_scale), SCALE_SEMANTICS)
+            if c is None or c[0] != key:
+                c = (key, mul_scale(self.input_scale))
                 self.__dict__["_qscale_cache"] = c
-            return c[2]
+            return c[1]
         return mul_scale(self.input_scale)
 
     def quantize_input(self, x: torch.Tensor):
@@ -186,6 +196,15 @@ class F8Linear(nn.Module):
             return
         if tuple(f8.shape) != full_shape or bool((w != 0).any()):
             raise RuntimeError(f"Weight tensor not found or has incorrect shape in state dict: {sd.keys()}")
+        if f8.dtype not in (torch.float8_e4m3fn, torch.float8_e5m2):
+            raise RuntimeError(f"float8_data has dtype {f8.dtype}, expected a float8 tensor: {sd.keys()}")
+        if w.dtype != torch.bfloat16 or ("bias" in sd and sd["bias"].dtype != torch.bfloat16):
+            # the kernels read bias as bf16 and write bf16; the placeholder's dtype defines out_dtype (reference
+            # float8_quantize.py:204-206, 290).  A float16 flow would be silently mis-read: refuse it.
+            raise cabi.FluxB200Error(
+                f"prequantised F8Linear state with weight placeholder {w.dtype} / bias "
+                f"{sd['bias'].dtype if 'bias' in sd else None}: the B200 path supports bfloat16 flows only "
+                "(flow_dtype=bfloat16); re-save the checkpoint from a bfloat16 flow")
         self._buffers["float8_data"] = f8
         self._parameters["weight"] = nn.Parameter(torch.zeros(1, dtype=w.dtype, device=w.device), requires_grad=False)
         if "bias" in sd:

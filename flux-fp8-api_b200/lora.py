@@ -12,8 +12,9 @@ diffusers -> BFL key conversion (lora_loading.py:36-461) is string manipulation 
 reference (out of scope).
 
 Differences by design: the quantised layer's buffers (`float8_data`, `scale`, `scale_reciprocal`) are updated IN
-PLACE, so a captured CUDA graph / ModulationBank over the model keeps working after a swap; no full-size fp32
-temporaries are made (the reference makes five per layer).
+PLACE, so a captured CUDA graph / ModulationBank over the model keeps working after a swap (pipeline.GraphedStep owns
+the per-request tensors its kernels read; a LoRA on txt_in / vector_in / guidance_in bumps Flux._invariant_epoch and
+the graph re-captures on its next call); no full-size fp32 temporaries are made (the reference makes five per layer).
 """
 from __future__ import annotations
 
@@ -106,11 +107,18 @@ def _fuse_into_linear(module: nn.Linear, lora_sd, lora_scale: float, unfuse: boo
     module.weight.data.copy_(((w - delta) if unfuse else (w + delta)).to(module.weight.dtype))
 
 
+#: sub-modules whose outputs Flux caches per request (model._StepInvariantCache): a LoRA touching them changes values a
+#: captured CUDA graph has baked in, so holders of such state must re-derive it (Flux.invalidate_step_invariants bumps
+#: the epoch pipeline.GraphedStep checks).  Every other layer is updated in place and needs nothing.
+_STEP_INVARIANT_PREFIXES = ("txt_in", "vector_in", "guidance_in")
+
+
 def _walk(model: nn.Module, lora_weights, lora_scale: float, unfuse: bool):
     if isinstance(lora_weights, LoraWeights):
         if unfuse:
             lora_scale = lora_weights.scale
         lora_weights = lora_weights.weights
+    touched_invariants = False
     for key in _keys_without_ab(lora_weights):
         module = get_module_for_key(key, model)
         lora_sd = get_lora_for_key(key, lora_weights)
@@ -122,26 +130,38 @@ def _walk(model: nn.Module, lora_weights, lora_scale: float, unfuse: bool):
             _fuse_into_linear(module, lora_sd, lora_scale, unfuse)
         else:
             raise TypeError(f"{key}: cannot fuse a LoRA into {type(module).__name__}")
-    # Flux caches the step-invariant embeddings of a request (txt_in(txt), pe); weights under them may have changed.
-    # (A CUDA graph captured earlier has those cached tensors baked in: after a LoRA on `txt_in` re-capture it.)
-    if hasattr(model, "reset_request_cache"):
-        model.reset_request_cache()
+        touched_invariants |= key.split(".")[0] in _STEP_INVARIANT_PREFIXES
+    if touched_invariants and hasattr(model, "invalidate_step_invariants"):
+        model.invalidate_step_invariants()
     return model
 
 
-def apply_lora_to_model(model: nn.Module, lora_path, lora_scale: float = 1.0, return_lora_resolved: bool = False):
-    """lora_loading.py:634-692.  `lora_path` is an already-loaded BFL-layout state dict or a LoraWeights."""
+def _resolve(lora_path):
+    """A loaded BFL-layout state dict, a LoraWeights, or the path of a .safetensors file holding one.  (The diffusers
+    / kohya -> BFL key conversion of lora_loading.py:36-461 is string manipulation off the hot path and stays with the
+    reference: convert once with it, save, load here.)"""
     if isinstance(lora_path, str):
-        raise NotImplementedError("pass a loaded BFL-layout LoRA state dict; file loading / diffusers key conversion "
-                                  "stays with the reference's lora_loading.py")
-    model = _walk(model, lora_path, lora_scale, unfuse=False)
+        from safetensors.torch import load_file
+
+        sd = load_file(lora_path, device="cpu")
+        bad = [k for k in sd if not (k.endswith(".lora_A.weight") or k.endswith(".lora_B.weight") or k.endswith(".alpha"))
+               or k.startswith(("transformer.", "lora_unet_"))]
+        if bad:
+            raise ValueError(f"{lora_path}: not in the BFL key layout (e.g. {bad[0]!r}); convert it with the reference's "
+                             "lora_loading.convert_* helpers first")
+        return sd
+    return lora_path
+
+
+def apply_lora_to_model(model: nn.Module, lora_path, lora_scale: float = 1.0, return_lora_resolved: bool = False):
+    """lora_loading.py:634-692.  `lora_path`: BFL-layout state dict, LoraWeights, or a .safetensors path."""
+    lora = _resolve(lora_path)
+    model = _walk(model, lora, lora_scale, unfuse=False)
     if return_lora_resolved:
-        return model, (lora_path.weights if isinstance(lora_path, LoraWeights) else lora_path)
+        return model, (lora.weights if isinstance(lora, LoraWeights) else lora)
     return model
 
 
 def remove_lora_from_module(model: nn.Module, lora_path, lora_scale: float = 1.0):
     """lora_loading.py:695-754."""
-    if isinstance(lora_path, str):
-        raise NotImplementedError("pass a loaded BFL-layout LoRA state dict")
-    return _walk(model, lora_path, lora_scale, unfuse=True)
+    return _walk(model, _resolve(lora_path), lora_scale, unfuse=True)

@@ -21,7 +21,8 @@ import torch
 from torch import Tensor, nn
 
 from . import _cabi as cabi
-from .blocks import DoubleStreamBlock, EmbedND, ModulationBank, SingleStreamBlock, tensor_version
+from .blocks import (DoubleStreamBlock, EmbedND, ModulationBank, SingleStreamBlock, extract_cos_sin,
+                     tensor_version)
 from .f8linear import F8Linear
 
 BF16 = torch.bfloat16
@@ -161,18 +162,92 @@ class Flux(nn.Module):
             for _ in range(p.depth_single_blocks)])
         self.final_layer = LastLayer(self.hidden_size, 1, self.out_channels)
         self._cache = _StepInvariantCache()
+        #: bumped whenever weights under the step-invariant embeddings change (LoRA on txt_in / vector_in /
+        #: guidance_in): holders of derived state (pipeline.GraphedStep) compare it and re-capture
+        self._invariant_epoch = 0
         #: set False to recompute txt_in / vector_in / pe every step exactly as the reference does
         self.cache_step_invariants = True
         #: one batched launch for all Modulation.lin of a step (False: each block runs its own, as the reference)
         self.batch_modulation = True
 
+    # ---- request cache ---------------------------------------------------------------------------------------
     def reset_request_cache(self) -> None:
         self._cache.clear()
 
+    def invalidate_step_invariants(self) -> None:
+        """Weights that the cached per-request embeddings were computed from have changed."""
+        self._cache.clear()
+        self._invariant_epoch += 1
+
+    def use_request_cache(self, cache: "_StepInvariantCache"):
+        """Context manager: run forwards against `cache` instead of the model's own.  pipeline.GraphedStep gives every
+        captured graph a private cache, so the tensors its kernels read (txt_in(txt), the vector / guidance embeddings,
+        pe, cos/sin) stay alive for as long as the graph does, whatever other requests or sessions do to the model's
+        shared cache."""
+        model = self
+
+        class _Swap:
+            def __enter__(self_inner):
+                self_inner.prev, model._cache = model._cache, cache
+
+            def __exit__(self_inner, *exc):
+                model._cache = self_inner.prev
+
+        return _Swap()
+
+    # ---- LoRA management (reference modules/flux_model.py:621-670) ----------------------------------------
+    def get_lora(self, identifier: str):
+        for lora in self.loras:
+            if lora.path == identifier or lora.name == identifier:
+                return lora
+
+    def has_lora(self, identifier: str):
+        for lora in self.loras:
+            if lora.path == identifier or lora.name == identifier:
+                return True
+
+    def load_lora(self, path, scale: float, name: str = None):
+        """Fuse a LoRA into the quantised weights on the device (lora.apply_lora_to_model).  `path` is a .safetensors
+        file in the BFL key layout or an already-loaded state dict (then `name` identifies it)."""
+        from . import lora as L
+
+        ident = path if isinstance(path, str) else (name or f"<state-dict {id(path):x}>")
+        if self.has_lora(ident):
+            lora = self.get_lora(ident)
+            if lora.scale == scale:
+                import warnings
+
+                warnings.warn(f"Lora {lora.name} already loaded with same scale - ignoring!")
+            else:
+                L.remove_lora_from_module(self, lora, lora.scale)
+                L.apply_lora_to_model(self, lora, scale)
+                for idx, lora_ in enumerate(self.loras):
+                    if lora_.path == lora.path:
+                        self.loras[idx].scale = scale
+                        break
+        else:
+            _, weights = L.apply_lora_to_model(self, path, scale, return_lora_resolved=True)
+            self.loras.append(L.LoraWeights(weights, ident, name, scale))
+
+    def unload_lora(self, path_or_identifier: str):
+        from . import lora as L
+
+        for idx, lora_ in enumerate(list(self.loras)):
+            if lora_.path == path_or_identifier or lora_.name == path_or_identifier:
+                L.remove_lora_from_module(self, lora_.weights, lora_.scale)
+                self.loras.pop(idx)
+                return True
+        import warnings
+
+        warnings.warn(f"Couldn't remove lora {path_or_identifier} as it wasn't found fused to the model!")
+        return False
+
+    # ---- modulation ------------------------------------------------------------------------------------------
     def _modulation_bank(self, vec: Tensor) -> Optional[ModulationBank]:
-        """The batched modulation launch, built lazily once every Modulation.lin is a frozen F8Linear (None while
-        calibrating or when modulation is left in bf16, quantize_modulation=False)."""
-        if not self.batch_modulation or vec.dtype != BF16:
+        """The batched modulation launch, built lazily once every Modulation.lin is a frozen F8Linear -- or when all
+        of them are bf16 nn.Linear (quantize_modulation=False).  None while calibrating, for mixed layer types, and
+        for batches beyond the kernel's 16 rows (then every block runs its own Modulation, as the reference does)."""
+        if not self.batch_modulation or vec.dtype != BF16 or vec.shape[0] > ModulationBank.MAX_BATCH:
             return None
         bank = self.__dict__.get("_mod_bank")
         if bank is not None and not bank.stale():
@@ -214,22 +289,59 @@ class Flux(nn.Module):
                                   lambda: self.guidance_in(timestep_embedding(guidance, 256).type(self.dtype)))
         vec = vec + cache.get("vector", (y,), lambda: self.vector_in(y))
         txt = cache.get("txt", (txt,), lambda: self.txt_in(txt))
-        pe = cache.get("pe", (txt_ids, img_ids), lambda: self.pe_embedder(torch.cat((txt_ids, img_ids), dim=1)))
+
+        def _pe():
+            pe_ = self.pe_embedder(torch.cat((txt_ids, img_ids), dim=1))
+            # the (cos, sin) pair the kernels read is extracted HERE, next to the table it comes from, and handed
+            # down to every block: no cache keyed on addresses anywhere on the steady-state path
+            return (pe_, extract_cos_sin(pe_) if pe_.dtype == BF16 else None)
+
+        pe, rope = cache.get("pe", (txt_ids, img_ids), _pe)
 
         T = txt.shape[1]
         bank = self._modulation_bank(vec)
         if bank is None:
             for block in self.double_blocks:
-                img, txt = block(img=img, txt=txt, vec=vec, pe=pe)
+                img, txt = block(img=img, txt=txt, vec=vec, pe=pe, rope=rope)
             x = torch.cat((txt, img), 1)
             for block in self.single_blocks:
-                x = block(x, vec=vec, pe=pe)
+                x = block(x, vec=vec, pe=pe, rope=rope)
         else:
             mods = iter(bank(vec))  # every block's shift/scale/gate from one batched launch
             for block in self.double_blocks:
-                img, txt = block(img=img, txt=txt, vec=vec, pe=pe, mods=(next(mods), next(mods)))
+                img, txt = block(img=img, txt=txt, vec=vec, pe=pe, mods=(next(mods), next(mods)), rope=rope)
             x = torch.cat((txt, img), 1)
             for block in self.single_blocks:
-                x = block(x, vec=vec, pe=pe, mod=next(mods)[0])
+                x = block(x, vec=vec, pe=pe, mod=next(mods)[0], rope=rope)
         x = x[:, T:, ...]
         return self.final_layer(x, vec)
+
+    @classmethod
+    def from_pretrained(cls, path: str, dtype: torch.dtype = torch.float16) -> "Flux":
+        """Reference modules/flux_model.py:718-734: `path` is a JSON model spec (the reference's ModelSpec fields that
+        Flux reads: params, prequantized_flow, quantize_modulation, quantize_flow_embedder_layers, ckpt_path) whose
+        `ckpt_path` names a .safetensors state dict in the BFL key layout.  Returns the model on the CPU, like the
+        reference; move it with .to("cuda") before use (there is no CPU compute path)."""
+        import json
+        from pathlib import Path
+
+        from safetensors.torch import load_file
+
+        p = Path(path)
+        if not p.exists():
+            raise ValueError(f"Path {path} does not exist")
+        if not p.is_file():
+            raise ValueError(f"Path {path} is not a file")
+        cfg = json.loads(p.read_text())
+        known = FluxParams.__dataclass_fields__.keys()
+        params = FluxParams(**{k: v for k, v in cfg["params"].items() if k in known})
+        spec = FluxSpec(params=params, prequantized_flow=cfg.get("prequantized_flow", False),
+                        quantize_modulation=cfg.get("quantize_modulation", True),
+                        quantize_flow_embedder_layers=cfg.get("quantize_flow_embedder_layers", False))
+        with torch.device("meta"):
+            klass = cls(spec, dtype=dtype)
+            if not spec.prequantized_flow:
+                klass.type(dtype)
+        ckpt = load_file(cfg["ckpt_path"], device="cpu")
+        klass.load_state_dict(ckpt, assign=True)
+        return klass.to("cpu")

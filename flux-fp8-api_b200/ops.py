@@ -22,6 +22,12 @@ BF16 = torch.bfloat16
 KERNEL_TIMELINE = None
 
 
+def _want(t: Optional[Tensor], dtype: torch.dtype, what: str) -> None:
+    """The kernels take raw pointers: an operand of another dtype would be silently mis-read, so refuse it here."""
+    if t is not None and t.dtype != dtype:
+        raise ValueError(f"{what} must be {dtype}, got {t.dtype}")
+
+
 def _contig(t: Tensor, what: str) -> Tensor:
     if not t.is_contiguous():
         raise ValueError(f"{what} must be contiguous")
@@ -103,6 +109,8 @@ def ln_mod_quant(x: Tensor, shift: Tensor, scale: Tensor, in_scale: Optional[Ten
     """LayerNorm(no affine) -> (1+scale)*x+shift -> quantise.  x [B,L,D]; shift/scale [B,1,D] or [B,D]
     (possibly strided views into the modulation output)."""
     cabi.require_cuda(x, shift, scale)
+    _want(x, BF16, "ln_mod_quant: x"), _want(shift, BF16, "ln_mod_quant: shift"), _want(scale, BF16, "ln_mod_quant: scale")
+    _want(in_scale, torch.float32, "ln_mod_quant: in_scale")
     B, L, D = x.shape
     if x.stride(-1) != 1 or x.stride(0) != L * x.stride(1):
         x = x.contiguous()
@@ -132,6 +140,8 @@ def ln_mod_quant_pair(items, dtype: torch.dtype, eps: float = 1e-6):
     total = 0.0
     for i, (x, shift, scale, in_scale) in enumerate(items):
         cabi.require_cuda(x, shift, scale, in_scale)
+        _want(x, BF16, "ln_mod_quant_pair: x"), _want(shift, BF16, "ln_mod_quant_pair: shift")
+        _want(scale, BF16, "ln_mod_quant_pair: scale"), _want(in_scale, torch.float32, "ln_mod_quant_pair: in_scale")
         B, L, Dx = x.shape
         if Dx != D:
             raise ValueError("ln_mod_quant_pair: both streams must share the hidden size")
@@ -158,6 +168,8 @@ def ln_mod_quant_pair(items, dtype: torch.dtype, eps: float = 1e-6):
 def qknorm_rope(x: Tensor, norm_w: Optional[Tensor], cos: Optional[Tensor], sin: Optional[Tensor]) -> Tensor:
     """Stand-alone QKNorm + RoPE on [B,H,S,128] (cos/sin: bf16 [Bp,S,64], Bp in {1,B})."""
     cabi.require_cuda(x)
+    _want(x, BF16, "qknorm_rope: x"), _want(norm_w, torch.float32, "qknorm_rope: norm_w")
+    _want(cos, BF16, "qknorm_rope: cos"), _want(sin, BF16, "qknorm_rope: sin")
     B, H, S, D = x.shape
     if D != 128:
         raise ValueError("head_dim must be 128")
@@ -175,6 +187,8 @@ def qknorm_rope(x: Tensor, norm_w: Optional[Tensor], cos: Optional[Tensor], sin:
 
 def f8_gemv(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tensor, w_scale_recip: Tensor) -> Tensor:
     cabi.require_cuda(a, w)
+    _want(bias, BF16, "f8_gemv: bias"), _want(a_scale_recip, torch.float32, "f8_gemv: a_scale_recip")
+    _want(w_scale_recip, torch.float32, "f8_gemv: w_scale_recip")
     M, K = a.shape
     N = w.shape[0]
     out = torch.empty((M, N), dtype=BF16, device=a.device)
@@ -190,6 +204,8 @@ def gemm_args(a: Tensor, w: Tensor, bias: Optional[Tensor], a_scale_recip: Tenso
     if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1]:
         raise ValueError(f"f8_gemm: incompatible shapes {tuple(a.shape)} x {tuple(w.shape)}^T")
     _contig(a, "A"), _contig(w, "W")
+    _want(bias, BF16, "f8_gemm: bias"), _want(a_scale_recip, torch.float32, "f8_gemm: a_scale_recip")
+    _want(w_scale_recip, torch.float32, "f8_gemm: w_scale_recip")
     g = cabi.GemmArgs()
     g.a, g.w, g.bias = a.data_ptr(), w.data_ptr(), cabi.ptr(bias)
     g.a_scale_recip, g.w_scale_recip = a_scale_recip.data_ptr(), w_scale_recip.data_ptr()
@@ -256,6 +272,8 @@ def f8_gemm_gate_residual(a, w, bias, sa, sw, resid: Tensor, gate: Tensor, rows_
     """out = resid + gate[b] * linear(a)   (resid [M,N] bf16 view, gate [B,N] view).  With `defer` (a list) the
     launch arguments are appended to it instead of being launched (see run_gemm_group)."""
     g = gemm_args(a, w, bias, sa, sw, cabi.EPI_GATE_RESIDUAL)
+    _want(resid, BF16, "f8_gemm_gate_residual: resid"), _want(gate, BF16, "f8_gemm_gate_residual: gate")
+    _want(out, BF16, "f8_gemm_gate_residual: out")
     if out is None:
         out = torch.empty((g.M, g.N), dtype=BF16, device=a.device)
     g.out, g.ldo = out.data_ptr(), out.stride(0)
@@ -273,6 +291,7 @@ def f8_gemm_gate_residual(a, w, bias, sa, sw, resid: Tensor, gate: Tensor, rows_
 def f8_gemm_gelu_quant(a, w, bias, sa, sw, out_scale: Tensor, out_dtype: torch.dtype, out: Optional[Tensor] = None,
                        out_col_offset: int = 0, defer: Optional[list] = None) -> Tensor:
     g = gemm_args(a, w, bias, sa, sw, cabi.EPI_GELU_QUANT)
+    _want(out_scale, torch.float32, "f8_gemm_gelu_quant: out_scale")
     if out is None:
         out = torch.empty((g.M, g.N), dtype=out_dtype, device=a.device)
     g.out, g.ldo = out.data_ptr(), out.stride(0)
@@ -293,6 +312,10 @@ def f8_gemm_qkv_rope(a, w, bias, sa, sw, q: Tensor, k: Tensor, v: Tensor, q_norm
     straight into the joint [B,H,S,128] buffers."""
     epi = cabi.EPI_LINEAR1 if mlp_out is not None else cabi.EPI_QKV_ROPE
     g = gemm_args(a, w, bias, sa, sw, epi)
+    for t, what in ((q, "q"), (k, "k"), (v, "v"), (cos, "cos"), (sin, "sin")):
+        _want(t, BF16, f"f8_gemm_qkv_rope: {what}")
+    _want(q_norm_w, torch.float32, "f8_gemm_qkv_rope: q_norm_w"), _want(k_norm_w, torch.float32, "f8_gemm_qkv_rope: k_norm_w")
+    _want(mlp_scale, torch.float32, "f8_gemm_qkv_rope: mlp_scale")
     B, H, S, D = q.shape
     g.q, g.k, g.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     g.num_heads, g.seq_total, g.seq_offset = H, S, seq_offset
@@ -317,6 +340,8 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Optional[Tensor] = None, out
     and scales are given; `out` may be a column-slice view of a wider buffer).  With `out1`, rows
     [0, split_row) go to `out` and rows [split_row, S) to `out1` (txt / img streams of a double block)."""
     cabi.require_cuda(q, k, v)
+    _want(q, BF16, "attention: q"), _want(k, BF16, "attention: k"), _want(v, BF16, "attention: v")
+    _want(out_scale0, torch.float32, "attention: out_scale0"), _want(out_scale1, torch.float32, "attention: out_scale1")
     B, H, S, D = q.shape
     if D != 128:
         raise ValueError("head_dim must be 128")

@@ -86,6 +86,11 @@ def broadcast_state(model: nn.Module, src: int = 0, bucket_bytes: int = 256 << 2
         size += n
         total += n
     flush()
+    # the buffers were rewritten IN PLACE: values derived from them (F8Linear quantising scales, RMSNorm fp32 weights,
+    # the batched-modulation table) must be recomputed from the received state, not from what this rank held before
+    from .blocks import invalidate_derived
+
+    invalidate_derived(model)
     return total
 
 
@@ -93,12 +98,14 @@ def frozen_flags_sync(model: nn.Module) -> None:
     """After broadcast_state the scale buffers are identical everywhere; mark every F8Linear frozen on the
     receiving ranks too (calibration ran on rank 0 only -- amax is a whole-batch statistic,
     float8_quantize.py:227, so it must not be recomputed per shard)."""
+    from .blocks import invalidate_derived
     from .f8linear import F8Linear
 
     for m in model.modules():
         if isinstance(m, F8Linear) and m.input_scale is not None:
             m.input_scale_initialized = True
             m.trial_index = m.num_scale_trials
+    invalidate_derived(model)
 
 
 def max_over_ranks(value: float, device) -> float:

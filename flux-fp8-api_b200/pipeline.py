@@ -128,7 +128,7 @@ def build_synthetic_flux(spec: FluxSpec, device, seed: int = 1234, quantize: boo
 # writer; this is the writer, and the artefact `parallel.broadcast_state` ships to the other ranks.
 # ------------------------------------------------------------------------------------------------
 PREQUANTIZED_FORMAT = "flux-fp8-b200/prequantized"
-PREQUANTIZED_VERSION = 1
+PREQUANTIZED_VERSION = 2  # 1 = round-1 torch.save pickle (still readable); 2 = safetensors
 
 
 def _spec_to_dict(spec: FluxSpec) -> dict:
@@ -139,43 +139,73 @@ def _spec_to_dict(spec: FluxSpec) -> dict:
     return d
 
 
+def _spec_from_dict(sd: dict) -> FluxSpec:
+    from .model import FluxParams
+
+    pd = dict(sd["params"])
+    pd["axes_dim"] = list(pd["axes_dim"])
+    return FluxSpec(**{**sd, "params": FluxParams(**pd)})
+
+
 def save_prequantized(model: Flux, path: str, spec: Optional[FluxSpec] = None) -> dict:
     """Write the quantised state (e4m3 `float8_data`, the four 0-dim fp32 scales, bf16 biases / norms / embedders,
-    zeros[1] `weight` placeholders) exactly as `state_dict()` names it -- the reference's own key layout, so the
-    file also loads into the reference's Flux built with prequantized_flow=True.  Returns the header."""
+    zeros[1] `weight` placeholders) exactly as `state_dict()` names it, as ONE .safetensors file -- the container and
+    the key layout the reference loads (`util.load_flow_model` -> `load_sft(ckpt_path)` -> `load_state_dict(...,
+    assign=True)`, util.py:249-255, with `prequantized_flow: true`), so the file is a valid `ckpt_path` for the
+    reference as well.  Format / version / model spec travel in the safetensors metadata.  Returns the header."""
+    import json
+
+    from safetensors.torch import save_file
+
     if not all_frozen(model):
         raise RuntimeError("save_prequantized: input scales are not frozen yet (run calibrate() first); a checkpoint "
                            "without them would silently re-calibrate on its first 12 steps")
-    state = {k: v.detach().to("cpu") for k, v in model.state_dict().items() if v is not None}
+    state = {k: v.detach().to("cpu").contiguous() for k, v in model.state_dict().items() if v is not None}
     n_f8 = sum(1 for k in state if k.endswith(".float8_data"))
     header = {"format": PREQUANTIZED_FORMAT, "version": PREQUANTIZED_VERSION, "f8_layers": n_f8,
               "bytes": int(sum(v.numel() * v.element_size() for v in state.values())),
               "spec": _spec_to_dict(spec) if spec is not None else None}
-    torch.save({"header": header, "state": state}, path)
+    save_file(state, path, metadata={k: json.dumps(v) for k, v in header.items()})
     return header
+
+
+def read_prequantized(path: str):
+    """(header, state dict on the CPU) of a save_prequantized file (safetensors; the round-1 pickle is still read)."""
+    import json
+
+    try:
+        from safetensors import safe_open
+
+        with safe_open(path, framework="pt", device="cpu") as f:
+            meta = f.metadata() or {}
+            state = {k: f.get_tensor(k) for k in f.keys()}
+        header = {k: json.loads(v) for k, v in meta.items()}
+    except Exception as ex:  # noqa: BLE001  (not a safetensors container: the version-1 pickle)
+        try:
+            blob = torch.load(path, map_location="cpu", weights_only=False)
+        except Exception:
+            raise RuntimeError(f"{path}: neither a safetensors file nor a version-1 checkpoint ({ex})") from ex
+        header, state = blob.get("header", {}), blob.get("state", {})
+    if header.get("format") != PREQUANTIZED_FORMAT:
+        raise RuntimeError(f"{path}: not a {PREQUANTIZED_FORMAT} file")
+    if header.get("version", 0) > PREQUANTIZED_VERSION:
+        raise RuntimeError(f"{path}: format version {header.get('version')} is newer than this build ({PREQUANTIZED_VERSION})")
+    return header, state
 
 
 def load_prequantized(path: str, device, spec: Optional[FluxSpec] = None) -> Flux:
     """Build a Flux with F8Linear layers in place (prequantized_flow) and load a `save_prequantized` file: no master
     weights, no quantisation pass, no calibration -- the model is frozen and graph-capturable straight away."""
-    blob = torch.load(path, map_location="cpu", weights_only=False)
-    header = blob.get("header", {})
-    if header.get("format") != PREQUANTIZED_FORMAT:
-        raise RuntimeError(f"{path}: not a {PREQUANTIZED_FORMAT} file")
-    if header.get("version", 0) > PREQUANTIZED_VERSION:
-        raise RuntimeError(f"{path}: format version {header.get('version')} is newer than this build ({PREQUANTIZED_VERSION})")
+    header, state = read_prequantized(path)
     if spec is None:
         sd = header.get("spec")
         if sd is None:
             raise ValueError("load_prequantized: the file carries no model spec; pass spec=")
-        from .model import FluxParams
-        pd = dict(sd["params"])
-        pd["axes_dim"] = list(pd["axes_dim"])
-        spec = FluxSpec(**{**sd, "params": FluxParams(**pd)})
+        spec = _spec_from_dict(sd)
     spec = FluxSpec(**{**spec.__dict__, "prequantized_flow": True})
     with torch.device(device):
         model = Flux(spec, dtype=BF16)
-    state = {k: v.to(device) for k, v in blob["state"].items()}
+    state = {k: v.to(device) for k, v in state.items()}
     model.load_state_dict(state, strict=True, assign=True)
     model.eval()
     if not all_frozen(model):
@@ -223,45 +253,94 @@ def denoise(model: Callable, request: Dict[str, Tensor], timesteps: List[float],
 class GraphedStep:
     """One denoise step (Flux.forward + Euler update) as a CUDA graph over static buffers.
 
-    Every kernel of the step -- ours through the C ABI and the few torch ops of the embedders -- is
-    captured once for a fixed (batch, L, T) and replayed per step; TMA descriptors are encoded at capture
-    time and baked into the kernel parameters.  Per step the host only copies the latent and the two
-    scalars (t, dt) into the static inputs."""
+    Every kernel of the step -- ours through the C ABI and the few torch ops of the embedders -- is captured once for
+    a fixed (batch, L, T) and replayed per step; TMA descriptors are encoded at capture time and baked into the kernel
+    parameters.  Per step the host passes the two scalars (t, dt) as kernel arguments of two fill kernels; the latent stays in the
+    graph's static buffer between steps (the graph's last node copies the updated latent back over its input).
+
+    Ownership: the graph's kernels read per-request tensors that Flux computes once (txt_in(txt), the vector and
+    guidance embeddings, pe, cos/sin).  They live in a cache PRIVATE to this object (Flux.use_request_cache), so no
+    other request, session or LoRA swap on the same model can free them under a later replay.  A LoRA that changes the
+    weights below those embeddings bumps Flux._invariant_epoch; the next call re-captures."""
 
     def __init__(self, model: Flux, request: Dict[str, Tensor], warmup: int = 2):
         if not all_frozen(model):
             raise RuntimeError("GraphedStep needs frozen input scales: run calibrate() first")
         self.model = model
         self.req = request
+        self.warmup = warmup
         dev = request["img"].device
         self.img = request["img"].clone()
         self.t_vec = torch.zeros((self.img.shape[0],), dtype=self.img.dtype, device=dev)
-        self.dt = torch.zeros((), dtype=torch.float32, device=dev)
+        #: [t as the bf16 value the reference's t_vec.fill_ would store, dt = t_prev - t_curr]
+        self.scal = torch.zeros((2,), dtype=torch.float32, device=dev)
         self.out = torch.empty_like(self.img)
+        self.captures = 0
+        self._capture()
+
+    @property
+    def dt(self) -> Tensor:
+        return self.scal[1]
+
+    def _capture(self):
+        from .model import _StepInvariantCache
+
+        dev = self.img.device
+        self.cache = _StepInvariantCache()  # strong references to everything step-invariant the kernels read
+        self.epoch = self.model._invariant_epoch
+        keep = self.img.clone()
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(stream), torch.inference_mode():
-            for _ in range(warmup):
+        with torch.cuda.stream(stream), torch.inference_mode(), self.model.use_request_cache(self.cache):
+            for _ in range(self.warmup):
                 self._step()
+                self.img.copy_(keep)
         torch.cuda.current_stream(dev).wait_stream(stream)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.inference_mode(), torch.cuda.graph(self.graph, stream=stream):
+        with torch.inference_mode(), self.model.use_request_cache(self.cache), \
+                torch.cuda.graph(self.graph, stream=stream):
             self._step()
+        self.img.copy_(keep)
+        self.captures += 1
 
     def _step(self):
         r = self.req
+        self.t_vec.copy_(self.scal[0].expand_as(self.t_vec))  # exact: scal[0] already holds a bf16 value
         pred = self.model(img=self.img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
                           timesteps=self.t_vec, guidance=r.get("guidance"))
         # img + (t_prev - t_curr) * pred: eager torch multiplies in fp32 by the python scalar, rounds the product
         # to bf16, then adds in bf16 -- reproduced with the fp32 0-dim `dt`
-        self.out.copy_(self.img + (self.dt * pred.float()).to(pred.dtype))
+        self.out.copy_(self.img + (self.scal[1] * pred.float()).to(pred.dtype))
+        self.img.copy_(self.out)  # the next step's input, unless the caller supplies another latent
 
-    def __call__(self, img: Tensor, t_vec: Tensor, dt: float) -> Tensor:
-        self.img.copy_(img)
-        self.t_vec.copy_(t_vec)
-        self.dt.fill_(dt)
+    @staticmethod
+    def _bf16_value(t: float) -> float:
+        return float(torch.tensor(t, dtype=torch.bfloat16))
+
+    def advance(self, t_curr: float, dt: float, latent: Optional[Tensor] = None, clone: bool = True) -> Tensor:
+        """One step from the latent held in the static buffer (or `latent`, copied in first).  With clone=False the
+        returned tensor IS the static output buffer: valid until the next call."""
+        if self.epoch != self.model._invariant_epoch:
+            self._capture()
+        if latent is not None and latent is not self.out:
+            self.img.copy_(latent)
+        # the two scalars travel as kernel arguments of two fill kernels (a pinned staging buffer rewritten by the host
+        # every step would race with the previous step's still-queued copy)
+        self.scal[0:1].fill_(self._bf16_value(t_curr))
+        self.scal[1:2].fill_(dt)
         self.graph.replay()
-        return self.out.clone()
+        return self.out.clone() if clone else self.out
+
+    def __call__(self, img: Tensor, t_vec: Tensor, dt: float, clone: bool = True) -> Tensor:
+        """denoise(step_fn=...) signature: t_vec is the reference's filled bf16 timestep vector."""
+        if self.epoch != self.model._invariant_epoch:
+            self._capture()
+        if img is not self.out:
+            self.img.copy_(img)
+        self.scal[0:1].copy_(t_vec[0:1])
+        self.scal[1:2].fill_(dt)
+        self.graph.replay()
+        return self.out.clone() if clone else self.out
 
 
 class DenoiseSession:
@@ -286,8 +365,10 @@ class DenoiseSession:
 
     @property
     def h2d_bytes_per_step(self) -> int:
-        return (self._host_in.numel() * self._host_in.element_size() + self._t_host.numel() * self._t_host.element_size()
-                + (4 if self.step is not None else 0))
+        latent = self._host_in.numel() * self._host_in.element_size()
+        if self.step is not None:
+            return latent  # (t, dt) travel as kernel arguments, not as a copy
+        return latent + self._t_host.numel() * self._t_host.element_size()
 
     @property
     def d2h_bytes_per_step(self) -> int:
@@ -295,13 +376,19 @@ class DenoiseSession:
 
     @torch.inference_mode()
     def run(self, timesteps: List[float]) -> Tensor:
-        return denoise(self.model, self.request, timesteps, step_fn=self.step)
+        """The whole Euler loop (flux_pipeline.py:627-651) with the latent resident in HBM."""
+        if self.step is None:
+            return denoise(self.model, self.request, timesteps)
+        g, img = self.step, self.request["img"]
+        for t_curr, t_prev in zip(timesteps[:-1], timesteps[1:]):
+            img = g.advance(t_curr, t_prev - t_curr, latent=img, clone=False)
+        return img.clone()
 
     @torch.inference_mode()
     def step_device(self, img: Tensor, t_curr: float, t_prev: float) -> Tensor:
-        self._t_vec.fill_(t_curr)
         if self.step is not None:
-            return self.step(img, self._t_vec, t_prev - t_curr)
+            return self.step.advance(t_curr, t_prev - t_curr, latent=img)
+        self._t_vec.fill_(t_curr)
         r = self.request
         pred = self.model(img=img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
                           timesteps=self._t_vec, guidance=r.get("guidance"))
@@ -312,17 +399,13 @@ class DenoiseSession:
         """One denoise step with HOST buffers: pinned H2D copy of the latent and timestep, the step on the
         device, D2H copy of the updated latent (synchronises before returning)."""
         self._host_in.copy_(img_host)
-        self._t_host.fill_(t_curr)
         if self.step is not None:
-            # straight into / out of the graph's static buffers: 3 H2D copies, one graph launch, one D2H copy
+            # straight into / out of the graph's static buffers: 2 H2D copies, one graph launch, one D2H copy
             g = self.step
-            self._dt_host.fill_(t_prev - t_curr)
             g.img.copy_(self._host_in, non_blocking=True)
-            g.t_vec.copy_(self._t_host, non_blocking=True)
-            g.dt.copy_(self._dt_host, non_blocking=True)
-            g.graph.replay()
-            out = g.out
+            out = g.advance(t_curr, t_prev - t_curr, clone=False)
         else:
+            self._t_host.fill_(t_curr)
             self._dev_in.copy_(self._host_in, non_blocking=True)
             self._t_vec.copy_(self._t_host, non_blocking=True)
             r = self.request

@@ -151,6 +151,15 @@ int fluxb200_modulation_batched(const void* vec_bf16, const fluxb200_gemv_layer*
                                 int total_blocks, void* aq_workspace, void* out_bf16, int64_t ld_out, int B,
                                 int K, int a_fmt, int w_fmt, fluxb200_stream_t stream);
 
+/* The same for Modulation.lin layers LEFT IN bf16 (quantize_modulation = false: float8_quantize.py:346 skips the
+ * swap, so modules/flux_model.py:252 runs nn.Linear): one launch for every layer of the step,
+ *   out[b, out_offset_l + n] = bf16( sum_k bf16(silu(vec[b,k])) * W_l[n,k] + bias_l[n] )      (fp32 accumulate)
+ * `layers[l].w` points to bf16 [N,K] row-major weights; in_qscale / a_scale_recip / w_scale_recip are ignored.
+ * K % 32 == 0, K <= 4096, B <= 16; no workspace (silu is applied while vec is staged into shared memory). */
+int fluxb200_modulation_batched_bf16(const void* vec_bf16, const fluxb200_gemv_layer* layers, int num_layers,
+                                     int total_blocks, void* out_bf16, int64_t ld_out, int B, int K,
+                                     fluxb200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Modulation prologue: y = quantize( bf16(silu(x)), scale )   (modules/flux_model.py:249,252 +
  * float8_quantize.py:274-276).  y_bf16 (optional) receives bf16(silu(x)) for unquantised lins.

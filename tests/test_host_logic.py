@@ -184,5 +184,5 @@ def test_lora_operands_reproduce_the_reference_delta(golden_dir):
     assert sorted(lora._keys_without_ab(w)) == ["a.b", "c"]
     with pytest.raises(ValueError):
         lora.lora_operands((torch.ones(5, 4), torch.ones(3, 2), None), None, "cpu")   # 5 rows do not chain with rank 2
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError):   # a path is loaded as a BFL-layout .safetensors file
         lora.apply_lora_to_model(torch.nn.Linear(2, 2), "some/file.safetensors")
