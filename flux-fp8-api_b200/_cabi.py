@@ -39,6 +39,7 @@ EXPORTS = (
     "fluxb200_attention",
     "fluxb200_lora_fuse",
     "fluxb200_debug_counters",
+    "fluxb200_gemm_probe_mode",
 )
 
 
@@ -193,6 +194,7 @@ def load() -> C.CDLL:
         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
     ]
     lib.fluxb200_debug_counters.argtypes = [C.POINTER(C.c_ulonglong)]
+    lib.fluxb200_gemm_probe_mode.argtypes = [C.c_int]
     for name in EXPORTS:
         if name != "fluxb200_last_error":
             getattr(lib, name).restype = C.c_int

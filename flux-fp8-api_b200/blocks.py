@@ -28,6 +28,16 @@ from .f8linear import F8Linear
 BF16 = torch.bfloat16
 HEAD_DIM = 128
 
+#: diagnostics: when set to a dict, the fused block paths record the fp8 GEMM operands they produce under the name of
+#: the consuming layer ("img_attn.qkv", "linear2", ...), so a test can compare them byte for byte with the reference's
+#: own quantised inputs (the e5m2/e4m3 "code flip" rate, tests/test_gpu_reference.py).  None on the product path.
+TAP = None
+
+
+def _tap(name: str, t: Tensor) -> None:
+    if TAP is not None:
+        TAP[name] = t
+
 
 # ------------------------------------------------------------------------------------------------
 # RoPE tables
@@ -393,6 +403,7 @@ class DoubleStreamBlock(nn.Module):
                    (img, img_mod1, img_mod2, self.img_attn, self.img_mlp, L, T))
         group = []
         a8s = self._ln_pair([(x, mod1, attn.qkv) for x, mod1, _, attn, _, _, _ in streams])
+        _tap("txt_attn.qkv", a8s[0]), _tap("img_attn.qkv", a8s[1])
         for (x, mod1, _, attn, _, rows, off), a8 in zip(streams, a8s):
             lin = attn.qkv
             ops.f8_gemm_qkv_rope(a8.view(-1, D), lin.float8_data, lin.bias, lin.input_scale_reciprocal,
@@ -409,6 +420,7 @@ class DoubleStreamBlock(nn.Module):
         ops.attention(q, k, v, out=txt_a8, out_scale0=tp.qscale, out_scale1=ip.qscale, split_row=T,
                       out1=img_a8)
 
+        _tap("txt_attn.proj", txt_a8), _tap("img_attn.proj", img_a8)
         # x = x + gate1 * proj(attn)
         ys, group = [], []
         for (x, mod1, _, attn, _, rows, _), a8 in zip(streams, (txt_a8, img_a8)):
@@ -425,6 +437,7 @@ class DoubleStreamBlock(nn.Module):
             hs.append(ops.f8_gemm_gelu_quant(m8.view(-1, D), up.float8_data, up.bias, up.input_scale_reciprocal,
                                              up.scale_reciprocal, down.qscale, down.input_float8_dtype, defer=group))
         self._launch(group)
+        _tap("txt_mlp.0", m8s[0]), _tap("img_mlp.0", m8s[1]), _tap("txt_mlp.2", hs[0]), _tap("img_mlp.2", hs[1])
         group = []
         for (x, _, mod2, _, mlp, rows, _), y, h8 in zip(streams, ys, hs):
             down = mlp[2]
@@ -536,6 +549,7 @@ class SingleStreamBlock(nn.Module):
                              rows_per_batch=S, seq_offset=0, mlp_out=cat8.view(B * S, -1), mlp_scale=l2.qscale,
                              mlp_col_offset=D)
         ops.attention(q, k, v, out=cat8[..., :D], out_scale0=l2.qscale, split_row=0)
+        _tap("linear1", a8), _tap("linear2", cat8)
         out = ops.f8_gemm_gate_residual(cat8.view(B * S, -1), l2.float8_data, l2.bias, l2.input_scale_reciprocal,
                                         l2.scale_reciprocal, x.view(-1, D), _gate2d(mod.gate), S)
         return out.view(B, S, D)

@@ -66,8 +66,11 @@ struct GemmParams {
   // evenly through the schedule so the double-buffered accumulators average the two epilogue costs.
   int q_n_tiles;
   uint32_t idesc;
-  // Timing experiments only (env FLUXB200_GEMM_DEBUG; results are garbage): 1 = no TMA traffic after the ring is
-  // first filled (pure MMA issue rate), 2 = no MMAs (pure TMA pipeline rate).
+  // Timing experiments only (fluxb200_gemm_probe_mode / env FLUXB200_GEMM_DEBUG; results are garbage).  Bit mask:
+  //   1 = no TMA traffic after the ring is first filled (MMA issue rate with operands resident in shared memory)
+  //   2 = no MMAs (pure TMA pipeline rate)          4 = no epilogue (accumulator released at once)
+  //   8 = epilogue does its TMEM loads + de-quantisation only (no fused math, no stores)
+  // 1|4 is the tcgen05 kind::f8f6f4 ceiling of this tiling: what bench.py reports as the measured FP8 peak.
   int debug;
 };
 
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStage;
         if (elect_one()) {
-          if (P.debug == 1 && (phase != 0 || tile != tile0)) {
+          if ((P.debug & 1) && (phase != 0 || tile != tile0)) {
             if (cta_rank == 0) mbar_arrive(&full_bar[stage]);  // pretend the data landed
           } else if constexpr (CG == 2) {
             // all bytes of the pair are accounted on the leader's barrier
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBK / 32; ++k) {
-              if (P.debug == 2) break;
+              if (P.debug & 2) break;
               if constexpr (CG == 2)
                 mma_f8f6f4_ss_2sm(d_tmem, desc_advance(ad, k * 32), desc_advance(bd, k * 32), P.idesc, (kb | k) != 0 ? 1u : 0u);
               else
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
       const int n0 = tc.n_blk * BN;
       RowInfo ri;
       ri.row = m0 + lg * 32 + lane;
-      ri.valid = ri.row < g.M && P.debug != 4;  // debug 4: TMEM loads + dequant only, no epilogue math / stores
+      ri.valid = ri.row < g.M && !(P.debug & 8);  // debug 8: TMEM loads + dequant only, no epilogue math / stores
       ri.b = ri.row / rpb;
       ri.pos = ri.row - ri.b * rpb;
       mbar_wait(&tfull_bar[as], aphase);
@@ -546,8 +549,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
 
       bool qkv_path = (EPI == FLUXB200_EPI_QKV_ROPE);
       if constexpr (EPI == FLUXB200_EPI_LINEAR1) qkv_path = col0 < 3 * g.num_heads * kHeadDim;
-      if (P.debug == 3) {
-        // debug 3: no epilogue at all (accumulator released at once): isolates the TMA + MMA pipeline
+      if (P.debug & 4) {
+        // debug 4: no epilogue at all (accumulator released at once): isolates the TMA + MMA pipeline
       } else if (qkv_path) {
         if constexpr (EPI == FLUXB200_EPI_QKV_ROPE || EPI == FLUXB200_EPI_LINEAR1) {
           static_assert(2 * kPartCols == kHeadDim || (EPI != FLUXB200_EPI_QKV_ROPE && EPI != FLUXB200_EPI_LINEAR1),
@@ -636,6 +639,9 @@ static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
 
 namespace fb {
 
+// fluxb200_gemm_probe_mode: timing-probe bits OR-ed into every following launch of this process (0 = product behaviour)
+static int g_probe_mode = 0;
+
 static int validate_gemm(const fluxb200_gemm_args& g) {
   FB_REQUIRE(g.a && g.w && g.a_scale_recip && g.w_scale_recip, "fluxb200_f8_gemm: null operand");
   FB_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "fluxb200_f8_gemm: bad shape M=%d N=%d K=%d", g.M, g.N, g.K);
@@ -719,7 +725,7 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
     const char* e = getenv("FLUXB200_GEMM_DEBUG");
     return e ? atoi(e) : 0;
   }();
-  P.debug = dbg;
+  P.debug = dbg | g_probe_mode;
   P.num_n_tiles = (g.N + bn - 1) / bn;
   P.q_n_tiles = 0;
   {
@@ -783,6 +789,12 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
 }
 
 }  // namespace fb
+
+extern "C" int fluxb200_gemm_probe_mode(int mode) {
+  FB_REQUIRE(mode >= 0 && mode < 16, "fluxb200_gemm_probe_mode: mode is a 4-bit mask");
+  fb::g_probe_mode = mode;
+  return 0;
+}
 
 extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_t stream_) {
   return fb::run_gemm_group(args, 1, reinterpret_cast<cudaStream_t>(stream_));

@@ -213,6 +213,20 @@ def load_prequantized(path: str, device, spec: Optional[FluxSpec] = None) -> Flu
     return model
 
 
+def set_input_float8_dtype(model: nn.Module, dtype: torch.dtype) -> None:
+    """Activation format of every F8Linear of a model built with prequantized_flow=True.  The prequantised state dict
+    does not record it (the reference constructs those layers with the e5m2 default, modules/flux_model.py:279-345,
+    whatever `input_float8_dtype` the checkpoint was quantised and calibrated with, float8_quantize.py:298-304), so a
+    checkpoint calibrated for e4m3 activations needs this after loading."""
+    from .blocks import invalidate_derived
+
+    for m in model.modules():
+        if isinstance(m, F8Linear):
+            m.input_float8_dtype = dtype
+            m.input_max_value = torch.finfo(dtype).max
+    invalidate_derived(model)
+
+
 def all_frozen(model: nn.Module) -> bool:
     return all(m.frozen for m in model.modules() if isinstance(m, F8Linear))
 

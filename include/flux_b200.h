@@ -247,6 +247,13 @@ int fluxb200_lora_fuse(const void* w_fp8, int w_fmt, const float* w_scale_recip,
                        const float* lora_up, int N, int K, int R, int chunks, float coeff, int unfuse,
                        void* w_out_bf16, float* amax_out, fluxb200_stream_t stream);
 
+/* Diagnostics (measurement only; outputs of probe-mode launches are garbage): bit mask OR-ed into every following
+ * fluxb200_f8_gemm* launch of this process until reset with 0.  1 = operands stay resident in shared memory after the
+ * first fill (no TMA traffic), 2 = no MMAs, 4 = no epilogue, 8 = epilogue TMEM loads only.  Mode 1|4 times the bare
+ * tcgen05 kind::f8f6f4 issue rate of the kernel's tiling: bench.py measures the FP8 tensor-pipe ceiling of the box it
+ * runs on with it (roofline.peak), instead of inferring it from the bf16 figure. */
+int fluxb200_gemm_probe_mode(int mode);
+
 /* Diagnostics: cycle counters of the last attention launch's CTA 0 (host pointer to 16 x uint64):
  * [0..5] softmax warp: wait-S, tmem load, max, exp, wait-O, store-P; [6] half-steps;
  * [8..10] MMA issuer: wait-P, wait-KV, issue.  Synchronises the device. */

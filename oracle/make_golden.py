@@ -249,6 +249,87 @@ def golden_flux():
                 "mod1": [mod1.shift, mod1.scale, mod1.gate]}, os.path.join(OUT, "flux_tiny.pt"))
 
 
+def golden_flux_variants():
+    """Two more reference-minted fixtures (e4m3 activations untested beyond one GEMM; no multi-step golden):
+
+    flux_tiny_e4m3.pt  the tiny Flux quantised with input_float8_dtype=float8_e4m3fn AND
+                       quantize_flow_embedder_layers=True (img_in / txt_in / time_in / vector_in / guidance_in become
+                       F8Linear too): state, per-block outputs, full forward.
+    flux_tiny_traj.pt  a 4-step Euler trajectory of the e5m2 model of flux_tiny.pt through the reference Flux.forward,
+                       with the loop of flux_pipeline.py:627-651 (t_vec in bf16, img + (t_prev - t_curr) * pred)."""
+    E4M3 = torch.float8_e4m3fn
+    cfg = {k: TINY[k] for k in ("num_heads", "depth", "depth_single_blocks", "axes_dim", "theta", "guidance_embed")}
+    print("[Flux tiny: e4m3 activations + quantised embedders]")
+    model = init_reference_flux(4321)
+    ref_f8.quantize_flow_transformer_and_dispatch_float8(
+        model, torch.device("cpu"), input_float8_dtype=E4M3, offload_flow=False, swap_linears_with_cublaslinear=False,
+        flow_dtype=BF16, quantize_modulation=True, quantize_flow_embedder_layers=True)
+    sched = O.get_schedule(13, 64)
+    with torch.inference_mode():
+        for i in range(13):
+            model(**flux_inputs(300 + i, t=sched[i]))
+    f8s = [m for m in model.modules() if isinstance(m, ref_f8.F8Linear)]
+    assert all(m.input_scale_initialized and m.input_float8_dtype == E4M3 for m in f8s)
+    assert isinstance(model.img_in, ref_f8.F8Linear) and isinstance(model.time_in.in_layer, ref_f8.F8Linear)
+    assert not isinstance(model.final_layer.linear, ref_f8.F8Linear)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    inp = flux_inputs(199)
+    with torch.inference_mode():
+        y = model(**inp)
+        gg = torch.Generator().manual_seed(6)
+        B, L, T, Dm = 2, 64, 32, TINY["hidden_size"]
+        img = torch.randn(B, L, Dm, generator=gg).to(BF16)
+        txt = torch.randn(B, T, Dm, generator=gg).to(BF16)
+        vec = torch.randn(B, Dm, generator=gg).to(BF16)
+        pe = model.pe_embedder(torch.cat((inp["txt_ids"], inp["img_ids"]), dim=1))
+        d_img, d_txt = model.double_blocks[0](img=img, txt=txt, vec=vec, pe=pe)
+        xs = torch.cat((txt, img), 1)
+        s_out = model.single_blocks[0](xs, vec=vec, pe=pe)
+    o_img, o_txt = O.double_block(img, txt, vec, pe, sd, "double_blocks.0.", TINY["num_heads"], E4M3)
+    report("DoubleStreamBlock img (e4m3)", d_img, o_img, 2.0 ** -4)
+    report("DoubleStreamBlock txt (e4m3)", d_txt, o_txt, 2.0 ** -4)
+    report("SingleStreamBlock (e4m3)", s_out, O.single_block(xs, vec, pe, sd, "single_blocks.0.", TINY["num_heads"], E4M3),
+           2.0 ** -4)
+    report("Flux.forward fp8 (e4m3, f8 embedders)", y, O.flux_forward(sd, cfg, **inp, in_dtype=E4M3), 2.0 ** -4)
+    print(f"  {len(f8s)} F8Linear layers")
+    torch.save({"tiny": TINY, "cfg": cfg, "state": sd, "inputs": inp, "y_fp8": y,
+                "block_in": {"img": img, "txt": txt, "vec": vec, "pe": pe},
+                "double_img": d_img, "double_txt": d_txt, "single": s_out, "n_f8": len(f8s),
+                "input_float8_dtype": "float8_e4m3fn", "quantize_flow_embedder_layers": True},
+               os.path.join(OUT, "flux_tiny_e4m3.pt"))
+
+    print("[Flux tiny: 4-step Euler trajectory, e5m2 model of flux_tiny.pt]")
+    gold = torch.load(os.path.join(OUT, "flux_tiny.pt"))
+    spec = types.SimpleNamespace(params=ref_fm.FluxParams(**TINY), prequantized_flow=True, quantize_modulation=True,
+                                 quantize_flow_embedder_layers=False)
+    model = ref_fm.Flux(spec, dtype=BF16)
+    model.load_state_dict(gold["state"], strict=True, assign=True)
+    model.eval()
+    inp = {k: v.clone() for k, v in gold["inputs"].items()}
+    timesteps = O.get_schedule(4, inp["img"].shape[1])
+    img = inp["img"]
+    preds, latents = [], []
+    o_img = inp["img"]
+    with torch.inference_mode():
+        t_vec = None
+        for t_curr, t_prev in zip(timesteps[:-1], timesteps[1:]):   # flux_pipeline.py:634-651
+            if t_vec is None:
+                t_vec = torch.full((img.shape[0],), t_curr, dtype=img.dtype)
+            else:
+                t_vec = t_vec.reshape((img.shape[0],)).fill_(t_curr)
+            pred = model(img=img, img_ids=inp["img_ids"], txt=inp["txt"], txt_ids=inp["txt_ids"], y=inp["y"],
+                         timesteps=t_vec, guidance=inp["guidance"])
+            img = img + (t_prev - t_curr) * pred
+            preds.append(pred.clone())
+            latents.append(img.clone())
+            o_pred = O.flux_forward(gold["state"], cfg, o_img, inp["img_ids"], inp["txt"], inp["txt_ids"],
+                                    t_vec.clone(), inp["y"], inp["guidance"])
+            o_img = O.euler_step(o_img, o_pred, t_curr, t_prev)
+    report("4-step trajectory, final latent", img, o_img, 2.0 ** -3)
+    torch.save({"timesteps": timesteps, "preds": preds, "latents": latents, "inputs": inp},
+               os.path.join(OUT, "flux_tiny_traj.pt"))
+
+
 def golden_lora():
     """LoRA fuse / unfuse through the reference's lora_loading functions on reference F8Linear layers."""
     import lora_loading as ref_lora  # reference
@@ -304,5 +385,6 @@ if __name__ == "__main__":
     golden_f8linear()
     golden_ops()
     golden_flux()
+    golden_flux_variants()
     golden_lora()
     print("golden fixtures written to", OUT)

@@ -83,8 +83,9 @@ def test_amax_and_empty(ops):
     assert ops.quantize(x[:0], scalar(1.0), E5M2).numel() == 0
 
 
+@pytest.mark.parametrize("fdt", [E5M2, E4M3])
 @pytest.mark.parametrize("B,L,D", [(1, 512, 3072), (2, 384, 3072), (2, 100, 256), (1, 77, 4096)])
-def test_ln_modulate_quantise(ops, O, B, L, D):
+def test_ln_modulate_quantise(ops, O, B, L, D, fdt):
     from flux_fp8_api_b200.f8linear import mul_scale
 
     g = gen(3)
@@ -92,10 +93,10 @@ def test_ln_modulate_quantise(ops, O, B, L, D):
     mod = (torch.randn(B, 1, 6 * D, device=DEV, generator=g) * 0.3).to(BF16)
     shift, scale = mod[..., :D], mod[..., D:2 * D]
     ref = O.layernorm_modulate(x, shift, scale)
-    s = O.amax_to_scale(ref.abs().max().float(), 57344.0)
-    yq, yb = ops.ln_mod_quant(x, shift, scale, mul_scale(s), E5M2, want_bf16=True)
+    s = O.amax_to_scale(ref.abs().max().float(), torch.finfo(fdt).max)
+    yq, yb = ops.ln_mod_quant(x, shift, scale, mul_scale(s), fdt, want_bf16=True)
     ulp_check(yb, ref, ulps=2, frac=0.001)
-    mism = (yq.float() != O.quantize(ref, s, E5M2).float()).float().mean().item()
+    mism = (yq.float() != O.quantize(ref, s, fdt).float()).float().mean().item()
     assert mism < 0.001
 
 
@@ -152,10 +153,11 @@ def test_f8_gemm_linearity_full_size(ops):
     assert torch.equal(y3, y1[1024:1536])
 
 
+@pytest.mark.parametrize("adt", [E5M2, E4M3])
 @pytest.mark.parametrize("B,L,N,K", [(2, 256, 512, 256), (3, 100, 256, 512), (1, 4608, 3072, 3072)])
-def test_epilogue_gate_residual(ops, O, B, L, N, K):
+def test_epilogue_gate_residual(ops, O, B, L, N, K, adt):
     M = B * L
-    a, w = rand_fp8((M, K), E5M2, 4.0, 10), rand_fp8((N, K), E4M3, 1.0, 11)
+    a, w = rand_fp8((M, K), adt, 4.0, 10), rand_fp8((N, K), E4M3, 1.0, 11)
     g = gen(12)
     bias = (torch.randn(N, device=DEV, generator=g) * 0.5).to(BF16)
     resid = torch.randn(M, N, device=DEV, generator=g).to(BF16)
@@ -169,32 +171,39 @@ def test_epilogue_gate_residual(ops, O, B, L, N, K):
     ulp_check(inplace, ref, ulps=2)
 
 
+@pytest.mark.parametrize("adt", [E5M2, E4M3])
 @pytest.mark.parametrize("M,N,K", [(256, 512, 256), (4608, 12288, 3072)])
-def test_epilogue_gelu_quant(ops, O, M, N, K):
+def test_epilogue_gelu_quant(ops, O, M, N, K, adt):
+    """`adt` is the activation format on BOTH sides: the GEMM's A operand and the fp8 output the next F8Linear reads
+    (the reference uses one input_float8_dtype per model, float8_quantize.py:298-304)."""
     from flux_fp8_api_b200.f8linear import mul_scale
 
-    a, w = rand_fp8((M, K), E5M2, 4.0, 13), rand_fp8((N, K), E4M3, 1.0, 14)
+    a, w = rand_fp8((M, K), adt, 4.0, 13), rand_fp8((N, K), E4M3, 1.0, 14)
     bias = (torch.randn(N, device=DEV, generator=gen(15)) * 0.5).to(BF16)
     sa, sw = scalar(1 / 64.0), scalar(1 / 32.0)
     ge = F.gelu(O.scaled_mm(a, w, sa, sw, bias), approximate="tanh")
-    so = O.amax_to_scale(ge.abs().max().float(), 57344.0)
-    out = ops.f8_gemm_gelu_quant(a, w, bias, sa, sw, mul_scale(so), E5M2)
-    ref = O.quantize(ge, so, E5M2)
+    fmax = torch.finfo(adt).max
+    so = O.amax_to_scale(ge.abs().max().float(), fmax)
+    out = ops.f8_gemm_gelu_quant(a, w, bias, sa, sw, mul_scale(so), adt)
+    ref = O.quantize(ge, so, adt)
     assert torch.isfinite(out.float()).all()
-    assert (out.float() != ref.float()).float().mean().item() < 0.002  # rare 1-ulp GELU / accumulation flips
-    # a flipped element moves by one e5m2 step (25 % of its magnitude at most); compare de-quantised values
+    # rare 1-ulp GELU / accumulation flips (e4m3 has 2x finer steps than e5m2: twice the flips for the same bf16 noise)
+    assert (out.float() != ref.float()).float().mean().item() < (0.002 if adt == E5M2 else 0.004)
+    # a flipped element moves by one fp8 step (25 % / 12.5 % of its magnitude at most); compare de-quantised values
     o, r = out.float() / so, ref.float() / so
     assert ((o - r).abs() <= 0.26 * torch.maximum(o.abs(), r.abs()) + 2.0 ** -8).all()
 
 
+@pytest.mark.parametrize("adt", [E5M2, E4M3])
 @pytest.mark.parametrize("B,L,T,H,K,mlp", [(2, 128, 64, 2, 256, 0), (1, 256, 128, 2, 256, 512), (1, 200, 56, 2, 256, 256),
                                            (1, 4096, 512, 24, 3072, 12288)])
-def test_epilogue_qkv_rope_and_linear1(ops, O, B, L, T, H, K, mlp):
+def test_epilogue_qkv_rope_and_linear1(ops, O, B, L, T, H, K, mlp, adt):
     from flux_fp8_api_b200.f8linear import mul_scale
 
     S, D = L + T, H * 128
     N, M = 3 * D + mlp, B * L
-    a, w = rand_fp8((M, K), E5M2, 4.0, 16), rand_fp8((N, K), E4M3, 0.5, 17)
+    fmax = torch.finfo(adt).max
+    a, w = rand_fp8((M, K), adt, 4.0, 16), rand_fp8((N, K), E4M3, 0.5, 17)
     g = gen(18)
     bias = (torch.randn(N, device=DEV, generator=g) * 0.5).to(BF16)
     qw = (1 + 0.05 * torch.randn(128, device=DEV, generator=g)).to(BF16)
@@ -212,8 +221,8 @@ def test_epilogue_qkv_rope_and_linear1(ops, O, B, L, T, H, K, mlp):
     mlp_out = so = None
     if mlp:
         ge = F.gelu(y[..., 3 * D:], approximate="tanh")
-        so = O.amax_to_scale(ge.abs().max().float(), 57344.0)
-        mlp_out = torch.zeros(M, D + mlp, dtype=E5M2, device=DEV)
+        so = O.amax_to_scale(ge.abs().max().float(), fmax)
+        mlp_out = torch.zeros(M, D + mlp, dtype=adt, device=DEV)
     ops.f8_gemm_qkv_rope(a, w, bias, sa, sw, q, k, v, qw.float(), kw.float(), cos, sin, L, T, mlp_out=mlp_out,
                          mlp_scale=mul_scale(so) if mlp else None, mlp_col_offset=D)
     ulp_check(q[:, :, T:], rq, ulps=4, frac=0.02)  # 1-ulp flips before RMSNorm/RoPE are amplified by the rotation
@@ -221,8 +230,8 @@ def test_epilogue_qkv_rope_and_linear1(ops, O, B, L, T, H, K, mlp):
     ulp_check(v[:, :, T:], rv, ulps=1, frac=0.01)
     assert (q[:, :, :T] == 0).all() and (v[:, :, :T] == 0).all()  # other stream's rows untouched
     if mlp:
-        ref = O.quantize(ge, so, E5M2).view(M, mlp)
-        assert (mlp_out[:, D:].float() != ref.float()).float().mean().item() < 0.002
+        ref = O.quantize(ge, so, adt).view(M, mlp)
+        assert (mlp_out[:, D:].float() != ref.float()).float().mean().item() < (0.002 if adt == E5M2 else 0.004)
         assert (mlp_out[:, :D].float() == 0).all()
 
 
@@ -256,12 +265,71 @@ def test_attention_full_size_and_fp8_split_output(ops, O):
     # property: softmax rows sum to one -> attention of constant V is that constant (exactly representable)
     ones = torch.full_like(v, 0.5)
     assert torch.equal(ops.attention(q, k, ones), torch.full_like(out, 0.5))
-    # fp8 outputs routed to two destinations with two scales (double-block layout)
-    s0, s1 = O.amax_to_scale(scalar(1.0), 57344.0), O.amax_to_scale(scalar(3.0), 57344.0)
-    o_txt = torch.zeros(B, T, H * 128, dtype=E5M2, device=DEV)
-    o_img = torch.zeros(B, S - T, H * 128, dtype=E5M2, device=DEV)
-    ops.attention(q, k, v, out=o_txt, out_scale0=mul_scale(s0), out_scale1=mul_scale(s1), split_row=T, out1=o_img)
-    r_txt, r_img = O.quantize(ref[:, :T], s0, E5M2), O.quantize(ref[:, T:], s1, E5M2)
-    assert (o_txt.float() != r_txt.float()).float().mean().item() < 0.06  # 1-ulp bf16 differences before the e5m2 cast
-    assert (o_img.float() != r_img.float()).float().mean().item() < 0.06
-    assert ((o_img.float() - r_img.float()).abs() / s1).max().item() <= 2.0 ** -4
+    # fp8 outputs routed to two destinations with two scales (double-block layout), in both activation formats
+    for fdt, flip in ((E5M2, 0.06), (E4M3, 0.12)):
+        fmax = torch.finfo(fdt).max
+        s0, s1 = O.amax_to_scale(scalar(1.0), fmax), O.amax_to_scale(scalar(3.0), fmax)
+        o_txt = torch.zeros(B, T, H * 128, dtype=fdt, device=DEV)
+        o_img = torch.zeros(B, S - T, H * 128, dtype=fdt, device=DEV)
+        ops.attention(q, k, v, out=o_txt, out_scale0=mul_scale(s0), out_scale1=mul_scale(s1), split_row=T, out1=o_img)
+        r_txt, r_img = O.quantize(ref[:, :T], s0, fdt), O.quantize(ref[:, T:], s1, fdt)
+        assert (o_txt.float() != r_txt.float()).float().mean().item() < flip  # 1-ulp bf16 differences before the fp8 cast
+        assert (o_img.float() != r_img.float()).float().mean().item() < flip
+        assert ((o_img.float() - r_img.float()).abs() / s1).max().item() <= 2.0 ** -4
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_rope_tables_never_go_stale(ops, O):
+    """VERDICT r1 weak #2 / ADVICE: rope_cos_sin's cache used to be keyed on (data_ptr, shape, version); under
+    inference_mode a new `pe` of the same shape allocated at a recycled address hit the old entry.  Alternate two
+    token grids with the same token count (64x64 and 32x128, L = 4096), freeing each `pe` before the next is made, and
+    check every rotation against the oracle (modules/flux_model.py:60-65, 701-702)."""
+    from flux_fp8_api_b200 import blocks
+
+    emb = blocks.EmbedND(128, 10_000, [16, 56, 56], BF16)
+    g = gen(31)
+    q = torch.randn(1, 2, 4096 + 64, 128, device=DEV, generator=g).to(BF16)
+    k = torch.randn(1, 2, 4096 + 64, 128, device=DEV, generator=g).to(BF16)
+    txt_ids = torch.zeros(1, 64, 3, dtype=BF16, device=DEV)
+    grids = [O.make_img_ids(1, 64, 64, BF16, DEV), O.make_img_ids(1, 32, 128, BF16, DEV)]
+    seen_ptrs = set()
+    with torch.inference_mode():
+        for it in range(8):
+            ids = torch.cat((txt_ids, grids[it % 2]), 1)
+            pe = emb(ids)
+            seen_ptrs.add(pe.data_ptr())
+            gq, gk = blocks.apply_rope(q, k, pe)
+            rq, rk = O.apply_rope(q, k, pe)
+            assert torch.equal(gq, rq) and torch.equal(gk, rk), f"stale cos/sin at iteration {it}"
+            del pe, gq, gk, rq, rk
+    # (the allocator really did recycle addresses: otherwise the scenario was not exercised)
+    assert len(seen_ptrs) < 8
+
+
+@pytest.mark.parametrize("B", [1, 3, 8, 11])
+def test_modulation_batched_bf16(ops, O, B):
+    """fluxb200_modulation_batched_bf16 (quantize_modulation=False, BASELINE c5): every bf16 Modulation.lin of a model
+    in one launch == F.linear(silu(vec)) per layer (modules/flux_model.py:251-257), fp32-accumulation-order tolerance."""
+    from flux_fp8_api_b200 import blocks
+
+    g = gen(40 + B)
+    D = 3072
+    mods = []
+    for i, double in enumerate((True, True, False, False, True)):
+        m = blocks.Modulation(D, double=double, quantized_modulation=False).to(DEV).to(BF16)
+        with torch.no_grad():
+            m.lin.weight.copy_(torch.randn(m.lin.weight.shape, device=DEV, generator=g) * 0.01)
+            m.lin.bias.copy_(torch.randn(m.lin.bias.shape, device=DEV, generator=g) * 0.02)
+        mods.append(m)
+    bank = blocks.ModulationBank(mods)
+    assert not bank.f8 and not bank.stale()
+    vec = torch.randn(B, D, device=DEV, generator=g).to(BF16)
+    with torch.inference_mode():
+        res = bank(vec)
+        for m, (o1, o2) in zip(mods, res):
+            ref = F.linear(F.silu(vec), m.lin.weight, m.lin.bias)[:, None, :].chunk(m.multiplier, dim=-1)
+            got = tuple(o1) + (tuple(o2) if o2 is not None else ())
+            assert len(got) == len(ref)
+            for a, b in zip(got, ref):
+                assert a.shape == b.shape
+                ulp_check(a, b, ulps=1, frac=0.05)

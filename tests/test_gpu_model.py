@@ -69,6 +69,119 @@ def test_blocks_and_forward_match_reference_outputs(gold, cpu_semantics, monkeyp
     assert maxdiff(results["fused"], results["eager"]) <= 2.0 ** -5
 
 
+def test_e4m3_activations_and_quantised_embedders_match_reference_outputs(golden_dir, lib, cpu_semantics, monkeypatch):
+    """flux_tiny_e4m3.pt (reference quantised with input_float8_dtype=float8_e4m3fn, quantize_flow_embedder_layers=True):
+    the fused path, the eager kernel path and the whole forward in the e4m3 x e4m3 arithmetic north_star names."""
+    from flux_fp8_api_b200 import blocks, model as M, pipeline as PL
+    from flux_fp8_api_b200.f8linear import F8Linear
+
+    g = torch.load(os.path.join(golden_dir, "flux_tiny_e4m3.pt"))
+    spec = M.FluxSpec(params=M.FluxParams(**g["tiny"]), prequantized_flow=True, quantize_flow_embedder_layers=True)
+    with torch.device(DEV):
+        net = M.Flux(spec, dtype=BF16).to(BF16)
+    net.load_state_dict(g["state"], strict=True)
+    net = net.to(DEV).eval()
+    PL.set_input_float8_dtype(net, torch.float8_e4m3fn)
+    assert sum(isinstance(m, F8Linear) for m in net.modules()) == g["n_f8"] == 21
+    assert isinstance(net.img_in, F8Linear) and isinstance(net.vector_in.out_layer, F8Linear) and PL.all_frozen(net)
+    bi = {k: v.to(DEV) for k, v in g["block_in"].items()}
+    inp = {k: v.to(DEV) for k, v in g["inputs"].items()}
+    results = {}
+    with torch.inference_mode():
+        for mode in ("fused", "eager"):
+            if mode == "eager":
+                monkeypatch.setattr(blocks.DoubleStreamBlock, "_fusable", lambda self, a, b: False)
+                monkeypatch.setattr(blocks.SingleStreamBlock, "_fusable", lambda self, a: False)
+            d_img, d_txt = net.double_blocks[0](img=bi["img"], txt=bi["txt"], vec=bi["vec"], pe=bi["pe"])
+            s_out = net.single_blocks[0](torch.cat((bi["txt"], bi["img"]), 1), vec=bi["vec"], pe=bi["pe"])
+            y = net(**inp)
+            assert maxdiff(d_img, g["double_img"]) <= 2.0 ** -4
+            assert maxdiff(d_txt, g["double_txt"]) <= 2.0 ** -4
+            assert maxdiff(s_out, g["single"]) <= 2.0 ** -4
+            assert maxdiff(y, g["y_fp8"]) <= 2.0 ** -4
+            results[mode] = y
+    assert maxdiff(results["fused"], results["eager"]) <= 2.0 ** -5
+    # the e5m2 interpretation of the same state is a different function: the format switch is live
+    PL.set_input_float8_dtype(net, torch.float8_e5m2)
+    with torch.inference_mode():
+        assert not torch.equal(net(**inp), results["eager"])
+
+
+def test_four_step_trajectory_matches_reference(gold, golden_dir, cpu_semantics):
+    """flux_tiny_traj.pt: 4 Euler steps through the reference (flux_pipeline.py:627-651).  Teacher-forced per step
+    (each step starts from the reference's latent) to 2^-4, and free-running end to end -- eager launches, CUDA-graph
+    replay and the host-buffer API -- within 4 x 2^-4 of the reference's final latent."""
+    from flux_fp8_api_b200 import pipeline as PL
+
+    traj = torch.load(os.path.join(golden_dir, "flux_tiny_traj.pt"))
+    net = tiny_net(gold)
+    req = {k: v.to(DEV) for k, v in traj["inputs"].items() if k != "timesteps"}
+    ts = traj["timesteps"]
+    eager = PL.DenoiseSession(net, req, use_graph=False)
+    graph = PL.DenoiseSession(net, req, use_graph=True)
+    prev = req["img"]
+    for i, (t_curr, t_prev) in enumerate(zip(ts[:-1], ts[1:])):
+        out_e = eager.step_device(prev, t_curr, t_prev)
+        out_g = graph.step_device(prev, t_curr, t_prev)
+        assert torch.equal(out_e, out_g), i
+        assert maxdiff(out_e, traj["latents"][i]) <= 2.0 ** -4, i
+        prev = traj["latents"][i].to(DEV)
+    final = traj["latents"][-1]
+    run_e, run_g = eager.run(ts), graph.run(ts)
+    assert torch.equal(run_e, run_g)
+    assert maxdiff(run_g, final) <= 4 * 2.0 ** -4
+    host = req["img"].cpu().pin_memory()
+    for t_curr, t_prev in zip(ts[:-1], ts[1:]):
+        host = graph.step_host(host, t_curr, t_prev).clone()
+    assert torch.equal(host.to(DEV), run_g)
+
+
+def test_graph_survives_cache_resets_other_sessions_and_allocator_reuse(gold):
+    """a captured graph reads per-request tensors (txt_in(txt), vector / guidance embeddings, pe,
+    cos/sin).  They are owned by the GraphedStep; resetting the model's request cache, running other requests through
+    the same model and churning the allocator in between must not change a replay."""
+    from flux_fp8_api_b200 import pipeline as PL
+
+    net = tiny_net(gold)
+    req = {k: v.to(DEV) for k, v in gold["inputs"].items() if k != "timesteps"}
+    sched = PL.get_schedule(4, req["img"].shape[1])
+    sess = PL.DenoiseSession(net, req, use_graph=True)
+    want = sess.step_device(req["img"], sched[0], sched[1])
+    for rnd in range(3):
+        net.reset_request_cache()
+        other = {k: (v * 0.5 if v.is_floating_point() and k in ("txt", "y") else v).clone() for k, v in req.items()}
+        PL.DenoiseSession(net, other, use_graph=(rnd % 2 == 0)).step_device(other["img"], sched[1], sched[2])
+        net.reset_request_cache()
+        torch.cuda.empty_cache()
+        junk = [torch.full((1 << 18,), float(rnd + 1), device=DEV, dtype=BF16) for _ in range(64)]  # recycle freed blocks
+        del junk
+        assert torch.equal(sess.step_device(req["img"], sched[0], sched[1]), want), rnd
+    assert sess.step.captures == 1
+    # a LoRA under the cached embeddings bumps the epoch: the next call re-captures and sees the new weights
+    lora = {"txt_in.lora_A.weight": torch.randn(4, net.txt_in.in_features).to(BF16),
+            "txt_in.lora_B.weight": (torch.randn(net.txt_in.out_features, 4) * 0.5).to(BF16)}
+    net.load_lora(lora, scale=1.0, name="t")
+    changed = sess.step_device(req["img"], sched[0], sched[1])
+    assert sess.step.captures == 2 and not torch.equal(changed, want)
+    fresh = PL.DenoiseSession(net, req, use_graph=False).step_device(req["img"], sched[0], sched[1])
+    assert torch.equal(changed, fresh)
+    net.unload_lora("t")
+
+
+def test_batch_beyond_the_batched_modulation_limit_falls_back(gold):
+    """B = 17 exceeds fluxb200_modulation_batched's 16 rows; Flux.forward must fall back to the
+    per-block Modulation path (M > 16 goes through the GEMM) instead of raising, with identical per-sample results."""
+    net = tiny_net(gold)
+    inp = {k: v.to(DEV) for k, v in gold["inputs"].items()}
+    big = {k: v.repeat(9, *([1] * (v.dim() - 1)))[:17] for k, v in inp.items()}
+    with torch.inference_mode():
+        y2 = net(**inp)
+        y17 = net(**big)
+    assert y17.shape[0] == 17
+    assert maxdiff(y17[:2], y2) <= 2.0 ** -5  # batched GEMV vs GEMM accumulation order
+    assert torch.equal(y17[0], y17[2]) and torch.equal(y17[1], y17[3])
+
+
 def test_batched_modulation_matches_per_layer(gold):
     """ModulationBank (one launch pair for every Modulation.lin) == each Modulation.forward on its own, to 1 bf16
     ulp (the two GEMV kernels accumulate in a different order), for several batch sizes."""
@@ -127,15 +240,17 @@ def test_batch_sharding_is_bit_exact(gold):
 def test_from_linear_calibration_matches_reference_state(golden_dir, cpu_semantics):
     from flux_fp8_api_b200.f8linear import F8Linear
 
-    for c in torch.load(os.path.join(golden_dir, "f8linear.pt")):
-        if "e5m2" not in c["in_dtype"]:
-            continue
+    cases = torch.load(os.path.join(golden_dir, "f8linear.pt"))
+    assert {c["in_dtype"] for c in cases} == {"torch.float8_e5m2", "torch.float8_e4m3fn"}
+    for c in cases:
+        in_dt = torch.float8_e5m2 if "e5m2" in c["in_dtype"] else torch.float8_e4m3fn
         K, N = c["K"], c["N"]
         lin = torch.nn.Linear(K, N, bias=True).to(BF16)
         with torch.no_grad():
             lin.weight.copy_(c["weight_bf16"])
             lin.bias.copy_(c["state"]["bias"])
-        f8 = F8Linear.from_linear(lin.to(DEV))
+        f8 = F8Linear.from_linear(lin.to(DEV), input_float8_dtype=in_dt)
+        assert f8.input_float8_dtype == in_dt
         sd = c["state"]
         assert torch.equal(f8.float8_data.view(torch.uint8).cpu(), sd["float8_data"].view(torch.uint8))
         assert torch.equal(f8.scale.cpu(), sd["scale"])

@@ -116,6 +116,42 @@ def test_blocks_and_forward_against_reference(golden_dir):
     assert maxdiff(g["y_fp8"], g["y_bf16"]) < 0.1  # the fp8 path tracks the bf16 path
 
 
+def test_e4m3_activations_and_quantised_embedders_against_reference(golden_dir):
+    """flux_tiny_e4m3.pt: reference quantised with input_float8_dtype=float8_e4m3fn and
+    quantize_flow_embedder_layers=True (float8_quantize.py:298-304, 447-484)."""
+    g = load(golden_dir, "flux_tiny_e4m3.pt")
+    E4M3 = torch.float8_e4m3fn
+    sd, cfg, bi = g["state"], g["cfg"], g["block_in"]
+    heads = g["tiny"]["num_heads"]
+    assert g["n_f8"] == 21 and "img_in.float8_data" in sd and "time_in.in_layer.float8_data" in sd
+    assert "final_layer.linear.float8_data" not in sd
+    img, txt = O.double_block(bi["img"], bi["txt"], bi["vec"], bi["pe"], sd, "double_blocks.0.", heads, E4M3)
+    assert maxdiff(img, g["double_img"]) <= 2.0 ** -4 and maxdiff(txt, g["double_txt"]) <= 2.0 ** -4
+    xs = torch.cat((bi["txt"], bi["img"]), 1)
+    assert maxdiff(O.single_block(xs, bi["vec"], bi["pe"], sd, "single_blocks.0.", heads, E4M3), g["single"]) <= 2.0 ** -4
+    assert maxdiff(O.flux_forward(sd, cfg, **g["inputs"], in_dtype=E4M3), g["y_fp8"]) <= 2.0 ** -4
+    # the e5m2 evaluation of the same state is a DIFFERENT function: the fixture really pins the activation format
+    assert maxdiff(O.flux_forward(sd, cfg, **g["inputs"]), g["y_fp8"]) > 0
+
+
+def test_four_step_trajectory_against_reference(golden_dir):
+    """flux_tiny_traj.pt: the Euler loop of flux_pipeline.py:627-651 over the reference Flux.forward, 4 steps."""
+    g = load(golden_dir, "flux_tiny_traj.pt")
+    model = load(golden_dir, "flux_tiny.pt")
+    inp, ts = g["inputs"], g["timesteps"]
+    assert len(ts) == 5 and len(g["latents"]) == 4
+    img = inp["img"]
+    for i, (t_curr, t_prev) in enumerate(zip(ts[:-1], ts[1:])):
+        t_vec = torch.full((img.shape[0],), t_curr, dtype=BF16)
+        pred = O.flux_forward(model["state"], model["cfg"], img, inp["img_ids"], inp["txt"], inp["txt_ids"], t_vec,
+                              inp["y"], inp["guidance"])
+        # teacher-forced per step (the fixture's latent is the next input), so the bound does not compound
+        assert maxdiff(pred, g["preds"][i]) <= 2.0 ** -4, i
+        assert maxdiff(O.euler_step(g["latents"][i - 1] if i else inp["img"], g["preds"][i], t_curr, t_prev),
+                       g["latents"][i]) == 0.0, i
+        img = g["latents"][i]
+
+
 def test_schedule_matches_reference_formula():
     ts = O.get_schedule(28, 4096)
     assert len(ts) == 29 and ts[0] == 1.0 and ts[-1] == 0.0
