@@ -145,7 +145,7 @@ class ClockSampler:
 def gemm_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum per f8_gemm_kernel launch, averaged over the GEMM launches of one
     c2 step, from the newest committed ncu capture (profiles/r*_gemm_traffic.json, written by tools/ncu_traffic.py from
-    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over tests/profile_step.py).  None if absent."""
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over tools/profile_step.py).  None if absent."""
     for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:

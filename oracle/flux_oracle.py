@@ -59,8 +59,9 @@ def quantize_weight(w: Tensor, dtype: torch.dtype = E4M3) -> Tuple[Tensor, Tenso
 
 
 #: "restated": the arithmetic below.  "library": call the same PyTorch entry points the reference calls
-#: (torch._scaled_mm with use_fast_accum, F.scaled_dot_product_attention) -- CUDA only; used by
-#: tests/ref_gpu_timing.py to time / cross-check "the reference's eager fp8 path" on the B200 itself.
+#: (torch._scaled_mm with use_fast_accum, F.scaled_dot_product_attention) -- CUDA only; a round-1 cross-check
+#: of the restatement against the library kernels.  (Round 2 runs the staged reference modules themselves on the
+#: B200: oracle/ref_loader.py, tests/test_gpu_reference.py, bench.py's gpu_reference block.)
 BACKEND = "restated"
 
 

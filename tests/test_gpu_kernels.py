@@ -241,14 +241,18 @@ def attn_ref(O, q, k, v):
     return x.reshape(q.shape[0], q.shape[2], -1)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
-@pytest.mark.parametrize("B,H,S,std", [(1, 1, 128, 1.0), (2, 2, 384, 2.0), (1, 2, 320, 1.0), (1, 3, 1000, 1.5)])
-def test_attention_small(ops, O, variant, B, H, S, std):
+@pytest.mark.parametrize("B,H,S,std", [(1, 1, 128, 1.0), (2, 2, 384, 2.0), (1, 2, 320, 1.0), (1, 3, 1000, 1.5), (1, 2, 1, 1.0),
+                                       (1, 1, 129, 1.0), (2, 1, 255, 3.0)])
+def test_attention_small(ops, O, B, H, S, std):
+    """Ragged sequence lengths (S not a multiple of the 128-row tiles, S = 1) and larger logits."""
     g = gen(19)
     q = (torch.randn(B, H, S, 128, device=DEV, generator=g) * std).to(BF16)
     k = (torch.randn(B, H, S, 128, device=DEV, generator=g) * std).to(BF16)
     v = torch.randn(B, H, S, 128, device=DEV, generator=g).to(BF16)
-    ulp_check(ops.attention(q, k, v, variant=variant), attn_ref(O, q, k, v), ulps=2, frac=1.0)
+    ulp_check(ops.attention(q, k, v), attn_ref(O, q, k, v), ulps=2, frac=1.0)
+    # the product library ships one attention kernel: experimental tilings are refused, not silently substituted
+    with pytest.raises(ValueError):
+        ops.attention(q, k, v, variant=5)
 
 
 def test_attention_full_size_and_fp8_split_output(ops, O):

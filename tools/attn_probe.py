@@ -1,4 +1,4 @@
-"""Attention phase-timing probe (diagnostics): python tests/attn_probe.py [variant ...]"""
+"""Attention phase-timing probe (diagnostics): python tools/attn_probe.py [variant ...]"""
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flux_fp8_api_b200 import ops, _cabi as cabi

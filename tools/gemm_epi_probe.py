@@ -1,5 +1,5 @@
 """Diagnostics: the fused-epilogue GEMMs of a Flux block at full size, a few launches each (for ncu / timing).
-    python tests/gemm_epi_probe.py [gelu|gate|all]"""
+    python tools/gemm_epi_probe.py [gelu|gate|all]"""
 import os
 import sys
 

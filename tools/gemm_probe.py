@@ -1,4 +1,4 @@
-"""GEMM timing probe (diagnostics): python tests/gemm_probe.py ; honours FLUXB200_GEMM_CG / FLUXB200_GEMM_DEBUG."""
+"""GEMM timing probe (diagnostics): python tools/gemm_probe.py ; honours FLUXB200_GEMM_CG / FLUXB200_GEMM_DEBUG."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flux_fp8_api_b200 import ops, _cabi as cabi

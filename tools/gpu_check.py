@@ -1,7 +1,7 @@
 """Stand-alone GPU bring-up / diagnostics script (run on the B200 box through gpurun).
 
-    python tests/gpu_check.py            # every group, each in its own subprocess with a timeout
-    python tests/gpu_check.py gemm       # one group in-process
+    python tools/gpu_check.py            # every group, each in its own subprocess with a timeout
+    python tools/gpu_check.py gemm       # one group in-process
 
 Each group compares the CUDA kernels (through the C ABI) with the oracle evaluated on the same
 tensors and prints max-abs / mismatch statistics plus a CUDA-event timing.  The pytest suite

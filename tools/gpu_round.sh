@@ -19,12 +19,12 @@ if has configs; then
   done
 fi
 if has shapes; then
-  python tests/step_shapes.py > gpurun_out/step_shapes.txt 2>&1; tail -14 gpurun_out/step_shapes.txt
+  python tools/step_shapes.py > gpurun_out/step_shapes.txt 2>&1; tail -14 gpurun_out/step_shapes.txt
 fi
 if has ncu; then
-  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tests/profile_step.py > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-  ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/traffic.csv python tests/profile_step.py > gpurun_out/ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
-  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:f8_gemm_kernel -c 8 -o gpurun_out/prof_gemm -f python tests/profile_step.py > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
-  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:attention_kernel -c 2 -o gpurun_out/prof_attn -f python tests/profile_step.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
+  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
+  ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/traffic.csv python tools/profile_step.py > gpurun_out/ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
+  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:f8_gemm_kernel -c 8 -o gpurun_out/prof_gemm -f python tools/profile_step.py > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
+  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:attention_kernel -c 2 -o gpurun_out/prof_attn -f python tools/profile_step.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
 fi
 ls -la gpurun_out | tail -30

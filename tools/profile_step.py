@@ -2,7 +2,7 @@
 denoise step (1024x1024, batch 1) between cudaProfilerStart/Stop.
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-        --log-file gpurun_out/launches.csv python tests/profile_step.py
+        --log-file gpurun_out/launches.csv python tools/profile_step.py
 """
 import os
 import sys

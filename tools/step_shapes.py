@@ -1,5 +1,5 @@
 """Per-shape breakdown of one Flux-dev 1024x1024 step, timed IN the step (eager launches, CUDA events around every
-launch of ours, GPU warm and power-capped as in the bench):  python tests/step_shapes.py"""
+launch of ours, GPU warm and power-capped as in the bench):  python tools/step_shapes.py"""
 import os
 import sys
 from collections import OrderedDict
