@@ -72,6 +72,8 @@ struct GemmParams {
   //   8 = epilogue does its TMEM loads + de-quantisation only (no fused math, no stores)
   // 1|4 is the tcgen05 kind::f8f6f4 ceiling of this tiling: what bench.py reports as the measured FP8 peak.
   int debug;
+  // 1: every epilogue row segment (out / resid / q,k,v) is 32-byte aligned -> 256-bit global loads / stores
+  int wide;
 };
 
 struct TileCoord {
@@ -150,7 +152,12 @@ __device__ __forceinline__ void dequant_bias_packed(const uint32_t (&v)[32], flo
   }
 }
 
-__device__ __forceinline__ void store_packed_bf16x32(__nv_bfloat16* dst, const uint32_t (&yp)[16]) {
+__device__ __forceinline__ void store_packed_bf16x32(__nv_bfloat16* dst, const uint32_t (&yp)[16], bool wide = false) {
+  if (wide) {
+    stg_v8(dst, yp[0], yp[1], yp[2], yp[3], yp[4], yp[5], yp[6], yp[7]);
+    stg_v8(dst + 16, yp[8], yp[9], yp[10], yp[11], yp[12], yp[13], yp[14], yp[15]);
+    return;
+  }
   uint4* op = reinterpret_cast<uint4*>(dst);
 #pragma unroll
   for (int q = 0; q < 4; ++q) op[q] = make_uint4(yp[q * 4], yp[q * 4 + 1], yp[q * 4 + 2], yp[q * 4 + 3]);
@@ -170,18 +177,20 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&
 }
 
 template <int FMT>
-__device__ __forceinline__ void store_fp8x32(uint8_t* dst, const float (&p)[32]) {
-  uint4* op = reinterpret_cast<uint4*>(dst);
+__device__ __forceinline__ void store_fp8x32(uint8_t* dst, const float (&p)[32], bool wide = false) {
+  uint32_t w[8];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint32_t w[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      int j = q * 16 + t * 4;
-      w[t] = static_cast<uint32_t>(to_fp8x2<FMT>(p[j], p[j + 1])) |
-             (static_cast<uint32_t>(to_fp8x2<FMT>(p[j + 2], p[j + 3])) << 16);
-    }
-    op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int t = 0; t < 8; ++t) {
+    const int j = t * 4;
+    w[t] = static_cast<uint32_t>(to_fp8x2<FMT>(p[j], p[j + 1])) |
+           (static_cast<uint32_t>(to_fp8x2<FMT>(p[j + 2], p[j + 3])) << 16);
+  }
+  if (wide) {
+    stg_v8(dst, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+  } else {
+    uint4* op = reinterpret_cast<uint4*>(dst);
+    op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    op[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
@@ -200,58 +209,74 @@ __device__ __forceinline__ void epi_plain(const fluxb200_gemm_args& g, const Row
 // exact, then the bf16 rounding of the eager op); HADD2 rounds the exact sum once (the eager op adds in fp32 and rounds:
 // identical unless the fp32 add itself had to round, i.e. operands > 2^16 apart, and then only on a tie).
 __device__ __forceinline__ void epi_gate_residual(const fluxb200_gemm_args& g, const RowInfo& ri, int col,
-                                                  uint32_t (&yp)[16]) {
-  const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.gate) +
-                                                   static_cast<int64_t>(ri.b) * g.gate_batch_stride + col);
-  const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.resid) +
-                                                   static_cast<int64_t>(ri.row) * g.ldr + col);
+                                                  uint32_t (&yp)[16], bool wide) {
+  const __nv_bfloat16* gsrc =
+      reinterpret_cast<const __nv_bfloat16*>(g.gate) + static_cast<int64_t>(ri.b) * g.gate_batch_stride + col;
+  const __nv_bfloat16* rsrc = reinterpret_cast<const __nv_bfloat16*>(g.resid) + static_cast<int64_t>(ri.row) * g.ldr + col;
+  uint32_t gw[16], rw[16];
+  if (wide) {
+    // (resid may alias out: plain loads, not the read-only path)
+    const u32x8 r0 = ldg_v8(rsrc), r1 = ldg_v8(rsrc + 16);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 gg = __ldg(gp + q);
-    uint4 rr = rp[q];
-    uint32_t gw[4] = {gg.x, gg.y, gg.z, gg.w};
-    uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+    for (int j = 0; j < 8; ++j) rw[j] = r0.v[j], rw[8 + j] = r1.v[j];
+  } else {
+    const uint4* rp = reinterpret_cast<const uint4*>(rsrc);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yp[q * 4 + t]);
-      const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[t]);
-      const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[t]);
-      const __nv_bfloat162 o2 = __hadd2_rn(r2, __hmul2_rn(g2, y2));
-      yp[q * 4 + t] = *reinterpret_cast<const uint32_t*>(&o2);
+    for (int q = 0; q < 4; ++q) {
+      const uint4 rr = rp[q];
+      rw[q * 4] = rr.x, rw[q * 4 + 1] = rr.y, rw[q * 4 + 2] = rr.z, rw[q * 4 + 3] = rr.w;
     }
   }
-  store_packed_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, yp);
+  {
+    const uint4* gp = reinterpret_cast<const uint4*>(gsrc);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 gg = __ldg(gp + q);
+      gw[q * 4] = gg.x, gw[q * 4 + 1] = gg.y, gw[q * 4 + 2] = gg.z, gw[q * 4 + 3] = gg.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yp[j]);
+    const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[j]);
+    const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+    const __nv_bfloat162 o2 = __hadd2_rn(r2, __hmul2_rn(g2, y2));
+    yp[j] = *reinterpret_cast<const uint32_t*>(&o2);
+  }
+  store_packed_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, yp, wide);
 }
 
 template <int FMT>
-__device__ __forceinline__ void gelu_quant_store(uint8_t* dst, float oscale, bool scale_is_bf16, float (&y)[32]) {
+__device__ __forceinline__ void gelu_quant_store(uint8_t* dst, float oscale, bool scale_is_bf16, float (&y)[32], bool wide) {
   if (scale_is_bf16) {
     // bf16(gelu) * scale -> bf16 -> fp8 on packed pairs (quant_pair_bf16scale)
     const __nv_bfloat162 s2 = __floats2bfloat162_rn(oscale, oscale);
-    uint4* op = reinterpret_cast<uint4*>(dst);
+    uint32_t w[8];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint32_t w[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int j = q * 16 + t * 4;
-        w[t] = static_cast<uint32_t>(quant_pair_bf16scale<FMT>(gelu_tanh_fast(y[j]), gelu_tanh_fast(y[j + 1]), s2)) |
-               (static_cast<uint32_t>(quant_pair_bf16scale<FMT>(gelu_tanh_fast(y[j + 2]), gelu_tanh_fast(y[j + 3]), s2)) << 16);
-      }
-      op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int t = 0; t < 8; ++t) {
+      const int j = t * 4;
+      w[t] = static_cast<uint32_t>(quant_pair_bf16scale<FMT>(gelu_tanh_fast(y[j]), gelu_tanh_fast(y[j + 1]), s2)) |
+             (static_cast<uint32_t>(quant_pair_bf16scale<FMT>(gelu_tanh_fast(y[j + 2]), gelu_tanh_fast(y[j + 3]), s2)) << 16);
+    }
+    if (wide) {
+      stg_v8(dst, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+    } else {
+      uint4* op = reinterpret_cast<uint4*>(dst);
+      op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      op[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) y[j] = quant_pre<FMT>(bf16r(gelu_tanh_fast(y[j])), oscale);
-    store_fp8x32<FMT>(dst, y);
+    store_fp8x32<FMT>(dst, y, wide);
   }
 }
 
 __device__ __forceinline__ void epi_gelu_quant(const fluxb200_gemm_args& g, const RowInfo& ri, int out_col, float oscale,
-                                               bool scale_is_bf16, float (&y)[32]) {
+                                               bool scale_is_bf16, float (&y)[32], bool wide) {
   uint8_t* dst = reinterpret_cast<uint8_t*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + out_col;
-  if (g.out_fmt == FLUXB200_E5M2) gelu_quant_store<1>(dst, oscale, scale_is_bf16, y);
-  else gelu_quant_store<0>(dst, oscale, scale_is_bf16, y);
+  if (g.out_fmt == FLUXB200_E5M2) gelu_quant_store<1>(dst, oscale, scale_is_bf16, y, wide);
+  else gelu_quant_store<0>(dst, oscale, scale_is_bf16, y, wide);
 }
 
 // One thread owns one row and HALF a head: 64 accumulator columns starting at TMEM address `taddr` (tile column
@@ -260,7 +285,7 @@ __device__ __forceinline__ void epi_gelu_quant(const fluxb200_gemm_args& g, cons
 // ([4 parts][128 rows], double-buffered by the caller) and a 64-thread named barrier `bar_id`.
 __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const RowInfo& ri, uint32_t taddr, int col0,
                                              float s, uint32_t norm_saddr, uint32_t ss_saddr, int part, int row_in_cta,
-                                             uint32_t bar_id) {
+                                             uint32_t bar_id, bool wide) {
   const int hd = g.num_heads * kHeadDim;
   const int which = col0 / hd;
   const int within = col0 - which * hd;
@@ -303,8 +328,8 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
   }
   if (which == 2) {
     if (ri.valid) {
-      store_packed_bf16x32(dst, yp[0]);
-      store_packed_bf16x32(dst + 32, yp[1]);
+      store_packed_bf16x32(dst, yp[0], wide);
+      store_packed_bf16x32(dst + 32, yp[1], wide);
     }
     return;
   }
@@ -355,7 +380,7 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
         op[t * 2 + u] = *reinterpret_cast<const uint32_t*>(&o);
       }
     }
-    store_packed_bf16x32(dst + c * 32, op);
+    store_packed_bf16x32(dst + c * 32, op, wide);
   }
 }
 
@@ -520,6 +545,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
     uint32_t aphase = 0;
     // Per-problem scalars, fetched ONCE: read per tile they put two dependent L2 round trips (~1 us) in front of every
     // tile's epilogue, which for K = 3072 is a tenth of the tile's time and sits on the path that frees the accumulator.
+    const bool wide = P.wide != 0;
     float s_pp[2] = {0.f, 0.f}, os_pp[2] = {0.f, 0.f};
 #pragma unroll
     for (int pi = 0; pi < 2; ++pi) {
@@ -556,7 +582,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
           static_assert(2 * kPartCols == kHeadDim || (EPI != FLUXB200_EPI_QKV_ROPE && EPI != FLUXB200_EPI_LINEAR1),
                         "QKV epilogues need BN == 256");
           epi_qkv_head(g, ri, taddr, col0, s, smem_u32(norm_smem) + tc.pi * 2 * kHeadDim * 4,
-                       smem_u32(ss_smem) + as * 4 * kBM * 4, part, lg * 32 + lane, 1 + lg * 2 + (part >> 1));
+                       smem_u32(ss_smem) + as * 4 * kBM * 4, part, lg * 32 + lane, 1 + lg * 2 + (part >> 1), wide);
         }
       } else {
         const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
@@ -572,12 +598,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
             // (N % 32 == 0 is validated on the host for this epilogue)
             uint32_t yp[16];
             dequant_bias_packed(v, s, bias, col, yp);
-            if (ri.valid) epi_gate_residual(g, ri, col, yp);
+            if (ri.valid) epi_gate_residual(g, ri, col, yp, wide);
           } else if (EPI == FLUXB200_EPI_PLAIN && full_cols) {
             uint32_t yp[16];
             dequant_bias_packed(v, s, bias, col, yp);
             if (ri.valid)
-              store_packed_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, yp);
+              store_packed_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<int64_t>(ri.row) * g.ldo + col, yp, wide);
           } else {
             float y[32];
             dequant_bias(v, s, full_cols ? bias : nullptr, col, y);
@@ -590,9 +616,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
             if constexpr (EPI == FLUXB200_EPI_PLAIN) {
               epi_plain(g, ri, col, y);
             } else if constexpr (EPI == FLUXB200_EPI_GELU_QUANT) {
-              epi_gelu_quant(g, ri, g.out_col_offset + col, oscale, oscale_is_bf16, y);
+              epi_gelu_quant(g, ri, g.out_col_offset + col, oscale, oscale_is_bf16, y, wide);
             } else if constexpr (EPI == FLUXB200_EPI_LINEAR1) {
-              epi_gelu_quant(g, ri, g.out_col_offset + col - 3 * g.num_heads * kHeadDim, oscale, oscale_is_bf16, y);
+              epi_gelu_quant(g, ri, g.out_col_offset + col - 3 * g.num_heads * kHeadDim, oscale, oscale_is_bf16, y, wide);
             }
           }
         }
@@ -736,6 +762,24 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
     if (ilv && epi == FLUXB200_EPI_LINEAR1 && count == 1) P.q_n_tiles = (3 * g.num_heads * kHeadDim) / bn;
   }
   P.num_k_blocks = (g.K + kBK - 1) / kBK;
+  {
+    // 256-bit epilogue accesses need every row segment the epilogue touches to start on a 32-byte boundary
+    static const bool allow_wide = [] {
+      const char* e = getenv("FLUXB200_GEMM_WIDE");
+      return e == nullptr || atoi(e) != 0;
+    }();
+    auto al32 = [](const void* p, int64_t row_bytes) {
+      return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31) == 0 && row_bytes % 32 == 0);
+    };
+    bool w = allow_wide;
+    for (int i = 0; i < count && w; ++i) {
+      const fluxb200_gemm_args& gi = args[i];
+      const bool f8out = gi.epilogue == FLUXB200_EPI_GELU_QUANT || gi.epilogue == FLUXB200_EPI_LINEAR1;
+      w = w && al32(gi.out, gi.ldo * (f8out ? 1 : 2)) && (!f8out || gi.out_col_offset % 32 == 0);
+      w = w && al32(gi.resid, gi.ldr * 2) && al32(gi.q, 256) && al32(gi.k, 256) && al32(gi.v, 256);
+    }
+    P.wide = w ? 1 : 0;
+  }
   P.idesc = make_idesc(g.a_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3, g.w_fmt == FLUXB200_E5M2 ? kFmtE5M2 : kFmtE4M3,
                        kBM * cg, bn);
   P.tiles0 = 0;

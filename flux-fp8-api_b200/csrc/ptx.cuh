@@ -56,6 +56,33 @@ __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
 
+// 256-bit global accesses (LDG/STG.E.ENL2.256, sm_100+, PTX 8.8): one instruction moves a thread's whole 32-byte L2
+// sector.  The GEMM epilogues are thread == output row, so a warp's access touches 32 different rows: with 16-byte
+// accesses every instruction half-fills 32 sectors and the L2 sees twice the transactions.  32-byte aligned addresses only.
+struct u32x8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ u32x8 ldg_v8(const void* p) {
+  u32x8 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ u32x8 ldg_nc_v8(const void* p) {  // read-only data (never written by this grid)
+  u32x8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                       uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4),
+               "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {  // one FMNMX3
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

@@ -89,7 +89,7 @@ def build_pair(name):
     PL.denoise(theirs, dict(req), PL.get_schedule(13, L, shift=guidance))  # the reference's own warm-up calibration
     assert R.all_frozen(ref, theirs)
     with torch.device(DEV):
-        ours = M.Flux(M.FluxSpec(params=params, prequantized_flow=True, quantize_modulation=qmod), dtype=BF16)
+        ours = M.Flux(M.FluxSpec(params=params, prequantized_flow=True, quantize_modulation=qmod), dtype=BF16).to(BF16)
     missing, unexpected = ours.load_state_dict(theirs.state_dict(), strict=True)
     assert not missing and not unexpected
     ours.eval()
@@ -213,6 +213,12 @@ def test_full_depth_parity_against_the_reference_on_this_gpu(name, lib):
             h.remove()
         ref.fm.attention = ref_attention
 
+    def dump():
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
+            json.dump(report, f)
+
+    dump()
     # ---- free-running forward at full depth: ours / reference / reference on another SDPA backend ----------------
     with torch.inference_mode():
         y_ours = ours(**call)
@@ -229,9 +235,7 @@ def test_full_depth_parity_against_the_reference_on_this_gpu(name, lib):
     report["free_running"] = free
     assert torch.isfinite(y_ours.float()).all()
 
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
-        json.dump(report, f)
+    dump()
 
     # ---- bars -------------------------------------------------------------------------------------------------------
     n_f8 = sum(isinstance(m, ref.f8.F8Linear) for m in theirs.modules())

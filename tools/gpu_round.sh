@@ -20,6 +20,10 @@ if has configs; then
 fi
 if has shapes; then
   python tools/step_shapes.py > gpurun_out/step_shapes.txt 2>&1; tail -14 gpurun_out/step_shapes.txt
+  FLUXB200_GEMM_WIDE=0 python tools/step_shapes.py > gpurun_out/step_shapes_narrow.txt 2>&1; tail -14 gpurun_out/step_shapes_narrow.txt
+fi
+if has sdpa; then
+  python tools/sdpa_compare.py > gpurun_out/sdpa_compare.txt 2>&1; cat gpurun_out/sdpa_compare.txt
 fi
 if has ncu; then
   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
