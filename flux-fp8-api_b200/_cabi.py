@@ -40,6 +40,7 @@ EXPORTS = (
     "fluxb200_lora_fuse",
     "fluxb200_debug_counters",
     "fluxb200_gemm_probe_mode",
+    "fluxb200_gemm_force_tiling",
 )
 
 
@@ -195,6 +196,7 @@ def load() -> C.CDLL:
     ]
     lib.fluxb200_debug_counters.argtypes = [C.POINTER(C.c_ulonglong)]
     lib.fluxb200_gemm_probe_mode.argtypes = [C.c_int]
+    lib.fluxb200_gemm_force_tiling.argtypes = [C.c_int, C.c_int]
     for name in EXPORTS:
         if name != "fluxb200_last_error":
             getattr(lib, name).restype = C.c_int

@@ -8,6 +8,13 @@
 //           128 rows of A and its 128-row half of W, the leader CTA issues M=256 MMAs that read both CTAs' shared
 //           memory, each CTA's TMEM receives its 128 accumulator rows.  Halves the shared-memory operand traffic
 //           per MMA, which is what caps the single-CTA form at ~55 % tensor-pipe utilisation (profiles/).
+//   CG = 2, MC = 2  ("quad"): a cluster of FOUR CTAs = two pairs working on two N-adjacent 256 x 256 tiles of the same
+//           256 rows.  Both pairs need the same A rows, so every 128-row A slab is fetched ONCE: the two CTAs that hold
+//           it (same in-pair rank, different pair) each load 64 of its rows and TMA-multicast them to both.  A 256 x 256
+//           pair tile moves 64 KB of operands per 16.8 MFLOP = 256 flop/B, and the step's large GEMMs sit exactly on the
+//           L2 -> SM delivery cap at that intensity (~6400 B/clk chip-wide, B300_MICROARCH.md "LTS throughput cap");
+//           the quad moves 96 KB per two tiles = 341 flop/B.  Four-CTA clusters occupy only 132 of the 148 SMs
+//           (GPC packing), which the power-capped clock largely gives back.
 // Roles per CTA:
 //   warp 0      TMA producer: A[128 x 128B] and W[BN x 128B] tiles, SWIZZLE_128B, kStages-deep ring
 //   warp 1      MMA issuer:   tcgen05.mma.kind::f8f6f4 (M=128, N=BN, K=32), fp32 accumulators in TMEM,
@@ -54,7 +61,7 @@ struct GemmSmem {
 // Up to two problems that share N, K, formats and epilogue (the txt and img streams of a DoubleStreamBlock) run
 // as one persistent launch: tiles [0, tiles0) belong to problem 0, the rest to problem 1.
 struct GemmParams {
-  CUtensorMap tmap_a[2];
+  CUtensorMap tmap_a[2];   // A boxes of 128 rows (one CTA's slab); MC == 2: 64 rows (half a slab, multicast)
   CUtensorMap tmap_w[2];
   fluxb200_gemm_args g[2];
   int num_m_tiles[2];
@@ -81,13 +88,20 @@ struct TileCoord {
   int m_blk;  // tile row (in units of the M tile of the launch)
   int n_blk;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) {
+// MC pairs of a cluster share a "super tile": MC N-adjacent tiles of one M block; tile indices, tiles0 and num_tiles
+// count super tiles, and pair `sub` of the cluster takes N tile  i * MC + sub.
+template <int MC = 1>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile, int sub = 0) {
   TileCoord c;
   c.pi = tile >= P.tiles0 ? 1 : 0;
   const int local = tile - (c.pi ? P.tiles0 : 0);
   const int nm = P.num_m_tiles[c.pi];
   c.m_blk = local % nm;
   int i = local / nm;
+  if constexpr (MC > 1) {
+    c.n_blk = i * MC + sub;
+    return c;
+  }
   if (P.q_n_tiles > 0) {
     // position i of the schedule is a QKV tile iff floor((i+1) q / N) > floor(i q / N)   (q of every N, evenly spaced)
     const int q = P.q_n_tiles, N = P.num_n_tiles;
@@ -386,10 +400,11 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
 
 // ---- the kernel -------------------------------------------------------------------------------------
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int MC = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_constant__ GemmParams P) {
   using S = GemmSmem<BN, CG>;
   static_assert(CG == 1 || BN == 256, "the 2-CTA tiling is 256 x 256");
+  static_assert(MC == 1 || (MC == 2 && CG == 2), "A multicast: two cta_group::2 pairs per cluster");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
@@ -402,10 +417,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;  // 0 = leader of the pair
-  const int tile0 = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;
-  const int tile_stride = CG == 2 ? gridDim.x >> 1 : gridDim.x;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0;  // rank in the cluster (CG * MC CTAs)
+  const uint32_t cta_rank = crank & 1;                      // rank in the pair: 0 = leader (issues the MMAs)
+  const uint32_t sub = crank >> 1;                          // which pair of the cluster (MC == 2)
+  const uint32_t leader = crank & ~1u;                      // cluster rank of this pair's leader
+  constexpr int kClusterCtas = CG * MC;
+  const int tile0 = blockIdx.x / kClusterCtas;
+  const int tile_stride = gridDim.x / kClusterCtas;
   constexpr int kTileM = kBM * CG;
+  constexpr uint16_t kAllMask = (1u << kClusterCtas) - 1;   // every CTA of the cluster
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << leader);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmap_a[0]);
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MC);  // MC == 2: a slot also receives multicast data for the OTHER pair's MMAs
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -461,7 +482,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-      const TileCoord tc = decode_tile(P, tile);
+      const TileCoord tc = decode_tile<MC>(P, tile, sub);
       const int m0 = tc.m_blk * kTileM + cta_rank * kBM;
       const int n0 = tc.n_blk * BN + cta_rank * S::kBRows;
       const CUtensorMap* tm_a = &P.tmap_a[tc.pi];
@@ -475,7 +496,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
           } else if constexpr (CG == 2) {
             // all bytes of the pair are accounted on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStage);
-            tma_load_2d_2sm(sa, tm_a, &full_bar[stage], kb * kBK, m0);
+            if constexpr (MC == 2) {
+              // this CTA fetches rows [64 sub, 64 sub + 64) of the slab that it and the same-rank CTA of the other pair
+              // both need, and multicasts them to the two
+              tma_load_2d_2sm_mc(sa + sub * (S::kA / 2), tm_a, &full_bar[stage], kb * kBK, m0 + sub * (kBM / 2),
+                                 static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + 2))));
+            } else {
+              tma_load_2d_2sm(sa, tm_a, &full_bar[stage], kb * kBK, m0);
+            }
             tma_load_2d_2sm(sa + S::kA, tm_w, &full_bar[stage], kb * kBK, n0);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], S::kStage);
@@ -517,10 +545,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
               else
                 mma_f8f6f4_ss(d_tmem, desc_advance(ad, k * 32), desc_advance(bd, k * 32), P.idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            // smem slot reusable (in both CTAs) once these MMAs have read it
-            if constexpr (CG == 2) tc_commit_2sm(&empty_bar[stage], 3); else tc_commit(&empty_bar[stage]);
+            // smem slot reusable once these MMAs have read it: in both CTAs of the pair, and (MC == 2) in the other
+            // pair's CTAs too, whose producers multicast into this pair's slots
+            if constexpr (CG == 2) tc_commit_2sm(&empty_bar[stage], MC == 2 ? kAllMask : pair_mask);
+            else tc_commit(&empty_bar[stage]);
             if (kb == P.num_k_blocks - 1) {
-              if constexpr (CG == 2) tc_commit_2sm(&tfull_bar[as], 3); else tc_commit(&tfull_bar[as]);
+              if constexpr (CG == 2) tc_commit_2sm(&tfull_bar[as], pair_mask); else tc_commit(&tfull_bar[as]);
             }
           }
           __syncwarp();
@@ -555,7 +585,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
       }
     }
     for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-      const TileCoord tc = decode_tile(P, tile);
+      const TileCoord tc = decode_tile<MC>(P, tile, sub);
       const fluxb200_gemm_args& g = P.g[tc.pi];
       const float s = tc.pi ? s_pp[1] : s_pp[0];
       const float oscale = tc.pi ? os_pp[1] : os_pp[0];
@@ -626,7 +656,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_remote_relaxed(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
+        if constexpr (CG == 2) mbar_arrive_remote_relaxed(&tempty_bar[as], leader); else mbar_arrive(&tempty_bar[as]);
       }
       if (++as == 2) {
         as = 0;
@@ -645,20 +675,53 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
 
 // ---- host side ---------------------------------------------------------------------------------------
 
-template <int BN, int EPI, int CG>
+// Co-resident clusters of `cluster_ctas` CTAs of this kernel (GPC packing: four-CTA clusters reach 132 of 148 SMs).
+template <typename K>
+static int max_active_clusters(K kern, int cluster_ctas, size_t smem) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cluster_ctas * 64);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_ctas;
+  attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count() / cluster_ctas;
+  }
+  return n;
+}
+
+template <int BN, int EPI, int CG, int MC = 1>
 static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
   using S = GemmSmem<BN, CG>;
   static bool attr_set = false;
-  auto kern = f8_gemm_kernel<BN, EPI, CG>;
+  static int units = 0;  // CTAs (CG == 1), pairs (CG == 2) or quads (MC == 2) that fit on the device
+  auto kern = f8_gemm_kernel<BN, EPI, CG, MC>;
   if (!attr_set) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    units = MC == 1 ? sm_count() / CG : max_active_clusters(kern, CG * MC, S::kTotal);
     attr_set = true;
   }
   const int tiles = P.num_tiles;
-  const int units = sm_count() / CG;  // CTAs (CG == 1) or CTA pairs (CG == 2) that fit on the device
-  const int grid = (tiles < units ? tiles : units) * CG;
-  FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, CG, P));
+  const int grid = (tiles < units ? tiles : units) * CG * MC;
+  FB_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kGemmThreads), S::kTotal, stream, CG * MC, P));
   return 0;
+}
+
+// (number of quads the device holds: for the tiling heuristic, before any launch)
+static int quad_units() {
+  static const int n = [] {
+    auto kern = f8_gemm_kernel<256, FLUXB200_EPI_PLAIN, 2, 2>;
+    using S = GemmSmem<256, 2>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) cudaGetLastError();
+    return max_active_clusters(kern, 4, S::kTotal);
+  }();
+  return n;
 }
 
 }  // namespace fb
@@ -667,6 +730,10 @@ namespace fb {
 
 // fluxb200_gemm_probe_mode: timing-probe bits OR-ed into every following launch of this process (0 = product behaviour)
 static int g_probe_mode = 0;
+// fluxb200_gemm_force_tiling: 0 = the heuristic below; otherwise the forced cta_group (1 | 2) / pairs per cluster (1 | 2).
+// Initialised from FLUXB200_GEMM_CG / FLUXB200_GEMM_MC.
+static int g_force_cg = [] { const char* e = getenv("FLUXB200_GEMM_CG"); return e ? atoi(e) : 0; }();
+static int g_force_mc = [] { const char* e = getenv("FLUXB200_GEMM_MC"); return e ? atoi(e) : 0; }();
 
 static int validate_gemm(const fluxb200_gemm_args& g) {
   FB_REQUIRE(g.a && g.w && g.a_scale_recip && g.w_scale_recip, "fluxb200_f8_gemm: null operand");
@@ -739,12 +806,23 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
   // 2-CTA tiling (256 x 256 per SM pair) when it fills most of the machine; FLUXB200_GEMM_CG=1|2 forces a form.
   int cg = 1;
   if (bn == 256 && g.N >= 256 && tiles256 >= (sm_count() / 2) * 3 / 4) cg = 2;
-  static const int forced_cg = [] {
-    const char* e = getenv("FLUXB200_GEMM_CG");
-    return e ? atoi(e) : 0;
-  }();
+  const int forced_cg = g_force_cg;
   if (forced_cg == 1) cg = 1;
   if (forced_cg == 2 && g.N >= 256 && (qkv || g.N % 256 == 0 || epi == FLUXB200_EPI_PLAIN)) { cg = 2; bn = 256; }
+
+  // Quad clusters (two pairs sharing the A rows by TMA multicast): fewer SMs (GPC packing) and coarser wave
+  // quantisation against 25 % less operand traffic.  FLUXB200_GEMM_MC=1|2 forces a form.
+  int mc = 1;
+  if (cg == 2 && ((g.N + bn - 1) / bn) % 2 == 0) {
+    const int forced_mc = g_force_mc;
+    const int pairs = sm_count() / 2, quads = quad_units();
+    const int64_t supers = tiles256 / 2;
+    const double eff_pair = static_cast<double>(tiles256) / (((tiles256 + pairs - 1) / pairs) * pairs);
+    const double eff_quad = static_cast<double>(supers) / (((supers + quads - 1) / quads) * quads) * (4.0 * quads) / sm_count();
+    // measured gain of the quad form at equal occupancy: kQuadGain (profiles/r2_gemm_quad.md)
+    constexpr double kQuadGain = 0.0;  // 0: the quad form is opt-in until its gain is measured
+    if (forced_mc == 2 || (forced_mc == 0 && eff_quad * kQuadGain > eff_pair * 1.03)) mc = 2;
+  }
 
   GemmParams P;
   static const int dbg = [] {
@@ -789,11 +867,11 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
     P.g[i] = gi;
     P.num_m_tiles[i] = (gi.M + kBM * cg - 1) / (kBM * cg);
     if (i < count) {
-      int rc = make_tmap_2d(&P.tmap_a[i], gi.a, 1, gi.M, gi.K, gi.K, kBM, kBK);
+      int rc = make_tmap_2d(&P.tmap_a[i], gi.a, 1, gi.M, gi.K, gi.K, kBM / mc, kBK);
       if (rc) return rc;
       rc = make_tmap_2d(&P.tmap_w[i], gi.w, 1, gi.N, gi.K, gi.K, bn / cg, kBK);
       if (rc) return rc;
-      const int t = P.num_m_tiles[i] * P.num_n_tiles;
+      const int t = P.num_m_tiles[i] * (P.num_n_tiles / mc);  // super tiles (mc N-adjacent tiles each)
       if (i == 0) P.tiles0 = t;
       P.num_tiles += t;
     } else {
@@ -804,7 +882,16 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
 
 #define FB_LAUNCH(BN_, EPI_) return launch_gemm<BN_, EPI_, 1>(P, stream)
 #define FB_LAUNCH2(EPI_) return launch_gemm<256, EPI_, 2>(P, stream)
-  if (cg == 2) {
+#define FB_LAUNCH4(EPI_) return launch_gemm<256, EPI_, 2, 2>(P, stream)
+  if (cg == 2 && mc == 2) {
+    switch (epi) {
+      case FLUXB200_EPI_PLAIN: FB_LAUNCH4(FLUXB200_EPI_PLAIN);
+      case FLUXB200_EPI_GATE_RESIDUAL: FB_LAUNCH4(FLUXB200_EPI_GATE_RESIDUAL);
+      case FLUXB200_EPI_GELU_QUANT: FB_LAUNCH4(FLUXB200_EPI_GELU_QUANT);
+      case FLUXB200_EPI_QKV_ROPE: FB_LAUNCH4(FLUXB200_EPI_QKV_ROPE);
+      case FLUXB200_EPI_LINEAR1: FB_LAUNCH4(FLUXB200_EPI_LINEAR1);
+    }
+  } else if (cg == 2) {
     switch (epi) {
       case FLUXB200_EPI_PLAIN: FB_LAUNCH2(FLUXB200_EPI_PLAIN);
       case FLUXB200_EPI_GATE_RESIDUAL: FB_LAUNCH2(FLUXB200_EPI_GATE_RESIDUAL);
@@ -829,6 +916,7 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
   }
 #undef FB_LAUNCH
 #undef FB_LAUNCH2
+#undef FB_LAUNCH4
   return set_error(FLUXB200_ERR_INVALID, "fluxb200_f8_gemm: no kernel for epilogue %d / BN %d", epi, bn);
 }
 
@@ -837,6 +925,14 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
 extern "C" int fluxb200_gemm_probe_mode(int mode) {
   FB_REQUIRE(mode >= 0 && mode < 16, "fluxb200_gemm_probe_mode: mode is a 4-bit mask");
   fb::g_probe_mode = mode;
+  return 0;
+}
+
+extern "C" int fluxb200_gemm_force_tiling(int cta_group, int pairs_per_cluster) {
+  FB_REQUIRE(cta_group >= 0 && cta_group <= 2 && pairs_per_cluster >= 0 && pairs_per_cluster <= 2,
+             "fluxb200_gemm_force_tiling: cta_group in {0,1,2}, pairs_per_cluster in {0,1,2}");
+  fb::g_force_cg = cta_group;
+  fb::g_force_mc = pairs_per_cluster;
   return 0;
 }
 

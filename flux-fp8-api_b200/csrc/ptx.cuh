@@ -236,6 +236,17 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap
       : "memory");
 }
 
+// 2-SM form with cluster multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each
+// destination signals the transaction bytes on the barrier (same offset) of ITS pair's leader CTA.
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+                                                   uint16_t cta_mask, uint64_t hint = kEvictNormal) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // thread-block clusters
 // ---------------------------------------------------------------------------------------------

@@ -40,6 +40,13 @@ def device_check() -> int:
     return n.value
 
 
+def gemm_force_tiling(cta_group: int = 0, pairs_per_cluster: int = 0) -> None:
+    """Measurement / test hook (fluxb200_gemm_force_tiling): (0, 0) restores the library's own choice."""
+    rc = cabi.load().fluxb200_gemm_force_tiling(cta_group, pairs_per_cluster)
+    if rc:
+        raise ValueError(cabi.load().fluxb200_last_error().decode())
+
+
 def quantize(x: Tensor, scale: Tensor, dtype: torch.dtype, out: Optional[Tensor] = None) -> Tensor:
     """F8Linear.to_fp8_saturated(...).to(fp8)  (reference float8_quantize.py:217-218, 274-276)."""
     cabi.require_cuda(x, scale)

@@ -254,6 +254,12 @@ int fluxb200_lora_fuse(const void* w_fp8, int w_fmt, const float* w_scale_recip,
  * runs on with it (roofline.peak), instead of inferring it from the bf16 figure. */
 int fluxb200_gemm_probe_mode(int mode);
 
+/* Tiling override for A/B measurements and tests (0, 0 = the library's own choice): cta_group 1 = one CTA per 128 x BN
+ * tile, 2 = one CTA pair per 256 x 256 tile; pairs_per_cluster 2 = two pairs per four-CTA cluster sharing their A rows
+ * by TMA multicast (needs cta_group 2 and an even number of N tiles; ignored otherwise).  Results are identical
+ * bit for bit across tilings (same MMA shapes and K order per output element). */
+int fluxb200_gemm_force_tiling(int cta_group, int pairs_per_cluster);
+
 /* Diagnostics: cycle counters of the last attention launch's CTA 0 (host pointer to 16 x uint64):
  * [0..5] softmax warp: wait-S, tmem load, max, exp, wait-O, store-P; [6] half-steps;
  * [8..10] MMA issuer: wait-P, wait-KV, issue.  Synchronises the device. */

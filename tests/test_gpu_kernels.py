@@ -337,3 +337,74 @@ def test_modulation_batched_bf16(ops, O, B):
             for a, b in zip(got, ref):
                 assert a.shape == b.shape
                 ulp_check(a, b, ulps=1, frac=0.05)
+
+
+@pytest.mark.parametrize("M,N,K", [(4608, 3072, 3072), (4096 + 512, 9216, 3072), (300, 1024, 256), (4608, 21504, 3072)])
+def test_gemm_tilings_agree(ops, O, M, N, K):
+    """One CTA per 128 x 256 tile, one CTA pair per 256 x 256 tile (cta_group::2), and two pairs per four-CTA cluster
+    sharing their A rows by TMA multicast compute the same function: every form against the oracle at 1 ulp, and
+    against each other bit for bit (same MMA K order per output element)."""
+    a, w = rand_fp8((M, K), E5M2, 4.0, 50), rand_fp8((N, K), E4M3, 1.0, 51)
+    g = gen(52)
+    bias = (torch.randn(N, device=DEV, generator=g) * 0.5).to(BF16)
+    resid = torch.randn(M, N, device=DEV, generator=g).to(BF16)
+    gate = torch.randn(1, N, device=DEV, generator=g).to(BF16)
+    sa, sw = scalar(1 / 64.0), scalar(1 / 32.0)
+    ref = O.scaled_mm(a, w, sa, sw, bias) if M * N * K < 1e11 else None
+    outs = {}
+    try:
+        for name, (cg, mc) in {"cta": (1, 1), "pair": (2, 1), "quad": (2, 2)}.items():
+            ops.gemm_force_tiling(cg, mc)
+            y = ops.f8_gemm(a, w, bias, sa, sw)
+            z = ops.f8_gemm_gate_residual(a, w, bias, sa, sw, resid, gate, M)
+            torch.cuda.synchronize()
+            outs[name] = (y, z)
+            if ref is not None:
+                ulp_check(y, ref)
+    finally:
+        ops.gemm_force_tiling(0, 0)
+    for name in ("pair", "quad"):
+        assert torch.equal(outs[name][0], outs["cta"][0]), name
+        assert torch.equal(outs[name][1], outs["cta"][1]), name
+
+
+def test_quad_tiling_in_the_fused_epilogues(ops, O):
+    """QKV+RMSNorm+RoPE / LINEAR1 / GELU-quant epilogues and a grouped (txt + img) launch under the quad tiling equal
+    the pair tiling bit for bit."""
+    from flux_fp8_api_b200.f8linear import mul_scale
+
+    B, L, T, H, K, mlp = 1, 1024, 256, 4, 512, 1024
+    S, D = L + T, H * 128
+    N = 3 * D + mlp
+    g = gen(60)
+    a_img, a_txt = rand_fp8((B * L, K), E5M2, 4.0, 61), rand_fp8((B * T, K), E5M2, 4.0, 62)
+    w = rand_fp8((N, K), E4M3, 0.5, 63)
+    bias = (torch.randn(N, device=DEV, generator=g) * 0.5).to(BF16)
+    qw = (1 + 0.05 * torch.randn(128, device=DEV, generator=g)).float()
+    kw = (1 + 0.05 * torch.randn(128, device=DEV, generator=g)).float()
+    ids = torch.cat((torch.zeros(1, T, 3), O.make_img_ids(1, 32, 32, torch.float32)), 1).to(BF16).to(DEV)
+    pe = O.embed_nd(ids, [16, 56, 56], 10000, BF16)
+    cos, sin = pe[:, 0, :, :, 0, 0].contiguous(), pe[:, 0, :, :, 1, 0].contiguous()
+    sa, sw, so = scalar(1 / 64.0), scalar(1 / 32.0), mul_scale(scalar(2048.0))
+    res = {}
+    try:
+        for name, (cg, mc) in {"pair": (2, 1), "quad": (2, 2)}.items():
+            ops.gemm_force_tiling(cg, mc)
+            q = torch.zeros(B, H, S, 128, dtype=BF16, device=DEV)
+            k, v = torch.zeros_like(q), torch.zeros_like(q)
+            cat8 = torch.zeros(B * S, D + mlp, dtype=E5M2, device=DEV)
+            group = []
+            # grouped launch: txt rows then img rows, each with the LINEAR1 epilogue writing into the joint buffers
+            ops.f8_gemm_qkv_rope(a_txt, w, bias, sa, sw, q, k, v, qw, kw, cos, sin, T, 0, mlp_out=cat8[:T], mlp_scale=so,
+                                 mlp_col_offset=D, defer=group)
+            ops.f8_gemm_qkv_rope(a_img, w, bias, sa, sw, q, k, v, qw, kw, cos, sin, L, T, mlp_out=cat8[T:], mlp_scale=so,
+                                 mlp_col_offset=D, defer=group)
+            ops.run_gemm_group(group)
+            h8 = ops.f8_gemm_gelu_quant(a_img, w[:2048].contiguous(), bias[:2048].contiguous(), sa, sw, so, E5M2)
+            torch.cuda.synchronize()
+            res[name] = (q, k, v, cat8, h8)
+    finally:
+        ops.gemm_force_tiling(0, 0)
+    for x, y in zip(res["pair"], res["quad"]):
+        assert torch.equal(x.view(torch.uint8) if x.dtype.itemsize == 1 else x, y.view(torch.uint8) if y.dtype.itemsize == 1 else y)
+    assert res["pair"][0].abs().sum() > 0

@@ -22,6 +22,12 @@ if has shapes; then
   python tools/step_shapes.py > gpurun_out/step_shapes.txt 2>&1; tail -14 gpurun_out/step_shapes.txt
   FLUXB200_GEMM_WIDE=0 python tools/step_shapes.py > gpurun_out/step_shapes_narrow.txt 2>&1; tail -14 gpurun_out/step_shapes_narrow.txt
 fi
+if has quad; then
+  FLUXB200_GEMM_MC=2 python tools/step_shapes.py > gpurun_out/step_shapes_quad.txt 2>&1; tail -14 gpurun_out/step_shapes_quad.txt
+fi
+if has ablate; then
+  python tools/ablate_step.py c2 > gpurun_out/ablate_c2.txt 2>&1; cat gpurun_out/ablate_c2.txt
+fi
 if has sdpa; then
   python tools/sdpa_compare.py > gpurun_out/sdpa_compare.txt 2>&1; cat gpurun_out/sdpa_compare.txt
 fi
