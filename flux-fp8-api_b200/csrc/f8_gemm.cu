@@ -488,10 +488,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
       const CUtensorMap* tm_a = &P.tmap_a[tc.pi];
       const CUtensorMap* tm_w = &P.tmap_w[tc.pi];
       for (int kb = 0; kb < P.num_k_blocks; ++kb) {
+        // probe mode 1: after the ring has been filled once no more TMA traffic; the leader just re-arms the barriers.
+        // The other CTAs of the cluster then have nothing to do and MUST NOT poll their slot barriers: decoupled from the
+        // data flow they could fall two phases behind the leader and wait for ever on an aliased parity.
+        const bool pretend = (P.debug & 1) && (phase != 0 || tile != tile0);
+        if (pretend && cta_rank != 0) {
+          if (++stage == S::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStage;
         if (elect_one()) {
-          if ((P.debug & 1) && (phase != 0 || tile != tile0)) {
+          if (pretend) {
             if (cta_rank == 0) mbar_arrive(&full_bar[stage]);  // pretend the data landed
           } else if constexpr (CG == 2) {
             // all bytes of the pair are accounted on the leader's barrier

@@ -33,8 +33,10 @@ if has sdpa; then
 fi
 if has ncu; then
   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-  ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/traffic.csv python tools/profile_step.py > gpurun_out/ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
-  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:f8_gemm_kernel -c 8 -o gpurun_out/prof_gemm -f python tools/profile_step.py > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
-  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:attention_kernel -c 2 -o gpurun_out/prof_attn -f python tools/profile_step.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
+  ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/traffic.csv python tools/profile_step.py > gpurun_out/ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
+  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:f8_gemm_kernel -c 4 -o gpurun_out/prof_gemm_double -f python tools/profile_step.py > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm double rc=$?"
+  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:f8_gemm_kernel --launch-skip 76 -c 2 -o gpurun_out/prof_gemm_single -f python tools/profile_step.py >> gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm single rc=$?"
+  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:attention_kernel -c 1 -o gpurun_out/prof_attn -f python tools/profile_step.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
+  ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:ln_mod_quant -c 2 -o gpurun_out/prof_ln -f python tools/profile_step.py > gpurun_out/ncu_ln.log 2>&1; echo "ncu ln rc=$?"
 fi
 ls -la gpurun_out | tail -30
