@@ -724,6 +724,7 @@ static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
   return 0;
 }
 
+#ifdef FLUXB200_GEMM_QUAD
 // (number of quads the device holds: for the tiling heuristic, before any launch)
 static int quad_units() {
   static const int n = [] {
@@ -734,6 +735,7 @@ static int quad_units() {
   }();
   return n;
 }
+#endif
 
 }  // namespace fb
 
@@ -821,19 +823,14 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
   if (forced_cg == 1) cg = 1;
   if (forced_cg == 2 && g.N >= 256 && (qkv || g.N % 256 == 0 || epi == FLUXB200_EPI_PLAIN)) { cg = 2; bn = 256; }
 
-  // Quad clusters (two pairs sharing the A rows by TMA multicast): fewer SMs (GPC packing) and coarser wave
-  // quantisation against 25 % less operand traffic.  FLUXB200_GEMM_MC=1|2 forces a form.
+  // Quad clusters (two pairs sharing the A rows by TMA multicast): 25 % less operand traffic, but four-CTA clusters
+  // reach only 132 of the 148 SMs and quantise waves more coarsely.  MEASURED (profiles/r2_gemm_quad.md): no gain on any
+  // shape of the step -- linear1 244 us either way, the N = 3072 GEMMs 15-20 % slower -- so the form is compiled only
+  // with -DFLUXB200_GEMM_QUAD (A/B builds, tests) and is never chosen automatically.
   int mc = 1;
-  if (cg == 2 && ((g.N + bn - 1) / bn) % 2 == 0) {
-    const int forced_mc = g_force_mc;
-    const int pairs = sm_count() / 2, quads = quad_units();
-    const int64_t supers = tiles256 / 2;
-    const double eff_pair = static_cast<double>(tiles256) / (((tiles256 + pairs - 1) / pairs) * pairs);
-    const double eff_quad = static_cast<double>(supers) / (((supers + quads - 1) / quads) * quads) * (4.0 * quads) / sm_count();
-    // measured gain of the quad form at equal occupancy: kQuadGain (profiles/r2_gemm_quad.md)
-    constexpr double kQuadGain = 0.0;  // 0: the quad form is opt-in until its gain is measured
-    if (forced_mc == 2 || (forced_mc == 0 && eff_quad * kQuadGain > eff_pair * 1.03)) mc = 2;
-  }
+#ifdef FLUXB200_GEMM_QUAD
+  if (cg == 2 && ((g.N + bn - 1) / bn) % 2 == 0 && g_force_mc == 2 && quad_units() > 0) mc = 2;
+#endif
 
   GemmParams P;
   static const int dbg = [] {
@@ -893,6 +890,7 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
 
 #define FB_LAUNCH(BN_, EPI_) return launch_gemm<BN_, EPI_, 1>(P, stream)
 #define FB_LAUNCH2(EPI_) return launch_gemm<256, EPI_, 2>(P, stream)
+#ifdef FLUXB200_GEMM_QUAD
 #define FB_LAUNCH4(EPI_) return launch_gemm<256, EPI_, 2, 2>(P, stream)
   if (cg == 2 && mc == 2) {
     switch (epi) {
@@ -902,7 +900,10 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
       case FLUXB200_EPI_QKV_ROPE: FB_LAUNCH4(FLUXB200_EPI_QKV_ROPE);
       case FLUXB200_EPI_LINEAR1: FB_LAUNCH4(FLUXB200_EPI_LINEAR1);
     }
-  } else if (cg == 2) {
+  }
+#undef FB_LAUNCH4
+#endif
+  if (cg == 2) {
     switch (epi) {
       case FLUXB200_EPI_PLAIN: FB_LAUNCH2(FLUXB200_EPI_PLAIN);
       case FLUXB200_EPI_GATE_RESIDUAL: FB_LAUNCH2(FLUXB200_EPI_GATE_RESIDUAL);
@@ -927,7 +928,6 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
   }
 #undef FB_LAUNCH
 #undef FB_LAUNCH2
-#undef FB_LAUNCH4
   return set_error(FLUXB200_ERR_INVALID, "fluxb200_f8_gemm: no kernel for epilogue %d / BN %d", epi, bn);
 }
 
@@ -942,6 +942,11 @@ extern "C" int fluxb200_gemm_probe_mode(int mode) {
 extern "C" int fluxb200_gemm_force_tiling(int cta_group, int pairs_per_cluster) {
   FB_REQUIRE(cta_group >= 0 && cta_group <= 2 && pairs_per_cluster >= 0 && pairs_per_cluster <= 2,
              "fluxb200_gemm_force_tiling: cta_group in {0,1,2}, pairs_per_cluster in {0,1,2}");
+#ifndef FLUXB200_GEMM_QUAD
+  if (pairs_per_cluster == 2)
+    return fb::set_error(FLUXB200_ERR_UNSUPPORTED, "fluxb200_gemm_force_tiling: the quad tiling is not built into this "
+                         "library (make EXTRA=-DFLUXB200_GEMM_QUAD)");
+#endif
   fb::g_force_cg = cta_group;
   fb::g_force_mc = pairs_per_cluster;
   return 0;

@@ -43,6 +43,8 @@ def device_check() -> int:
 def gemm_force_tiling(cta_group: int = 0, pairs_per_cluster: int = 0) -> None:
     """Measurement / test hook (fluxb200_gemm_force_tiling): (0, 0) restores the library's own choice."""
     rc = cabi.load().fluxb200_gemm_force_tiling(cta_group, pairs_per_cluster)
+    if rc == cabi.ERR_UNSUPPORTED:
+        raise NotImplementedError(cabi.load().fluxb200_last_error().decode())
     if rc:
         raise ValueError(cabi.load().fluxb200_last_error().decode())
 

@@ -354,7 +354,10 @@ def test_gemm_tilings_agree(ops, O, M, N, K):
     outs = {}
     try:
         for name, (cg, mc) in {"cta": (1, 1), "pair": (2, 1), "quad": (2, 2)}.items():
-            ops.gemm_force_tiling(cg, mc)
+            try:
+                ops.gemm_force_tiling(cg, mc)
+            except NotImplementedError:  # the quad form exists only in -DFLUXB200_GEMM_QUAD builds (measured: no gain)
+                continue
             y = ops.f8_gemm(a, w, bias, sa, sw)
             z = ops.f8_gemm_gate_residual(a, w, bias, sa, sw, resid, gate, M)
             torch.cuda.synchronize()
@@ -363,7 +366,7 @@ def test_gemm_tilings_agree(ops, O, M, N, K):
                 ulp_check(y, ref)
     finally:
         ops.gemm_force_tiling(0, 0)
-    for name in ("pair", "quad"):
+    for name in set(outs) - {"cta"}:
         assert torch.equal(outs[name][0], outs["cta"][0]), name
         assert torch.equal(outs[name][1], outs["cta"][1]), name
 
@@ -387,6 +390,10 @@ def test_quad_tiling_in_the_fused_epilogues(ops, O):
     cos, sin = pe[:, 0, :, :, 0, 0].contiguous(), pe[:, 0, :, :, 1, 0].contiguous()
     sa, sw, so = scalar(1 / 64.0), scalar(1 / 32.0), mul_scale(scalar(2048.0))
     res = {}
+    try:
+        ops.gemm_force_tiling(2, 2)
+    except NotImplementedError:
+        pytest.skip("quad tiling not built into this library (-DFLUXB200_GEMM_QUAD); passed in the round-2 A/B build")
     try:
         for name, (cg, mc) in {"pair": (2, 1), "quad": (2, 2)}.items():
             ops.gemm_force_tiling(cg, mc)
