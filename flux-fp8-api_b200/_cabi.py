@@ -29,6 +29,7 @@ EXPORTS = (
     "fluxb200_amax",
     "fluxb200_f8_gemm",
     "fluxb200_f8_gemm_grouped",
+    "fluxb200_f8_gemm_ln",
     "fluxb200_f8_gemv",
     "fluxb200_modulation_batched",
     "fluxb200_modulation_batched_bf16",
@@ -168,6 +169,8 @@ def load() -> C.CDLL:
     lib.fluxb200_amax.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.fluxb200_f8_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.fluxb200_f8_gemm_grouped.argtypes = [C.POINTER(GemmArgs), C.c_int, C.c_void_p]
+    lib.fluxb200_f8_gemm_ln.argtypes = [C.POINTER(GemmArgs), C.c_int, C.POINTER(LnArgs), C.c_int, C.c_int, C.c_int,
+                                        C.c_float, C.c_void_p, C.c_void_p]
     lib.fluxb200_f8_gemv.argtypes = [
         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_int, C.c_int, C.c_int, C.c_void_p,

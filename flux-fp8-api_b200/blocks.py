@@ -401,16 +401,19 @@ class DoubleStreamBlock(nn.Module):
         # grouped launch (the txt problem alone, M = 512 per sample, would leave most SMs idle).
         streams = ((txt, txt_mod1, txt_mod2, self.txt_attn, self.txt_mlp, T, 0),
                    (img, img_mod1, img_mod2, self.img_attn, self.img_mlp, L, T))
-        group = []
-        a8s = self._ln_pair([(x, mod1, attn.qkv) for x, mod1, _, attn, _, _, _ in streams])
+        def qkv_gemms(a8s):
+            group = []
+            for (x, mod1, _, attn, _, rows, off), a8 in zip(streams, a8s):
+                lin = attn.qkv
+                ops.f8_gemm_qkv_rope(a8.view(-1, D), lin.float8_data, lin.bias, lin.input_scale_reciprocal,
+                                     lin.scale_reciprocal, q, k, v, attn.norm.query_norm.weight_fp32(),
+                                     attn.norm.key_norm.weight_fp32(), cos, sin, rows_per_batch=rows, seq_offset=off,
+                                     defer=group)
+            return group
+
+        # LN1 -> modulate -> quantise -> QKV GEMM (+ QK-RMSNorm + RoPE epilogue) of both streams: one launch
+        a8s = self._ln_then_gemms([(x, mod1, attn.qkv) for x, mod1, _, attn, _, _, _ in streams], qkv_gemms)
         _tap("txt_attn.qkv", a8s[0]), _tap("img_attn.qkv", a8s[1])
-        for (x, mod1, _, attn, _, rows, off), a8 in zip(streams, a8s):
-            lin = attn.qkv
-            ops.f8_gemm_qkv_rope(a8.view(-1, D), lin.float8_data, lin.bias, lin.input_scale_reciprocal,
-                                 lin.scale_reciprocal, q, k, v, attn.norm.query_norm.weight_fp32(),
-                                 attn.norm.key_norm.weight_fp32(), cos, sin, rows_per_batch=rows, seq_offset=off,
-                                 defer=group)
-        self._launch(group)
 
         tp, ip = self.txt_attn.proj, self.img_attn.proj
         if tp.input_float8_dtype != ip.input_float8_dtype:
@@ -429,14 +432,20 @@ class DoubleStreamBlock(nn.Module):
                                                 proj.scale_reciprocal, x.view(-1, D), _gate2d(mod1.gate), rows,
                                                 defer=group))
         self._launch(group)
-        # x = x + gate2 * mlp((1 + scale2) * LN(x) + shift2)
-        hs, group = [], []
-        m8s = self._ln_pair([(y.view(B, rows, D), mod2, mlp[0]) for (_, _, mod2, _, mlp, rows, _), y in zip(streams, ys)])
-        for (x, _, mod2, _, mlp, rows, _), y, m8 in zip(streams, ys, m8s):
-            up, down = mlp[0], mlp[2]
-            hs.append(ops.f8_gemm_gelu_quant(m8.view(-1, D), up.float8_data, up.bias, up.input_scale_reciprocal,
-                                             up.scale_reciprocal, down.qscale, down.input_float8_dtype, defer=group))
-        self._launch(group)
+        # x = x + gate2 * mlp((1 + scale2) * LN(x) + shift2): LN2 -> modulate -> quantise -> MLP-up GEMM (GELU + quantise
+        # epilogue) of both streams in one launch, then the MLP-down GEMMs
+        hs = []
+
+        def up_gemms(m8s):
+            group = []
+            for (x, _, mod2, _, mlp, rows, _), m8 in zip(streams, m8s):
+                up, down = mlp[0], mlp[2]
+                hs.append(ops.f8_gemm_gelu_quant(m8.view(-1, D), up.float8_data, up.bias, up.input_scale_reciprocal,
+                                                 up.scale_reciprocal, down.qscale, down.input_float8_dtype, defer=group))
+            return group
+
+        m8s = self._ln_then_gemms([(y.view(B, rows, D), mod2, mlp[0])
+                                   for (_, _, mod2, _, mlp, rows, _), y in zip(streams, ys)], up_gemms)
         _tap("txt_mlp.0", m8s[0]), _tap("img_mlp.0", m8s[1]), _tap("txt_mlp.2", hs[0]), _tap("img_mlp.2", hs[1])
         group = []
         for (x, _, mod2, _, mlp, rows, _), y, h8 in zip(streams, ys, hs):
@@ -446,6 +455,19 @@ class DoubleStreamBlock(nn.Module):
         self._launch(group)
         txt_out, img_out = ys[0].view(B, T, D), ys[1].view(B, L, D)
         return img_out, txt_out
+
+    @staticmethod
+    def _ln_then_gemms(items, build_gemms):
+        """LN -> modulate -> quantise of the txt and img rows followed by the GEMMs that consume them.  When both
+        consumers take the same fp8 input format everything goes out as ONE launch (ops.ln_gemm_group: the LayerNorm
+        is a prologue phase of the persistent GEMM grid); else one LN launch per stream, then the GEMMs."""
+        (x0, m0, l0), (x1, m1, l1) = items
+        if l0.input_float8_dtype == l1.input_float8_dtype:
+            return ops.ln_gemm_group([(x0, m0.shift, m0.scale, l0.qscale), (x1, m1.shift, m1.scale, l1.qscale)],
+                                     l0.input_float8_dtype, build_gemms)
+        a8s = [ops.ln_mod_quant(x, m.shift, m.scale, l.qscale, l.input_float8_dtype)[0] for x, m, l in items]
+        DoubleStreamBlock._launch(build_gemms(a8s))
+        return a8s
 
     @staticmethod
     def _ln_pair(items):
@@ -539,15 +561,21 @@ class SingleStreamBlock(nn.Module):
         x = x.contiguous()
         cos, sin = rope if rope is not None else rope_cos_sin(pe)
         dev = x.device
-        a8, _ = ops.ln_mod_quant(x, mod.shift, mod.scale, l1.qscale, l1.input_float8_dtype)
         q = torch.empty((B, H, S, HEAD_DIM), dtype=BF16, device=dev)
         k, v = torch.empty_like(q), torch.empty_like(q)
         # linear2's input = [attention | gelu(mlp)] is assembled in fp8 by the two producers
         cat8 = torch.empty((B, S, D + self.mlp_hidden_dim), dtype=l2.input_float8_dtype, device=dev)
-        ops.f8_gemm_qkv_rope(a8.view(-1, D), l1.float8_data, l1.bias, l1.input_scale_reciprocal, l1.scale_reciprocal,
-                             q, k, v, self.norm.query_norm.weight_fp32(), self.norm.key_norm.weight_fp32(), cos, sin,
-                             rows_per_batch=S, seq_offset=0, mlp_out=cat8.view(B * S, -1), mlp_scale=l2.qscale,
-                             mlp_col_offset=D)
+
+        def linear1_gemm(a8s):
+            group = []
+            ops.f8_gemm_qkv_rope(a8s[0].view(-1, D), l1.float8_data, l1.bias, l1.input_scale_reciprocal,
+                                 l1.scale_reciprocal, q, k, v, self.norm.query_norm.weight_fp32(),
+                                 self.norm.key_norm.weight_fp32(), cos, sin, rows_per_batch=S, seq_offset=0,
+                                 mlp_out=cat8.view(B * S, -1), mlp_scale=l2.qscale, mlp_col_offset=D, defer=group)
+            return group
+
+        # pre_norm -> modulate -> quantise -> linear1 (QKV + RMSNorm + RoPE | GELU + quantise epilogues): one launch
+        (a8,) = ops.ln_gemm_group([(x, mod.shift, mod.scale, l1.qscale)], l1.input_float8_dtype, linear1_gemm)
         ops.attention(q, k, v, out=cat8[..., :D], out_scale0=l2.qscale, split_row=0)
         _tap("linear1", a8), _tap("linear2", cat8)
         out = ops.f8_gemm_gate_residual(cat8.view(B * S, -1), l2.float8_data, l2.bias, l2.input_scale_reciprocal,

@@ -32,6 +32,7 @@
 
 #include "flux_b200.h"
 #include "host_util.h"
+#include "ln_row.cuh"
 #include "ptx.cuh"
 
 namespace fb {
@@ -81,6 +82,11 @@ struct GemmParams {
   int debug;
   // 1: every epilogue row segment (out / resid / q,k,v) is 32-byte aligned -> 256-bit global loads / stores
   int wide;
+  // Fused LayerNorm-modulate-quantise prologue (fluxb200_f8_gemm_ln): when grid_bar != nullptr every warp of the grid
+  // first turns rows of ln.seg[*].x into the fp8 A operand(s) of this launch, the grid synchronises, then the GEMM runs.
+  LnParams ln;
+  int ln_fmt;
+  unsigned int* grid_bar;
 };
 
 struct TileCoord {
@@ -400,7 +406,7 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
 
 // ---- the kernel -------------------------------------------------------------------------------------
 
-template <int BN, int EPI, int CG, int MC = 1>
+template <int BN, int EPI, int CG, int MC = 1, bool LN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_constant__ GemmParams P) {
   using S = GemmSmem<BN, CG>;
   static_assert(CG == 1 || BN == 256, "the 2-CTA tiling is 256 x 256");
@@ -467,6 +473,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   // PDL: everything above overlapped the previous kernel's tail; from here on we touch its outputs.  This grid is
   // one persistent wave, so the next kernel may be scheduled as soon as our CTAs start retiring.
   pdl_wait();
+  if constexpr (LN) {
+    // ---- phase 0: LayerNorm -> (1 + scale) x + shift -> fp8, one warp per row, every warp of the grid ----
+    // (modules/flux_model.py:367-368 / 374-375 / 389 / 395 / 469-470 + the consuming F8Linear's input quantisation).
+    // Removes a kernel boundary per LayerNorm: measured in the captured step a stand-alone LN launch between two
+    // persistent GEMMs costs ~45 us (its own ~10 us plus the drain / refill of 148 SMs on either side).
+    constexpr int kWarps = kGemmThreads / 32;
+    const int rows0 = P.ln.seg[0].rows, rows = rows0 + P.ln.seg[1].rows;
+    for (int r = blockIdx.x * kWarps + warp; r < rows; r += gridDim.x * kWarps) {
+      const bool second = r >= rows0;
+      const LnSeg& G = second ? P.ln.seg[1] : P.ln.seg[0];
+      if (P.ln_fmt == FLUXB200_E5M2) ln_mod_quant_row<1, 12>(G, r - (second ? rows0 : 0), P.ln.D, P.ln.eps, lane);
+      else ln_mod_quant_row<0, 12>(G, r - (second ? rows0 : 0), P.ln.D, P.ln.eps, lane);
+    }
+    // the A rows were written through the generic proxy and are read back by TMA (async proxy) on other SMs
+    fence_proxy_async_global();
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) grid_barrier(P.grid_bar, gridDim.x);
+    __syncthreads();
+    fence_proxy_async_global();
+  }
   pdl_launch_dependents();
 
   const int num_tiles = P.num_tiles;
@@ -707,12 +734,12 @@ static int max_active_clusters(K kern, int cluster_ctas, size_t smem) {
   return n;
 }
 
-template <int BN, int EPI, int CG, int MC = 1>
+template <int BN, int EPI, int CG, int MC = 1, bool LN = false>
 static int launch_gemm(const GemmParams& P, cudaStream_t stream) {
   using S = GemmSmem<BN, CG>;
   static bool attr_set = false;
   static int units = 0;  // CTAs (CG == 1), pairs (CG == 2) or quads (MC == 2) that fit on the device
-  auto kern = f8_gemm_kernel<BN, EPI, CG, MC>;
+  auto kern = f8_gemm_kernel<BN, EPI, CG, MC, LN>;
   if (!attr_set) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     units = MC == 1 ? sm_count() / CG : max_active_clusters(kern, CG * MC, S::kTotal);
@@ -794,7 +821,14 @@ static int validate_gemm(const fluxb200_gemm_args& g) {
   return 0;
 }
 
-static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_t stream) {
+struct LnFuse {
+  const fluxb200_ln_args* ln;
+  int count, fmt, D;
+  float eps;
+  unsigned int* ws;
+};
+
+static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_t stream, const LnFuse* lnf = nullptr) {
   FB_REQUIRE(args != nullptr && (count == 1 || count == 2), "fluxb200_f8_gemm: args NULL or count not in {1,2}");
   for (int i = 0; i < count; ++i) {
     int rc = validate_gemm(args[i]);
@@ -838,6 +872,25 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
     return e ? atoi(e) : 0;
   }();
   P.debug = dbg | g_probe_mode;
+  P.grid_bar = nullptr;
+  P.ln_fmt = 0;
+  P.ln = LnParams{};
+  if (lnf != nullptr) {
+    for (int i = 0; i < lnf->count; ++i) {
+      const fluxb200_ln_args& a = lnf->ln[i];
+      P.ln.seg[i] = LnSeg{static_cast<const __nv_bfloat16*>(a.x), static_cast<const __nv_bfloat16*>(a.shift),
+                          static_cast<const __nv_bfloat16*>(a.scale), static_cast<uint8_t*>(a.y_fp8), nullptr, a.in_scale,
+                          a.ldx, a.ldy, 0, a.mod_batch_stride, a.B * a.L, a.L};
+    }
+    if (lnf->count == 1) {
+      P.ln.seg[1] = P.ln.seg[0];
+      P.ln.seg[1].rows = 0;
+    }
+    P.ln.D = lnf->D;
+    P.ln.eps = lnf->eps;
+    P.ln_fmt = lnf->fmt;
+    P.grid_bar = lnf->ws;
+  }
   P.num_n_tiles = (g.N + bn - 1) / bn;
   P.q_n_tiles = 0;
   {
@@ -903,6 +956,19 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
   }
 #undef FB_LAUNCH4
 #endif
+  if (lnf != nullptr) {
+    // the fused LayerNorm prologue exists for the pair tiling and the epilogues that consume a LayerNorm in the model
+    if (cg == 2 && mc == 1) {
+      switch (epi) {
+        case FLUXB200_EPI_GELU_QUANT: return launch_gemm<256, FLUXB200_EPI_GELU_QUANT, 2, 1, true>(P, stream);
+        case FLUXB200_EPI_QKV_ROPE: return launch_gemm<256, FLUXB200_EPI_QKV_ROPE, 2, 1, true>(P, stream);
+        case FLUXB200_EPI_LINEAR1: return launch_gemm<256, FLUXB200_EPI_LINEAR1, 2, 1, true>(P, stream);
+        default: break;
+      }
+    }
+    return set_error(FLUXB200_ERR_UNSUPPORTED, "fluxb200_f8_gemm_ln: no fused LayerNorm kernel for epilogue %d with this "
+                     "problem size (cta_group %d); use fluxb200_ln_mod_quant_grouped + fluxb200_f8_gemm_grouped", epi, cg);
+  }
   if (cg == 2) {
     switch (epi) {
       case FLUXB200_EPI_PLAIN: FB_LAUNCH2(FLUXB200_EPI_PLAIN);
@@ -958,4 +1024,25 @@ extern "C" int fluxb200_f8_gemm(const fluxb200_gemm_args* args, fluxb200_stream_
 
 extern "C" int fluxb200_f8_gemm_grouped(const fluxb200_gemm_args* args, int count, fluxb200_stream_t stream_) {
   return fb::run_gemm_group(args, count, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int fluxb200_f8_gemm_ln(const fluxb200_gemm_args* args, int count, const fluxb200_ln_args* ln, int ln_count,
+                                   int fmt, int D, float eps, void* grid_barrier_ws, fluxb200_stream_t stream_) {
+  using namespace fb;
+  FB_REQUIRE(ln != nullptr && (ln_count == 1 || ln_count == 2), "fluxb200_f8_gemm_ln: 1 or 2 LayerNorm row sets");
+  FB_REQUIRE(fmt == 0 || fmt == 1, "fluxb200_f8_gemm_ln: bad fp8 format %d", fmt);
+  FB_REQUIRE(grid_barrier_ws != nullptr && (reinterpret_cast<uintptr_t>(grid_barrier_ws) & 7) == 0,
+             "fluxb200_f8_gemm_ln: grid_barrier_ws must point to two zero-initialised 32-bit words (8-byte aligned)");
+  if (D != 3072)
+    return set_error(FLUXB200_ERR_UNSUPPORTED, "fluxb200_f8_gemm_ln: the fused prologue is built for D = 3072 (got %d); "
+                     "use fluxb200_ln_mod_quant_grouped + fluxb200_f8_gemm_grouped", D);
+  for (int i = 0; i < ln_count; ++i) {
+    const fluxb200_ln_args& a = ln[i];
+    FB_REQUIRE(a.x && a.shift && a.scale && a.y_fp8 && a.in_scale && a.B > 0 && a.L > 0,
+               "fluxb200_f8_gemm_ln: bad row set %d", i);
+    FB_REQUIRE(a.ldx % 8 == 0 && a.mod_batch_stride % 8 == 0 && a.ldy % 8 == 0,
+               "fluxb200_f8_gemm_ln: strides must keep 16-byte (bf16) / 8-byte (fp8) alignment");
+  }
+  LnFuse f{ln, ln_count, fmt, D, eps, static_cast<unsigned int*>(grid_barrier_ws)};
+  return run_gemm_group(args, count, reinterpret_cast<cudaStream_t>(stream_), &f);
 }

@@ -157,6 +157,44 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05.mma reads)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_global() {
+  // generic-proxy accesses to global memory <-> async-proxy (TMA) accesses to the same locations
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// Grid-wide barrier for a grid whose CTAs are all co-resident (persistent kernels: <= 1 CTA per SM, grid <= #SMs).
+// `ws` points to two zero-initialised 32-bit words (arrive counter, generation) that only kernels of ONE stream use:
+// launches never overlap inside the barrier (it sits behind griddepcontrol.wait), the last arriver re-arms the
+// counter, so the words need no host-side reset between launches or CUDA-graph replays.  One thread per CTA calls it.
+__device__ __forceinline__ void grid_barrier(unsigned int* ws, unsigned int num_ctas) {
+  unsigned int g0;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g0) : "l"(ws + 1) : "memory");
+  __threadfence();
+  const unsigned int old = atomicAdd(ws, 1u);
+  if (old == num_ctas - 1) {
+    atomicExch(ws, 0u);
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ws + 1) : "memory");
+  } else {
+    unsigned int g = g0;
+#if FLUXB200_HANG_TRAP_NS
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+#endif
+    while (g == g0) {
+      __nanosleep(64);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(ws + 1) : "memory");
+#if FLUXB200_HANG_TRAP_NS
+      if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > FLUXB200_HANG_TRAP_NS) {
+        printf("fluxb200: grid barrier timed out (block %d of %u)\n", blockIdx.x, num_ctas);
+        __trap();
+      }
+#endif
+    }
+  }
+  __threadfence();
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -140,20 +140,19 @@ def ln_mod_quant(x: Tensor, shift: Tensor, scale: Tensor, in_scale: Optional[Ten
     return yq, yb
 
 
-def ln_mod_quant_pair(items, dtype: torch.dtype, eps: float = 1e-6):
-    """Two independent LN-modulate-quantise problems (the txt and img streams of a DoubleStreamBlock) in ONE launch.
-    items: [(x [B,L,D], shift, scale, in_scale)] * 2 with the same D; returns the two fp8 tensors."""
+def _ln_args(items, dtype: torch.dtype):
+    """fluxb200_ln_args array + freshly allocated fp8 outputs for 1 or 2 (x [B,L,D], shift, scale, in_scale) row sets."""
     args = (cabi.LnArgs * len(items))()
     outs, keep = [], []
     D = items[0][0].shape[-1]
     total = 0.0
     for i, (x, shift, scale, in_scale) in enumerate(items):
         cabi.require_cuda(x, shift, scale, in_scale)
-        _want(x, BF16, "ln_mod_quant_pair: x"), _want(shift, BF16, "ln_mod_quant_pair: shift")
-        _want(scale, BF16, "ln_mod_quant_pair: scale"), _want(in_scale, torch.float32, "ln_mod_quant_pair: in_scale")
+        _want(x, BF16, "ln_mod_quant: x"), _want(shift, BF16, "ln_mod_quant: shift")
+        _want(scale, BF16, "ln_mod_quant: scale"), _want(in_scale, torch.float32, "ln_mod_quant: in_scale")
         B, L, Dx = x.shape
         if Dx != D:
-            raise ValueError("ln_mod_quant_pair: both streams must share the hidden size")
+            raise ValueError("ln_mod_quant: the row sets must share the hidden size")
         if x.stride(-1) != 1 or x.stride(0) != L * x.stride(1):
             x = x.contiguous()
         sh = shift.reshape(B, D) if shift.dim() == 3 else shift
@@ -165,12 +164,82 @@ def ln_mod_quant_pair(items, dtype: torch.dtype, eps: float = 1e-6):
         a.x, a.shift, a.scale, a.y_fp8, a.in_scale = x.data_ptr(), sh.data_ptr(), sc.data_ptr(), yq.data_ptr(), in_scale.data_ptr()
         a.ldx, a.ldy, a.mod_batch_stride, a.B, a.L = x.stride(1), D, (sh.stride(0) if B > 1 else D), B, L
         outs.append(yq)
-        keep += [x, sh, sc]
+        keep += [x, sh, sc, in_scale]
         total += B * L * D * 3.0
+    return args, outs, keep, D, total
+
+
+def ln_mod_quant_pair(items, dtype: torch.dtype, eps: float = 1e-6):
+    """Two independent LN-modulate-quantise problems (the txt and img streams of a DoubleStreamBlock) in ONE launch.
+    items: [(x [B,L,D], shift, scale, in_scale)] * 2 with the same D; returns the two fp8 tensors."""
+    args, outs, keep, D, total = _ln_args(items, dtype)
     _timed("ln_mod_quant", total,
            lambda: cabi.check(cabi.load().fluxb200_ln_mod_quant_grouped(args, len(items), cabi.fp8_fmt(dtype), D, eps,
                                                                         cabi.stream_ptr()),
                               "fluxb200_ln_mod_quant_grouped"))
+    return outs
+
+
+_grid_barrier_ws = {}
+
+
+def grid_barrier_ws(device) -> Tensor:
+    """The two self-re-arming words of the fused LN -> GEMM launches' grid barrier: one pair per (device, stream) --
+    launches that share a pair must be stream-ordered (include/flux_b200.h, fluxb200_f8_gemm_ln)."""
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _grid_barrier_ws.get(key)
+    if ws is None:
+        with torch.cuda.stream(torch.cuda.default_stream(device)):
+            ws = torch.zeros(2, dtype=torch.int32, device=device)
+        torch.cuda.default_stream(device).synchronize()
+        _grid_barrier_ws[key] = ws
+    return ws
+
+
+#: (epilogue, N, K, tuple of M) -> False once the library answered FLUXB200_ERR_UNSUPPORTED for that fused launch
+_ln_fused_unsupported = set()
+#: set False to always run LayerNorm-modulate-quantise as its own launch (A/B measurements)
+FUSE_LN_INTO_GEMM = True
+
+
+def ln_gemm_group(items, dtype: torch.dtype, build_gemms, eps: float = 1e-6):
+    """LayerNorm-modulate-quantise of 1-2 row sets + the GEMM(s) that consume them, as ONE launch when the library has a
+    fused kernel for the shape (fluxb200_f8_gemm_ln), else as the two grouped launches.  `build_gemms(a8s)` receives
+    the fp8 A tensors ([B,L,D] each) and returns the list of deferred GemmArgs (ops.f8_gemm_*(..., defer=list))."""
+    args, outs, keep, D, total = _ln_args(items, dtype)
+    gs = list(build_gemms(outs))
+    key = (gs[0].epilogue, gs[0].N, gs[0].K, tuple(g.M for g in gs))
+    same = all(g.N == gs[0].N and g.K == gs[0].K and g.a_fmt == gs[0].a_fmt and g.w_fmt == gs[0].w_fmt and
+               g.out_fmt == gs[0].out_fmt for g in gs)
+    if FUSE_LN_INTO_GEMM and same and D == 3072 and key not in _ln_fused_unsupported:
+        arr = (cabi.GemmArgs * len(gs))(*gs)
+        ws = grid_barrier_ws(items[0][0].device)
+        done = []
+
+        def launch():
+            rc = cabi.load().fluxb200_f8_gemm_ln(arr, len(gs), args, len(items), cabi.fp8_fmt(dtype), D, eps,
+                                                 ws.data_ptr(), cabi.stream_ptr())
+            if rc == cabi.ERR_UNSUPPORTED:
+                return
+            cabi.check(rc, "fluxb200_f8_gemm_ln")
+            done.append(True)
+
+        _timed("f8_gemm", sum(2.0 * g.M * g.N * g.K for g in gs), launch,
+               "ln+" + _gemm_detail(gs) if KERNEL_TIMELINE is not None else "")
+        if done:
+            return outs
+        _ln_fused_unsupported.add(key)
+        if KERNEL_TIMELINE is not None and KERNEL_TIMELINE:
+            KERNEL_TIMELINE.pop()  # the refused call launched nothing
+    _timed("ln_mod_quant", total,
+           lambda: cabi.check(cabi.load().fluxb200_ln_mod_quant_grouped(args, len(items), cabi.fp8_fmt(dtype), D, eps,
+                                                                        cabi.stream_ptr()),
+                              "fluxb200_ln_mod_quant_grouped"))
+    if same and len(gs) > 1:
+        run_gemm_group(gs)
+    else:
+        for g in gs:
+            run_gemm(g)
     return outs
 
 

@@ -192,6 +192,17 @@ typedef struct fluxb200_ln_args {
 int fluxb200_ln_mod_quant_grouped(const fluxb200_ln_args* args, int count, int fmt, int D, float eps,
                                   fluxb200_stream_t stream);
 
+/* LayerNorm-modulate-quantise FUSED INTO THE CONSUMING GEMM LAUNCH (modules/flux_model.py:367-371, 374-378, 389-390,
+ * 395-396, 469-471): every warp of the persistent GEMM grid first turns rows of ln[i].x into ln[i].y_fp8 -- which
+ * must be the A operand(s) of `args` -- exactly as fluxb200_ln_mod_quant_grouped would, the grid synchronises, and the
+ * GEMM(s) of fluxb200_f8_gemm_grouped run.  One launch instead of two: in the captured step a stand-alone LayerNorm
+ * kernel between two persistent GEMMs costs ~45 us (drain and refill of every SM on both sides), four times its own
+ * run time.  D must be 3072 (FLUXB200_ERR_UNSUPPORTED otherwise: use the two separate calls).
+ * grid_barrier_ws: two 32-bit words in device memory, zeroed ONCE by the caller and then only ever passed to this
+ * entry point on launches of one stream (the kernels re-arm it themselves; CUDA-graph replays need no reset). */
+int fluxb200_f8_gemm_ln(const fluxb200_gemm_args* args, int count, const fluxb200_ln_args* ln, int ln_count, int fmt,
+                        int D, float eps, void* grid_barrier_ws, fluxb200_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stand-alone QKNorm + apply_rope on [B,H,S,128] tensors (modules/flux_model.py:164, 60-65).
  * norm_w may be NULL (skip RMSNorm); cos/sin may be NULL (skip RoPE).  In-place allowed.

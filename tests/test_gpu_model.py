@@ -361,3 +361,40 @@ def test_baseline_configs_full_width(lib, name, res, text_len, guidance, qmod, b
         sess_g = PL.DenoiseSession(net, req, use_graph=True)
         sess_e = PL.DenoiseSession(net, req, use_graph=False)
         assert torch.equal(sess_g.step_device(req["img"], sched[0], sched[1]), sess_e.step_device(req["img"], sched[0], sched[1]))
+
+
+@pytest.mark.parametrize("res,batch", [(1024, 1), (512, 3)])
+def test_layernorm_fused_into_the_gemm_launch_is_bit_identical(lib, res, batch):
+    """fluxb200_f8_gemm_ln (LayerNorm-modulate-quantise as a prologue phase of the persistent GEMM grid + a grid barrier)
+    against the two separate launches: same fp8 operands, same outputs, three launches fewer per double + single block;
+    repeated calls and CUDA-graph replays re-use the self-re-arming barrier words."""
+    from flux_fp8_api_b200 import _cabi, model as M, ops, pipeline as PL
+
+    params = M.FluxParams(depth=1, depth_single_blocks=1)
+    net = PL.build_synthetic_flux(M.FluxSpec(params=params), DEV, seed=11)
+    req = PL.synthetic_request(params, res, res, batch, 512, DEV, seed=5)
+    PL.calibrate(net, req, num_steps=13)
+    t = torch.full((batch,), 0.6, dtype=BF16, device=DEV)
+    call = dict(img=req["img"], img_ids=req["img_ids"], txt=req["txt"], txt_ids=req["txt_ids"], timesteps=t, y=req["y"],
+                guidance=req["guidance"])
+    try:
+        with torch.inference_mode():
+            ops.FUSE_LN_INTO_GEMM = False
+            n0 = _cabi.LAUNCHES
+            y_sep = net(**call)
+            n_sep = _cabi.LAUNCHES - n0
+            ops.FUSE_LN_INTO_GEMM = True
+            n0 = _cabi.LAUNCHES
+            y_fused = net(**call)
+            n_fused = _cabi.LAUNCHES - n0
+            assert n_fused == n_sep - 3, (n_sep, n_fused)
+            assert torch.equal(y_fused, y_sep)
+            for _ in range(5):
+                assert torch.equal(net(**call), y_sep)
+        sched = PL.get_schedule(4, req["img"].shape[1])
+        g = PL.DenoiseSession(net, req, use_graph=True)
+        e = PL.DenoiseSession(net, req, use_graph=False)
+        for i in range(3):
+            assert torch.equal(g.step_device(req["img"], sched[i], sched[i + 1]), e.step_device(req["img"], sched[i], sched[i + 1]))
+    finally:
+        ops.FUSE_LN_INTO_GEMM = True
