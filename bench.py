@@ -20,7 +20,7 @@ One JSON line on stdout (rank 0):
   value         sample-steps/s over all GPUs, latents resident in HBM (CUDA-graph replay per step)
   e2e           the same through DenoiseSession.step_host (pinned host latents, H2D + step + D2H per step)
   roofline      tcgen05 FP8 GEMM kernels: algorithmic FLOP/s from CUDA events around every launch of an instrumented
-                pass, against the FP8 tensor-pipe ceiling MEASURED on this box in the same run (fluxb200_gemm_probe_mode)
+                pass, against the FP8 tensor-pipe ceiling MEASURED on this box in the same run (fluxb200_fp8_mma_probe)
   gpu_reference the UNMODIFIED reference modules (oracle/_ref) timed on the same GPU: eager, and torch.compile'd blocks
   cpu_baseline  the reference's bf16 blocks on the host cores (bounded sample)
 
@@ -450,46 +450,43 @@ def synthetic_lora(params, rank=16, seed=11):
 
 
 def measure_fp8_peak(ops, cabi, dev):
-    """The tcgen05 kind::f8f6f4 ceiling of THIS box, measured with the product GEMM kernel in probe mode 1|4 (operands
-    resident in shared memory after the first fill, no epilogue: the bare MMA issue rate of the 256x256 cta_group::2
-    tiling).  burst = best single launch; sustained = back-to-back launches for ~1.5 s (the power-capped regime the
-    step runs in)."""
-    M = N = K = 8192
-    # activation- / weight-like values (tensor-core power, and with it the sustained clock, depends on the operand bits)
-    g = torch.Generator(device=dev).manual_seed(0)
-    a = (torch.randn((M, K), device=dev, generator=g) * 4.0).to(torch.bfloat16).to(torch.float8_e5m2)
-    w = torch.randn((N, K), device=dev, generator=g).to(torch.bfloat16).to(torch.float8_e4m3fn)
-    one = torch.ones((), dtype=torch.float32, device=dev)
-    out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
-    flops = 2.0 * M * N * K
-    cabi.check(cabi.load().fluxb200_gemm_probe_mode(5), "fluxb200_gemm_probe_mode")
-    try:
-        for _ in range(3):
-            ops.f8_gemm(a, w, None, one, one, out=out)
-        torch.cuda.synchronize()
-        best = float("inf")
-        for _ in range(8):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            ops.f8_gemm(a, w, None, one, one, out=out)
-            e.record()
-            torch.cuda.synchronize()
-            best = min(best, s.elapsed_time(e))
-            time.sleep(0.05)
-        reps = max(8, int(1500.0 / best))
+    """The tcgen05 kind::f8f6f4 ceiling of THIS box: fluxb200_fp8_mma_probe = the bare MMA loop of the product GEMM tiling
+    (cta_group::2, M = 256, N = 256, K = 32), operands resident in shared memory, no TMA / epilogue / global traffic.
+    burst = best single ~0.3 ms launch after a pause; sustained = back-to-back launches for ~1.5 s (the power-capped
+    regime the step runs in)."""
+    import ctypes as C
+
+    lib = cabi.load()
+    flops = C.c_double(0.0)
+
+    def launch(tiles):
+        cabi.check(lib.fluxb200_fp8_mma_probe(tiles, C.byref(flops), cabi.stream_ptr()), "fluxb200_fp8_mma_probe")
+        return flops.value
+
+    for _ in range(2):
+        launch(40)
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(8):
+        time.sleep(0.05)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        for _ in range(reps):
-            ops.f8_gemm(a, w, None, one, one, out=out)
+        f_burst = launch(40)
         e.record()
         torch.cuda.synchronize()
-        sustained_ms = s.elapsed_time(e) / reps
-    finally:
-        cabi.check(cabi.load().fluxb200_gemm_probe_mode(0), "fluxb200_gemm_probe_mode")
-    return {"fp8_tflops_burst": flops / (best * 1e-3) / 1e12, "fp8_tflops_sustained": flops / (sustained_ms * 1e-3) / 1e12,
-            "shape": [M, N, K], "sustained_launches": reps,
-            "how": "f8_gemm_kernel<256, PLAIN, cta_group::2> in probe mode 1|4 (no TMA after the first ring fill, no "
-                   "epilogue): tcgen05.mma.kind::f8f6f4 M=256 N=256 K=32 issue rate, CUDA events"}
+        best = min(best, s.elapsed_time(e))
+    reps = max(8, int(1500.0 / (best * 10)))
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        f_sus = launch(400)
+    e.record()
+    torch.cuda.synchronize()
+    sustained_ms = s.elapsed_time(e) / reps
+    return {"fp8_tflops_burst": f_burst / (best * 1e-3) / 1e12, "fp8_tflops_sustained": f_sus / (sustained_ms * 1e-3) / 1e12,
+            "burst_launch_ms": best, "sustained_launches": reps, "sustained_launch_ms": sustained_ms,
+            "how": "fluxb200_fp8_mma_probe: tcgen05.mma.cta_group::2.kind::f8f6f4 M=256 N=256 K=32 issued back to back on "
+                   "all 74 SM pairs, operands resident in shared memory (no TMA, no epilogue), CUDA events"}
 
 
 def main():
@@ -663,7 +660,7 @@ def main():
             "peak": fp8_peak, "unit": "TFLOP/s", "frac": achieved / fp8_peak,
             "traffic": traffic if args.config == "c2" else None, "traffic_source": traffic_src,
             "peak_source": "measured in this run on this GPU: sustained tcgen05 kind::f8f6f4 issue rate of the GEMM "
-                           "kernel's own tiling (fluxb200_gemm_probe_mode 1|4); MEASURED_PEAKS.json has no fp8 row",
+                           "kernel's own tiling (fluxb200_fp8_mma_probe); MEASURED_PEAKS.json has no fp8 row",
             "fp8_peak_probe": fp8_probe,
             "frac_of_burst_peak": achieved / fp8_probe["fp8_tflops_burst"],
             "frac_of_2x_bf16_sustained": achieved / (2.0 * peaks["bf16_tflops_sustained"]),

@@ -42,6 +42,7 @@ EXPORTS = (
     "fluxb200_debug_counters",
     "fluxb200_gemm_probe_mode",
     "fluxb200_gemm_force_tiling",
+    "fluxb200_fp8_mma_probe",
 )
 
 
@@ -200,6 +201,7 @@ def load() -> C.CDLL:
     lib.fluxb200_debug_counters.argtypes = [C.POINTER(C.c_ulonglong)]
     lib.fluxb200_gemm_probe_mode.argtypes = [C.c_int]
     lib.fluxb200_gemm_force_tiling.argtypes = [C.c_int, C.c_int]
+    lib.fluxb200_fp8_mma_probe.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_void_p]
     for name in EXPORTS:
         if name != "fluxb200_last_error":
             getattr(lib, name).restype = C.c_int

@@ -711,6 +711,72 @@ __global__ void __launch_bounds__(kGemmThreads, 1) f8_gemm_kernel(const __grid_c
   }
 }
 
+// ---- FP8 tensor-pipe ceiling probe ---------------------------------------------------------------------
+// The bare tcgen05.mma.kind::f8f6f4 issue rate of the product tiling (cta_group::2, M = 256, N = 256, K = 32 per
+// instruction, 4 instructions per 128-byte K slab, two TMEM accumulators alternating every kProbeKBlocks slabs), operands
+// resident in shared memory: no TMA, no epilogue, no global traffic.  What a GEMM with free data movement would reach
+// on THIS box under its power cap: bench.py times it (burst and sustained) and reports it as roofline.peak.
+constexpr int kProbeKBlocks = 24;  // one "tile" = 24 K slabs, as K = 3072
+
+__global__ void __launch_bounds__(128, 1) fp8_mma_probe_kernel(int tiles, uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kA = kBM * kBK, kB = kBM * kBK, kStage = kA + kB, kStages = 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStage);  // acc_done[2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t cta_rank = cluster_ctarank();
+  // operand bytes: a fixed pseudo-random pattern of finite fp8 values (tensor-core power depends on the operand bits)
+  for (int i = threadIdx.x; i < kStages * kStage / 4; i += blockDim.x) {
+    uint32_t h = (i + 1) * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15;
+    reinterpret_cast<uint32_t*>(smem)[i] = h & 0x3f3f3f3fu;  // |x| < 2 in both fp8 formats, no NaN / Inf encodings
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_ptr, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (warp == 0 && cta_rank == 0) {
+    const uint64_t a_desc0 = make_desc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t b_desc0 = make_desc_sw128(smem_u32(smem) + kA, 16, 1024);
+    for (int t = 0; t < tiles; ++t) {
+      const int as = t & 1;
+      if (t >= 2) mbar_wait(&bars[as], ((t >> 1) - 1) & 1);  // accumulator `as` free again (tile t-2 retired)
+      tc_fence_after();
+      if (elect_one()) {
+        for (int kb = 0; kb < kProbeKBlocks; ++kb) {
+          const uint64_t ad = desc_advance(a_desc0, (kb % kStages) * kStage), bd = desc_advance(b_desc0, (kb % kStages) * kStage);
+#pragma unroll
+          for (int k = 0; k < kBK / 32; ++k)
+            mma_f8f6f4_ss_2sm(tmem_base + as * 256, desc_advance(ad, k * 32), desc_advance(bd, k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit_2sm(&bars[as], 1);  // leader only
+      }
+      __syncwarp();
+    }
+    for (int as = 0; as < 2; ++as) {  // drain: the last tile on each accumulator
+      const int last = tiles - 1 - ((tiles - 1 - as) & 1);
+      if (last >= 0) mbar_wait(&bars[as], (last >> 1) & 1);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 
 // Co-resident clusters of `cluster_ctas` CTAs of this kernel (GPC packing: four-CTA clusters reach 132 of 148 SMs).
@@ -1002,6 +1068,24 @@ static int run_gemm_group(const fluxb200_gemm_args* args, int count, cudaStream_
 extern "C" int fluxb200_gemm_probe_mode(int mode) {
   FB_REQUIRE(mode >= 0 && mode < 16, "fluxb200_gemm_probe_mode: mode is a 4-bit mask");
   fb::g_probe_mode = mode;
+  return 0;
+}
+
+extern "C" int fluxb200_fp8_mma_probe(int tiles_per_pair, double* flops_out, fluxb200_stream_t stream_) {
+  using namespace fb;
+  FB_REQUIRE(tiles_per_pair > 0 && tiles_per_pair <= (1 << 20), "fluxb200_fp8_mma_probe: 0 < tiles_per_pair <= 2^20");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  constexpr int kSmem = 4 * (2 * kBM * kBK) + 64 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FB_CUDA_OK(cudaFuncSetAttribute(fp8_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set = true;
+  }
+  const int pairs = sm_count() / 2;
+  const uint32_t idesc = make_idesc(kFmtE5M2, kFmtE4M3, 256, 256);
+  FB_CUDA_OK(launch_kernel(fp8_mma_probe_kernel, dim3(pairs * 2), dim3(128), kSmem, stream, 2, tiles_per_pair, idesc));
+  if (flops_out != nullptr)
+    *flops_out = static_cast<double>(pairs) * tiles_per_pair * kProbeKBlocks * (kBK / 32) * (2.0 * 256 * 256 * 32);
   return 0;
 }
 

@@ -265,6 +265,12 @@ int fluxb200_lora_fuse(const void* w_fp8, int w_fmt, const float* w_scale_recip,
  * runs on with it (roofline.peak), instead of inferring it from the bf16 figure. */
 int fluxb200_gemm_probe_mode(int mode);
 
+/* Measurement: launches the bare tcgen05.mma.kind::f8f6f4 loop of the product GEMM tiling (cta_group::2, M = 256, N = 256,
+ * K = 32; operands resident in shared memory: no TMA, no epilogue, no global traffic) on every SM pair, `tiles_per_pair`
+ * accumulator tiles of 24 K-slabs each; *flops_out (host pointer, may be NULL) receives the FLOPs the launch performs.
+ * Timed with CUDA events by the caller (bench.py) it gives the FP8 tensor-pipe ceiling of the box under its power cap. */
+int fluxb200_fp8_mma_probe(int tiles_per_pair, double* flops_out, fluxb200_stream_t stream);
+
 /* Tiling override for A/B measurements and tests (0, 0 = the library's own choice): cta_group 1 = one CTA per 128 x BN
  * tile, 2 = one CTA pair per 256 x 256 tile; pairs_per_cluster 2 = two pairs per four-CTA cluster sharing their A rows
  * by TMA multicast (needs cta_group 2 and an even number of N tiles; ignored otherwise).  Results are identical

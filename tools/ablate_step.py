@@ -52,6 +52,10 @@ def step_ms(steps=20, warm=5):
 results = {}
 results["full"] = step_ms()
 print(f"full step: {results['full']:.3f} ms", flush=True)
+ops.FUSE_LN_INTO_GEMM = False
+results["ln_as_separate_launches"] = step_ms()
+ops.FUSE_LN_INTO_GEMM = True
+print(f"LayerNorm as separate launches: {results['ln_as_separate_launches']:.3f} ms", flush=True)
 
 lib = cabi.load()
 real = {n: getattr(lib, n) for n in ("fluxb200_attention", "fluxb200_ln_mod_quant", "fluxb200_ln_mod_quant_grouped",
@@ -80,7 +84,7 @@ for label, names in (("attention", ("fluxb200_attention",)),
     results[f"without_{label}"] = ms
     print(f"without {label:14s}: {ms:8.3f} ms   -> marginal {results['full'] - ms:7.3f} ms", flush=True)
 
-for mode, label in ((4, "gemm_no_epilogue"), (1, "gemm_no_tma"), (5, "gemm_mma_only"), (2, "gemm_no_mma")):
+for mode, label in ((4, "gemm_no_epilogue"), (2, "gemm_no_mma")):
     cabi.check(lib.fluxb200_gemm_probe_mode(mode), "probe")
     try:
         ms = step_ms()
