@@ -198,8 +198,12 @@ def grid_barrier_ws(device) -> Tensor:
 
 #: (epilogue, N, K, tuple of M) -> False once the library answered FLUXB200_ERR_UNSUPPORTED for that fused launch
 _ln_fused_unsupported = set()
-#: set False to always run LayerNorm-modulate-quantise as its own launch (A/B measurements)
-FUSE_LN_INTO_GEMM = True
+#: LayerNorm-modulate-quantise as a prologue phase of the consuming GEMM launch (fluxb200_f8_gemm_ln: 210 instead of
+#: 286 launches per Flux-dev step) or as its own grouped launch.  Measured in the captured c2 step (tools/ablate_step.py,
+#: profiles/r2_ablation.md): 40.94 ms fused vs 40.64 ms separate -- programmatic dependent launch already hides the
+#: kernel boundary, and inside the GEMM grid the LayerNorm has 20 warps per SM to hide its L2 latency instead of 32.
+#: The separate launch is therefore the default; env FLUXB200_FUSE_LN=1 (or setting this flag) selects the fused form.
+FUSE_LN_INTO_GEMM = __import__("os").environ.get("FLUXB200_FUSE_LN", "0") not in ("0", "")
 
 
 def ln_gemm_group(items, dtype: torch.dtype, build_gemms, eps: float = 1e-6):

@@ -377,6 +377,7 @@ def test_layernorm_fused_into_the_gemm_launch_is_bit_identical(lib, res, batch):
     t = torch.full((batch,), 0.6, dtype=BF16, device=DEV)
     call = dict(img=req["img"], img_ids=req["img_ids"], txt=req["txt"], txt_ids=req["txt_ids"], timesteps=t, y=req["y"],
                 guidance=req["guidance"])
+    prev = ops.FUSE_LN_INTO_GEMM
     try:
         with torch.inference_mode():
             ops.FUSE_LN_INTO_GEMM = False
@@ -392,9 +393,10 @@ def test_layernorm_fused_into_the_gemm_launch_is_bit_identical(lib, res, batch):
             for _ in range(5):
                 assert torch.equal(net(**call), y_sep)
         sched = PL.get_schedule(4, req["img"].shape[1])
-        g = PL.DenoiseSession(net, req, use_graph=True)
-        e = PL.DenoiseSession(net, req, use_graph=False)
+        g = PL.DenoiseSession(net, req, use_graph=True)    # captured with the fused launches
+        ops.FUSE_LN_INTO_GEMM = False
+        e = PL.DenoiseSession(net, req, use_graph=False)   # eager, separate launches
         for i in range(3):
             assert torch.equal(g.step_device(req["img"], sched[i], sched[i + 1]), e.step_device(req["img"], sched[i], sched[i + 1]))
     finally:
-        ops.FUSE_LN_INTO_GEMM = True
+        ops.FUSE_LN_INTO_GEMM = prev

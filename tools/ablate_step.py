@@ -52,10 +52,10 @@ def step_ms(steps=20, warm=5):
 results = {}
 results["full"] = step_ms()
 print(f"full step: {results['full']:.3f} ms", flush=True)
-ops.FUSE_LN_INTO_GEMM = False
-results["ln_as_separate_launches"] = step_ms()
 ops.FUSE_LN_INTO_GEMM = True
-print(f"LayerNorm as separate launches: {results['ln_as_separate_launches']:.3f} ms", flush=True)
+results["ln_fused_into_gemm_launch"] = step_ms()
+ops.FUSE_LN_INTO_GEMM = False
+print(f"LayerNorm fused into the GEMM launches: {results['ln_fused_into_gemm_launch']:.3f} ms", flush=True)
 
 lib = cabi.load()
 real = {n: getattr(lib, n) for n in ("fluxb200_attention", "fluxb200_ln_mod_quant", "fluxb200_ln_mod_quant_grouped",
