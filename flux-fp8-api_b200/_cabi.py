@@ -33,6 +33,9 @@ EXPORTS = (
     "fluxb200_f8_gemv",
     "fluxb200_modulation_batched",
     "fluxb200_modulation_batched_bf16",
+    "fluxb200_bf16_gemv",
+    "fluxb200_timestep_embedding",
+    "fluxb200_euler_update",
     "fluxb200_silu_quant",
     "fluxb200_ln_mod_quant",
     "fluxb200_ln_mod_quant_grouped",
@@ -183,6 +186,10 @@ def load() -> C.CDLL:
     lib.fluxb200_modulation_batched_bf16.argtypes = [
         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
     ]
+    lib.fluxb200_bf16_gemv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.fluxb200_timestep_embedding.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.fluxb200_euler_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.fluxb200_silu_quant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     lib.fluxb200_ln_mod_quant.argtypes = [
         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

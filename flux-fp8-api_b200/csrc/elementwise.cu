@@ -523,24 +523,38 @@ __device__ __forceinline__ void mma_m16n8k16_bf16(float (&c)[4], uint32_t a0, ui
 // row pitch 2K + 64 bytes: a quarter-warp (two batch rows x four 16-byte pieces) covers all 32 banks exactly once
 constexpr int kModBf16Pad = 64;
 
+// SILU: apply bf16(silu(.)) to the input while staging it (Modulation / MLPEmbedder.out_layer / LastLayer.adaLN).
+// ONE: a single layer passed BY VALUE (`one`, no device table) with up to two bf16 [B, N] addends applied after the
+// bias, each followed by its own bf16 rounding (Flux.forward: vec = time_in(..) + guidance_in(..) + vector_in(y)).
+struct GemvOne {
+  fluxb200_gemv_layer layer;
+  const __nv_bfloat16* add0;
+  const __nv_bfloat16* add1;
+  int64_t ld_add;
+};
+
+template <bool SILU, bool ONE>
 __global__ void __launch_bounds__(kModMmaWarps * 32, 4) gemv_layers_bf16_kernel(
     const fluxb200_gemv_layer* __restrict__ layers, int num_layers, const __nv_bfloat16* __restrict__ vec,
-    __nv_bfloat16* __restrict__ out, int64_t ld_out, int B, int K) {
+    __nv_bfloat16* __restrict__ out, int64_t ld_out, int B, int K, const GemvOne one) {
   pdl_wait();
   extern __shared__ __align__(16) uint8_t a_sm8[];
   __shared__ int s_layer;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) s_layer = 0;
-  __syncthreads();
-  {
-    int mine = 0;
-    for (int i = threadIdx.x; i < num_layers; i += blockDim.x)
-      mine += layers[i].block_start <= static_cast<int>(blockIdx.x) ? 1 : 0;
-    if (mine) atomicAdd(&s_layer, mine);
+  int l = 0;
+  if constexpr (!ONE) {
+    if (threadIdx.x == 0) s_layer = 0;
+    __syncthreads();
+    {
+      int mine = 0;
+      for (int i = threadIdx.x; i < num_layers; i += blockDim.x)
+        mine += layers[i].block_start <= static_cast<int>(blockIdx.x) ? 1 : 0;
+      if (mine) atomicAdd(&s_layer, mine);
+    }
+    __syncthreads();
+    l = s_layer - 1;
   }
-  __syncthreads();
-  const int l = s_layer - 1;
-  const fluxb200_gemv_layer L = layers[l];
+  const fluxb200_gemv_layer L = ONE ? one.layer : layers[l];
   const int pitch = 2 * K + kModBf16Pad;
   const int n0 = (static_cast<int>(blockIdx.x) - L.block_start) * kModColsPerBlock + warp * 16;
   const int g = lane >> 2, t = lane & 3;
@@ -557,7 +571,7 @@ __global__ void __launch_bounds__(kModMmaWarps * 32, 4) gemv_layers_bf16_kernel(
       for (int i = threadIdx.x; i < mt * K; i += blockDim.x) {
         const int r = i / K, c = i - r * K;
         const float v = __bfloat162float(vec[static_cast<int64_t>(m0 + r) * K + c]);
-        *reinterpret_cast<__nv_bfloat16*>(a_sm8 + r * pitch + c * 2) = __float2bfloat16_rn(v / (1.f + expf(-v)));
+        *reinterpret_cast<__nv_bfloat16*>(a_sm8 + r * pitch + c * 2) = __float2bfloat16_rn(SILU ? v / (1.f + expf(-v)) : v);
       }
       for (int i = threadIdx.x; i < pitch / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_sm8 + mt * pitch)[i] = 0u;
     }
@@ -598,11 +612,50 @@ __global__ void __launch_bounds__(kModMmaWarps * 32, 4) gemv_layers_bf16_kernel(
         const int col = n0 + g + (j >> 1) * 8, row = t * 2 + (j & 1);
         if (row < mt && col < L.N) {
           const float bb = bias ? __bfloat162float(bias[col]) : 0.f;
-          out[static_cast<int64_t>(m0 + row) * ld_out + L.out_offset + col] = __float2bfloat16_rn(c0[j] + c1[j] + bb);
+          float y = bf16r(c0[j] + c1[j] + bb);
+          if constexpr (ONE) {
+            if (one.add0) y = bf16r(y + __bfloat162float(one.add0[static_cast<int64_t>(m0 + row) * one.ld_add + col]));
+            if (one.add1) y = bf16r(y + __bfloat162float(one.add1[static_cast<int64_t>(m0 + row) * one.ld_add + col]));
+          }
+          out[static_cast<int64_t>(m0 + row) * ld_out + L.out_offset + col] = __float2bfloat16_rn(y);
         }
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// timestep_embedding(t, dim) .type(bf16)          modules/flux_model.py:95-116 (called at :687, :694)
+//   t' = bf16(time_factor * t) (the product is formed in t's dtype, bf16);  args = float(t') * freqs[j]  (fp32);
+//   emb = [cos(args) | sin(args)] -> bf16.   freqs = exp(-ln(max_period) * arange(half) / half) is passed in (fp32).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) timestep_embedding_kernel(const __nv_bfloat16* __restrict__ t,
+                                                                 const float* __restrict__ freqs,
+                                                                 __nv_bfloat16* __restrict__ out, int B, int half,
+                                                                 float time_factor) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, j = i - b * half;
+  const float ts = bf16r(time_factor * __bfloat162float(t[b]));
+  const float a = ts * freqs[j];
+  out[static_cast<int64_t>(b) * 2 * half + j] = __float2bfloat16_rn(cosf(a));
+  out[static_cast<int64_t>(b) * 2 * half + half + j] = __float2bfloat16_rn(sinf(a));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Euler step of the flow: img + (t_prev - t_curr) * pred          flux_pipeline.py:651
+//   eager torch: the python scalar multiplies in fp32, the product is rounded to bf16, the sum is rounded to bf16
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) euler_update_kernel(const __nv_bfloat16* __restrict__ img,
+                                                           const __nv_bfloat16* __restrict__ pred,
+                                                           const float* __restrict__ dt, __nv_bfloat16* __restrict__ out,
+                                                           int64_t n) {
+  pdl_wait();
+  const float d = __ldg(dt);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __float2bfloat16_rn(__bfloat162float(img[i]) + bf16r(d * __bfloat162float(pred[i])));
 }
 
 static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
@@ -814,10 +867,63 @@ extern "C" int fluxb200_modulation_batched_bf16(const void* vec, const fluxb200_
   FB_REQUIRE(num_layers > 0 && total_blocks > 0 && B > 0 && B <= 16, "fluxb200_modulation_batched_bf16: bad sizes");
   FB_REQUIRE(K % 32 == 0 && K <= 4096, "fluxb200_modulation_batched_bf16: K=%d must be a multiple of 32 and <= 4096", K);
   const size_t smem = static_cast<size_t>((B < 8 ? B : 8) + 1) * (2 * K + kModBf16Pad);
-  auto kern = gemv_layers_bf16_kernel;
+  auto kern = gemv_layers_bf16_kernel<true, false>;
   if (smem > 48 * 1024) FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   FB_CUDA_OK(launch_kernel(kern, dim3(total_blocks), dim3(kModMmaWarps * 32), smem, stream, 1, layers, num_layers,
-                           static_cast<const __nv_bfloat16*>(vec), static_cast<__nv_bfloat16*>(out), ld_out, B, K));
+                           static_cast<const __nv_bfloat16*>(vec), static_cast<__nv_bfloat16*>(out), ld_out, B, K,
+                           GemvOne{}));
   FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_bf16_gemv(const void* x, const void* w, const void* bias, const void* add0, const void* add1,
+                                  int64_t ld_add, void* out, int64_t ld_out, int B, int N, int K, int silu_input,
+                                  fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(x && w && out, "fluxb200_bf16_gemv: null operand");
+  FB_REQUIRE(B > 0 && B <= 16 && N > 0, "fluxb200_bf16_gemv: need 0 < B <= 16, N > 0");
+  FB_REQUIRE(K % 32 == 0 && K > 0 && K <= 4096, "fluxb200_bf16_gemv: K=%d must be a multiple of 32 and <= 4096", K);
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "fluxb200_bf16_gemv: w must be 16-byte aligned");
+  FB_REQUIRE(ld_out >= N && (add0 == nullptr || ld_add >= N) && (add1 == nullptr || ld_add >= N),
+             "fluxb200_bf16_gemv: row strides smaller than N");
+  GemvOne one{};
+  one.layer.w = w;
+  one.layer.bias = bias;
+  one.layer.N = N;
+  one.layer.out_offset = 0;
+  one.layer.block_start = 0;
+  one.add0 = static_cast<const __nv_bfloat16*>(add0);
+  one.add1 = static_cast<const __nv_bfloat16*>(add1);
+  one.ld_add = ld_add;
+  const size_t smem = static_cast<size_t>((B < 8 ? B : 8) + 1) * (2 * K + kModBf16Pad);
+  const int blocks = (N + kModColsPerBlock - 1) / kModColsPerBlock;
+  auto kern = silu_input ? gemv_layers_bf16_kernel<true, true> : gemv_layers_bf16_kernel<false, true>;
+  if (smem > 48 * 1024) FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FB_CUDA_OK(launch_kernel(kern, dim3(blocks), dim3(kModMmaWarps * 32), smem, stream, 1,
+                           static_cast<const fluxb200_gemv_layer*>(nullptr), 1, static_cast<const __nv_bfloat16*>(x),
+                           static_cast<__nv_bfloat16*>(out), ld_out, B, K, one));
+  FB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fluxb200_timestep_embedding(const void* t, const float* freqs, void* out, int B, int dim, float time_factor,
+                                           fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(t && freqs && out && B > 0 && dim > 0 && dim % 2 == 0, "fluxb200_timestep_embedding: bad operand (dim even)");
+  const int half = dim / 2;
+  FB_CUDA_OK(launch_kernel(timestep_embedding_kernel, dim3((B * half + 127) / 128), dim3(128), 0, stream, 1,
+                           static_cast<const __nv_bfloat16*>(t), freqs, static_cast<__nv_bfloat16*>(out), B, half,
+                           time_factor));
+  return 0;
+}
+
+extern "C" int fluxb200_euler_update(const void* img, const void* pred, const float* dt, void* out, int64_t n,
+                                     fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(img && pred && dt && out && n >= 0, "fluxb200_euler_update: null operand");
+  if (n == 0) return 0;
+  FB_CUDA_OK(launch_kernel(euler_update_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, 1,
+                           static_cast<const __nv_bfloat16*>(img), static_cast<const __nv_bfloat16*>(pred), dt,
+                           static_cast<__nv_bfloat16*>(out), n));
   return 0;
 }

@@ -21,6 +21,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _cabi as cabi
+from . import ops
 from .blocks import (DoubleStreamBlock, EmbedND, ModulationBank, SingleStreamBlock, extract_cos_sin,
                      tensor_version)
 from .f8linear import F8Linear
@@ -80,6 +81,19 @@ def _linear(in_f: int, out_f: int, f8: bool) -> nn.Module:
     return F8Linear(in_features=in_f, out_features=out_f, bias=True) if f8 else nn.Linear(in_f, out_f, bias=True)
 
 
+def _skinny_bf16(x: Tensor, *lins: nn.Module) -> bool:
+    """True when `lins` are plain bf16 nn.Linear layers on the GPU and x is a skinny bf16 matrix our GEMV kernel takes
+    (fluxb200_bf16_gemv: B <= 16, K % 32 == 0, K <= 4096).  Otherwise torch's library GEMM runs (larger batches)."""
+    if x.dim() != 2 or x.dtype != BF16 or not x.is_cuda or x.shape[0] > 16:
+        return False
+    for l in lins:
+        if type(l) is not nn.Linear or l.weight.dtype != BF16 or not l.weight.is_cuda or not l.weight.is_contiguous():
+            return False
+        if l.in_features % 32 or l.in_features > 4096 or (l.bias is not None and l.bias.dtype != BF16):
+            return False
+    return True
+
+
 class MLPEmbedder(nn.Module):
     def __init__(self, in_dim: int, hidden_dim: int, prequantized: bool = False, quantized=False):
         super().__init__()
@@ -88,8 +102,17 @@ class MLPEmbedder(nn.Module):
         self.silu = nn.SiLU()
         self.out_layer = _linear(hidden_dim, hidden_dim, f8)
 
-    def forward(self, x: Tensor) -> Tensor:
-        return self.out_layer(self.silu(self.in_layer(x)))
+    def forward(self, x: Tensor, add0: Optional[Tensor] = None, add1: Optional[Tensor] = None) -> Tensor:
+        """out_layer(silu(in_layer(x))) [+ add0] [+ add1] (reference modules/flux_model.py:154-155; the optional addends
+        are Flux.forward's `vec = vec + ...` sums, :694-697, carried by the out_layer launch)."""
+        if _skinny_bf16(x, self.in_layer, self.out_layer):
+            h = ops.bf16_gemv(x, self.in_layer.weight, self.in_layer.bias)
+            return ops.bf16_gemv(h, self.out_layer.weight, self.out_layer.bias, silu_input=True, add0=add0, add1=add1)
+        out = self.out_layer(self.silu(self.in_layer(x)))
+        for a in (add0, add1):
+            if a is not None:
+                out = out + a
+        return out
 
 
 class LastLayer(nn.Module):
@@ -100,6 +123,13 @@ class LastLayer(nn.Module):
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 2 * hidden_size, bias=True))
 
     def forward(self, x: Tensor, vec: Tensor) -> Tensor:
+        lin = self.adaLN_modulation[1]
+        if _skinny_bf16(vec, lin) and x.dtype == BF16 and x.is_cuda and x.shape[-1] % 256 == 0 and x.shape[-1] <= 4096:
+            # SiLU + adaLN linear as one weight-streaming launch, LayerNorm + modulate as one launch (the same kernel
+            # the blocks use, bf16 output); the [L, 3072] x [3072, 64] projection stays a plain library GEMM
+            shift, scale = ops.bf16_gemv(vec, lin.weight, lin.bias, silu_input=True).chunk(2, dim=1)
+            _, xm = ops.ln_mod_quant(x, shift, scale, None, None, want_bf16=True, eps=self.norm_final.eps)
+            return self.linear(xm)
         shift, scale = self.adaLN_modulation(vec).chunk(2, dim=1)
         x = (1 + scale[:, None, :]) * self.norm_final(x) + shift[:, None, :]
         return self.linear(x)
@@ -281,13 +311,20 @@ class Flux(nn.Module):
         cache = self._cache if self._invariants_cacheable() else _StepInvariantCache()
 
         img = self.img_in(img)
-        vec = self.time_in(timestep_embedding(timesteps, 256).type(self.dtype))
+
+        def t_emb(t: Tensor) -> Tensor:
+            if t.dtype == BF16 and self.dtype == BF16 and t.is_cuda:
+                return ops.timestep_embedding(t, 256)  # one kernel instead of ~10 eager elementwise launches
+            return timestep_embedding(t, 256).type(self.dtype)
+
+        g_emb = None
         if self.params.guidance_embed:
             if guidance is None:
                 raise ValueError("Didn't get guidance strength for guidance distilled model.")
-            vec = vec + cache.get("guidance", (guidance,),
-                                  lambda: self.guidance_in(timestep_embedding(guidance, 256).type(self.dtype)))
-        vec = vec + cache.get("vector", (y,), lambda: self.vector_in(y))
+            g_emb = cache.get("guidance", (guidance,), lambda: self.guidance_in(t_emb(guidance)))
+        y_emb = cache.get("vector", (y,), lambda: self.vector_in(y))
+        # vec = time_in(..) [+ guidance_in(..)] + vector_in(y): the additions ride on time_in's out_layer launch
+        vec = self.time_in(t_emb(timesteps), g_emb if g_emb is not None else y_emb, y_emb if g_emb is not None else None)
         txt = cache.get("txt", (txt,), lambda: self.txt_in(txt))
 
         def _pe():

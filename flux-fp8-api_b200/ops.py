@@ -113,6 +113,68 @@ def silu_quant(x: Tensor, scale: Optional[Tensor], dtype: Optional[torch.dtype],
     return yq, yb
 
 
+def bf16_gemv(x: Tensor, weight: Tensor, bias: Optional[Tensor], silu_input: bool = False,
+              add0: Optional[Tensor] = None, add1: Optional[Tensor] = None) -> Tensor:
+    """F.linear(f(x), weight, bias) [+ add0] [+ add1] for a skinny bf16 input x [B <= 16, K] (fluxb200_bf16_gemv):
+    f = silu when silu_input; every addition is followed by its own bf16 rounding, as the eager ops would."""
+    cabi.require_cuda(x, weight)
+    for t, what in ((x, "x"), (weight, "weight"), (bias, "bias"), (add0, "add0"), (add1, "add1")):
+        _want(t, BF16, f"bf16_gemv: {what}")
+    B, K = x.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise ValueError(f"bf16_gemv: x {tuple(x.shape)} does not match weight {tuple(weight.shape)}")
+    x, weight = x.contiguous(), _contig(weight, "weight")
+    adds = [a.contiguous() if a is not None else None for a in (add0, add1)]
+    for a in adds:
+        if a is not None and tuple(a.shape) != (B, N):
+            raise ValueError(f"bf16_gemv: addend {tuple(a.shape)} is not [{B}, {N}]")
+    out = torch.empty((B, N), dtype=BF16, device=x.device)
+    _timed("bf16_gemv", 2.0 * N * K,
+           lambda: cabi.check(cabi.load().fluxb200_bf16_gemv(x.data_ptr(), weight.data_ptr(), cabi.ptr(bias), cabi.ptr(adds[0]),
+                                                             cabi.ptr(adds[1]), N, out.data_ptr(), N, B, N, K,
+                                                             1 if silu_input else 0, cabi.stream_ptr()),
+                              "fluxb200_bf16_gemv"))
+    return out
+
+
+_freqs_cache = {}
+
+
+def timestep_embedding(t: Tensor, dim: int = 256, max_period: int = 10000, time_factor: float = 1000.0) -> Tensor:
+    """modules/flux_model.py:95-116 followed by .type(bfloat16): [B] bf16 timesteps -> [B, dim] bf16."""
+    cabi.require_cuda(t)
+    _want(t, BF16, "timestep_embedding: t")
+    if dim % 2:
+        raise ValueError("timestep_embedding: odd dim is not supported by the kernel")
+    key = (t.device, dim, max_period)
+    freqs = _freqs_cache.get(key)
+    if freqs is None:
+        half = dim // 2
+        freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=t.device) / half)
+        _freqs_cache[key] = freqs
+    t = t.contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
+    cabi.check(cabi.load().fluxb200_timestep_embedding(t.data_ptr(), freqs.data_ptr(), out.data_ptr(), t.shape[0], dim,
+                                                       float(time_factor), cabi.stream_ptr()), "fluxb200_timestep_embedding")
+    return out
+
+
+def euler_update(img: Tensor, pred: Tensor, dt: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """img + dt * pred with eager torch's rounding (flux_pipeline.py:651); dt is a 0-dim fp32 device tensor."""
+    cabi.require_cuda(img, pred, dt)
+    _want(img, BF16, "euler_update: img"), _want(pred, BF16, "euler_update: pred"), _want(dt, torch.float32, "euler_update: dt")
+    if img.shape != pred.shape:
+        raise ValueError("euler_update: img and pred shapes differ")
+    img, pred = img.contiguous(), pred.contiguous()
+    if out is None:
+        out = torch.empty_like(img)
+    _contig(out, "out")
+    cabi.check(cabi.load().fluxb200_euler_update(img.data_ptr(), pred.data_ptr(), dt.data_ptr(), out.data_ptr(), img.numel(),
+                                                 cabi.stream_ptr()), "fluxb200_euler_update")
+    return out
+
+
 def ln_mod_quant(x: Tensor, shift: Tensor, scale: Tensor, in_scale: Optional[Tensor], dtype: Optional[torch.dtype],
                  out_fp8: Optional[Tensor] = None, want_bf16: bool = False, eps: float = 1e-6):
     """LayerNorm(no affine) -> (1+scale)*x+shift -> quantise.  x [B,L,D]; shift/scale [B,1,D] or [B,D]

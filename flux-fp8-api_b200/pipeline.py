@@ -18,6 +18,7 @@ from typing import Callable, Dict, List, Optional
 import torch
 from torch import Tensor, nn
 
+from . import ops
 from .f8linear import F8Linear, quantize_flow_transformer_and_dispatch_float8
 from .model import Flux, FluxSpec
 
@@ -323,8 +324,11 @@ class GraphedStep:
         pred = self.model(img=self.img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
                           timesteps=self.t_vec, guidance=r.get("guidance"))
         # img + (t_prev - t_curr) * pred: eager torch multiplies in fp32 by the python scalar, rounds the product
-        # to bf16, then adds in bf16 -- reproduced with the fp32 0-dim `dt`
-        self.out.copy_(self.img + (self.scal[1] * pred.float()).to(pred.dtype))
+        # to bf16, then adds in bf16 -- fluxb200_euler_update with the fp32 0-dim `dt`
+        if pred.dtype == BF16:
+            ops.euler_update(self.img, pred, self.scal[1], out=self.out)
+        else:
+            self.out.copy_(self.img + (self.scal[1] * pred.float()).to(pred.dtype))
         self.img.copy_(self.out)  # the next step's input, unless the caller supplies another latent
 
     @staticmethod

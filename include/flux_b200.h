@@ -161,6 +161,27 @@ int fluxb200_modulation_batched_bf16(const void* vec_bf16, const fluxb200_gemv_l
                                      fluxb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Per-step extras around the block stack: the skinny bf16 linears of MLPEmbedder / LastLayer and the
+ * elementwise glue of Flux.forward and the Euler loop, so that a step launches no eager torch elementwise kernels.
+ *
+ * fluxb200_bf16_gemv:  out[b, n] = bf16( bf16( bf16( sum_k f(x[b,k]) W[n,k] + bias[n] ) + add0[b,n] ) + add1[b,n] )
+ *   with f = bf16(silu(.)) when silu_input else identity; add0 / add1 optional (NULL).  B <= 16, K % 32 == 0, K <= 4096.
+ *   MLPEmbedder.forward (modules/flux_model.py:154-155: in_layer, then out_layer with silu_input),
+ *   LastLayer.adaLN_modulation (:495-497, 500) and `vec = time_in(..) + guidance_in(..) + vector_in(y)` (:687-697: the two
+ *   bf16 additions ride on the out_layer launch).
+ * fluxb200_timestep_embedding:  out[b, :] = bf16([cos | sin](float(bf16(time_factor * t[b])) * freqs))  (:95-116);
+ *   freqs = exp(-ln(max_period) * arange(dim/2) / (dim/2)) as fp32 [dim/2], computed once by the caller.
+ * fluxb200_euler_update:  out = bf16( img + bf16( (*dt) * pred ) )    flux_pipeline.py:651  (in place allowed).
+ * ------------------------------------------------------------------------------------------- */
+int fluxb200_bf16_gemv(const void* x_bf16, const void* w_bf16, const void* bias_bf16, const void* add0_bf16,
+                       const void* add1_bf16, int64_t ld_add, void* out_bf16, int64_t ld_out, int B, int N, int K,
+                       int silu_input, fluxb200_stream_t stream);
+int fluxb200_timestep_embedding(const void* t_bf16, const float* freqs, void* out_bf16, int B, int dim,
+                                float time_factor, fluxb200_stream_t stream);
+int fluxb200_euler_update(const void* img_bf16, const void* pred_bf16, const float* dt, void* out_bf16, int64_t n,
+                          fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Modulation prologue: y = quantize( bf16(silu(x)), scale )   (modules/flux_model.py:249,252 +
  * float8_quantize.py:274-276).  y_bf16 (optional) receives bf16(silu(x)) for unquantised lins.
  * ------------------------------------------------------------------------------------------- */

@@ -415,3 +415,43 @@ def test_quad_tiling_in_the_fused_epilogues(ops, O):
     for x, y in zip(res["pair"], res["quad"]):
         assert torch.equal(x.view(torch.uint8) if x.dtype.itemsize == 1 else x, y.view(torch.uint8) if y.dtype.itemsize == 1 else y)
     assert res["pair"][0].abs().sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-step extras: embedder / final-layer GEMVs, timestep embedding, Euler update
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,K,silu", [(1, 3072, 256, False), (1, 3072, 3072, True), (3, 6144, 3072, True),
+                                        (2, 256, 64, False), (16, 3072, 768, False), (5, 100, 96, True)])
+def test_bf16_gemv_against_torch_linear(ops, B, N, K, silu):
+    g = gen(70 + B)
+    x = torch.randn(B, K, device=DEV, generator=g).to(BF16)
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.02).to(BF16)
+    b = (torch.randn(N, device=DEV, generator=g) * 0.02).to(BF16)
+    a0 = torch.randn(B, N, device=DEV, generator=g).to(BF16)
+    a1 = torch.randn(B, N, device=DEV, generator=g).to(BF16)
+    ref = F.linear(F.silu(x) if silu else x, w, b)
+    ulp_check(ops.bf16_gemv(x, w, b, silu_input=silu), ref, ulps=1, frac=0.05)
+    ulp_check(ops.bf16_gemv(x, w, None, silu_input=silu), F.linear(F.silu(x) if silu else x, w), ulps=1, frac=0.05)
+    ulp_check(ops.bf16_gemv(x, w, b, silu_input=silu, add0=a0, add1=a1), (ref + a0) + a1, ulps=1, frac=0.05)
+    ulp_check(ops.bf16_gemv(x, w, b, silu_input=silu, add0=a0), ref + a0, ulps=1, frac=0.05)
+
+
+def test_timestep_embedding_and_euler_update(ops):
+    from flux_fp8_api_b200 import model as M
+
+    t = torch.tensor([1.0, 0.9531, 0.5, 0.0273, 0.0, 3.5], device=DEV).to(BF16)
+    ref = M.timestep_embedding(t, 256).to(BF16)                      # the reference formula in torch (modules/flux_model.py:95-116)
+    got = ops.timestep_embedding(t, 256)
+    assert got.shape == ref.shape
+    d = (got.float() - ref.float()).abs()
+    assert d.max().item() <= 2.0 ** -8 and (d > 0).float().mean().item() < 0.01   # libdevice cos/sin vs ATen's: <= 1 ulp, rare
+    g = gen(81)
+    img = torch.randn(2, 4096, 64, device=DEV, generator=g).to(BF16)
+    pred = torch.randn(2, 4096, 64, device=DEV, generator=g).to(BF16)
+    for dt in (-0.0357142873108387, -0.25, 0.0117):
+        want = img + dt * pred                                       # flux_pipeline.py:651 in eager torch
+        dtt = torch.tensor(dt, dtype=torch.float32, device=DEV)
+        assert torch.equal(ops.euler_update(img, pred, dtt), want)
+    out = img.clone()
+    ops.euler_update(out, pred, dtt, out=out)                        # in place
+    assert torch.equal(out, want)
