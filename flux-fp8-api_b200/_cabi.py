@@ -36,6 +36,7 @@ EXPORTS = (
     "fluxb200_bf16_gemv",
     "fluxb200_timestep_embedding",
     "fluxb200_euler_update",
+    "fluxb200_bf16_gemm_small",
     "fluxb200_silu_quant",
     "fluxb200_ln_mod_quant",
     "fluxb200_ln_mod_quant_grouped",
@@ -190,6 +191,8 @@ def load() -> C.CDLL:
                                        C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.fluxb200_timestep_embedding.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
     lib.fluxb200_euler_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.fluxb200_bf16_gemm_small.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.fluxb200_silu_quant.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     lib.fluxb200_ln_mod_quant.argtypes = [
         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

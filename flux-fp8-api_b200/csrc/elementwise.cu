@@ -658,6 +658,105 @@ __global__ void __launch_bounds__(256) euler_update_kernel(const __nv_bfloat16* 
     out[i] = __float2bfloat16_rn(__bfloat162float(img[i]) + bf16r(d * __bfloat162float(pred[i])));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small bf16 GEMM for the two un-quantised linears that bracket the block stack:
+//   img_in      [B*L, 64]   x [3072, 64]^T   (modules/flux_model.py:686)          K = 64, output-write bound
+//   final_layer [B*L, 3072] x [64, 3072]^T   (:502, 716) + the Euler update (flux_pipeline.py:651) fused
+//   out[m, n] = bf16( sum_k x[m,k] W[n,k] + bias[n] )            (fp32 accumulate, as cuBLAS)
+//   euler:  out[m, n] = bf16( img[m, n] + bf16( dt * out[m, n] ) )
+// 0.03 % of the step's flops: mma.sync.m16n8k16 (bf16) from shared memory, 32 x 64 tiles, 4-stage cp.async ring; the
+// point is that the step launches no library kernel, not tensor-core peak.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSgBM = 32, kSgBN = 64, kSgBK = 32, kSgStages = 4, kSgPitch = kSgBK + 8;  // pitch 40 bf16 = 80 B
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(128) bf16_gemm_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                              const __nv_bfloat16* __restrict__ w,
+                                                              const __nv_bfloat16* __restrict__ bias,
+                                                              __nv_bfloat16* __restrict__ out, int64_t ldo,
+                                                              const __nv_bfloat16* __restrict__ euler_img,
+                                                              const float* __restrict__ euler_dt, int M, int N, int K) {
+  pdl_wait();
+  __shared__ __align__(16) __nv_bfloat16 As[kSgStages][kSgBM][kSgPitch];
+  __shared__ __align__(16) __nv_bfloat16 Ws[kSgStages][kSgBN][kSgPitch];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.x * kSgBM, n0 = blockIdx.y * kSgBN;
+  const int wm = (warp & 1) * 16, wn = (warp >> 1) * 32;  // warp tile: 16 rows x 32 columns
+  const int kt = K / kSgBK;
+
+  auto load_stage = [&](int stage, int kb) {
+    // A: 32 rows x 64 B = 128 16-byte pieces; W: 64 rows x 64 B = 256 pieces; 128 threads -> 1 + 2 pieces each
+    {
+      const int r = threadIdx.x >> 2, c = threadIdx.x & 3;
+      const bool ok = m0 + r < M;
+      cp_async16(&As[stage][r][c * 8], x + static_cast<int64_t>(ok ? m0 + r : 0) * ldx + kb * kSgBK + c * 8, ok);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int p = threadIdx.x + i * 128, r = p >> 2, c = p & 3;
+      const bool ok = n0 + r < N;
+      cp_async16(&Ws[stage][r][c * 8], w + static_cast<int64_t>(ok ? n0 + r : 0) * K + kb * kSgBK + c * 8, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+
+  for (int s = 0; s < kSgStages - 1; ++s) {
+    if (s < kt) load_stage(s, s);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kb = 0; kb < kt; ++kb) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kSgStages - 2) : "memory");
+    __syncthreads();
+    {  // prefetch k-block kb + stages - 1 into the slot freed last iteration
+      const int nk = kb + kSgStages - 1;
+      if (nk < kt) load_stage(nk % kSgStages, nk);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int st = kb % kSgStages;
+#pragma unroll
+    for (int kk = 0; kk < kSgBK; kk += 16) {
+      const uint32_t a0 = *reinterpret_cast<const uint32_t*>(&As[st][wm + g][kk + 2 * t]);
+      const uint32_t a1 = *reinterpret_cast<const uint32_t*>(&As[st][wm + g + 8][kk + 2 * t]);
+      const uint32_t a2 = *reinterpret_cast<const uint32_t*>(&As[st][wm + g][kk + 2 * t + 8]);
+      const uint32_t a3 = *reinterpret_cast<const uint32_t*>(&As[st][wm + g + 8][kk + 2 * t + 8]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ws[st][wn + j * 8 + g][kk + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ws[st][wn + j * 8 + g][kk + 2 * t + 8]);
+        mma_m16n8k16_bf16(acc[j], a0, a1, a2, a3, b0, b1);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const float dt = euler_dt ? __ldg(euler_dt) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = m0 + wm + g + h * 8, col = n0 + wn + j * 8 + 2 * t;
+      if (row >= M || col >= N) continue;  // N is even (validated): col + 1 < N as well
+      float y0 = bf16r(acc[j][h * 2] + (bias ? __bfloat162float(bias[col]) : 0.f));
+      float y1 = bf16r(acc[j][h * 2 + 1] + (bias ? __bfloat162float(bias[col + 1]) : 0.f));
+      if (euler_img) {
+        const __nv_bfloat162 im = *reinterpret_cast<const __nv_bfloat162*>(euler_img + static_cast<int64_t>(row) * ldo + col);
+        y0 = __bfloat162float(im.x) + bf16r(dt * y0);
+        y1 = __bfloat162float(im.y) + bf16r(dt * y1);
+      }
+      *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(row) * ldo + col) = pack_bf16x2(y0, y1);
+    }
+  }
+}
+
 static int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
   int64_t blocks = (work_items + threads - 1) / threads;
   int64_t cap = static_cast<int64_t>(sm_count()) * max_blocks_per_sm;
@@ -925,5 +1024,25 @@ extern "C" int fluxb200_euler_update(const void* img, const void* pred, const fl
   FB_CUDA_OK(launch_kernel(euler_update_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, 1,
                            static_cast<const __nv_bfloat16*>(img), static_cast<const __nv_bfloat16*>(pred), dt,
                            static_cast<__nv_bfloat16*>(out), n));
+  return 0;
+}
+
+extern "C" int fluxb200_bf16_gemm_small(const void* x, int64_t ldx, const void* w, const void* bias, void* out, int64_t ldo,
+                                        const void* euler_img, const float* euler_dt, int M, int N, int K,
+                                        fluxb200_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  FB_REQUIRE(x && w && out && M > 0 && N > 0 && K > 0, "fluxb200_bf16_gemm_small: null operand / empty shape");
+  FB_REQUIRE(K % 32 == 0 && N % 2 == 0, "fluxb200_bf16_gemm_small: K=%d must be a multiple of 32 and N=%d even", K, N);
+  FB_REQUIRE(ldx % 8 == 0 && ldo % 2 == 0 && ldx >= K && ldo >= N, "fluxb200_bf16_gemm_small: ldx %% 8, ldo %% 2, ld >= width");
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+             "fluxb200_bf16_gemm_small: x / w must be 16-byte, out 4-byte aligned");
+  FB_REQUIRE((euler_img == nullptr) == (euler_dt == nullptr), "fluxb200_bf16_gemm_small: euler_img and euler_dt go together");
+  const dim3 grid((M + kSgBM - 1) / kSgBM, (N + kSgBN - 1) / kSgBN);
+  FB_REQUIRE(grid.y <= 65535, "fluxb200_bf16_gemm_small: N too large");
+  FB_CUDA_OK(launch_kernel(bf16_gemm_small_kernel, grid, dim3(128), 0, stream, 1, static_cast<const __nv_bfloat16*>(x), ldx,
+                           static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(bias),
+                           static_cast<__nv_bfloat16*>(out), ldo, static_cast<const __nv_bfloat16*>(euler_img), euler_dt, M,
+                           N, K));
   return 0;
 }

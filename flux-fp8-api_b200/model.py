@@ -94,6 +94,14 @@ def _skinny_bf16(x: Tensor, *lins: nn.Module) -> bool:
     return True
 
 
+def _small_bf16_linear(x: Tensor, lin: nn.Module) -> bool:
+    """True when `lin` is a plain bf16 nn.Linear our small mma.sync GEMM takes (fluxb200_bf16_gemm_small)."""
+    return (type(lin) is nn.Linear and x.dtype == BF16 and x.is_cuda and lin.weight.dtype == BF16 and lin.weight.is_cuda
+            and lin.weight.is_contiguous() and lin.in_features % 32 == 0 and lin.out_features % 2 == 0
+            and (lin.bias is None or lin.bias.dtype == BF16) and x.shape[-1] == lin.in_features
+            and (x.stride(-1) == 1 and (x.dim() < 2 or x.stride(-2) % 8 == 0)))
+
+
 class MLPEmbedder(nn.Module):
     def __init__(self, in_dim: int, hidden_dim: int, prequantized: bool = False, quantized=False):
         super().__init__()
@@ -122,17 +130,32 @@ class LastLayer(nn.Module):
         self.linear = nn.Linear(hidden_size, patch_size * patch_size * out_channels, bias=True)
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 2 * hidden_size, bias=True))
 
-    def forward(self, x: Tensor, vec: Tensor) -> Tensor:
+    def forward(self, x: Tensor, vec: Tensor, euler=None) -> Tensor:
+        """Reference signature (x, vec).  `euler = (img, dt, out)` (pipeline.GraphedStep) additionally applies the Euler
+        update of flux_pipeline.py:651 to the prediction inside the projection's launch: out = img + dt * linear(...)."""
         lin = self.adaLN_modulation[1]
         if _skinny_bf16(vec, lin) and x.dtype == BF16 and x.is_cuda and x.shape[-1] % 256 == 0 and x.shape[-1] <= 4096:
             # SiLU + adaLN linear as one weight-streaming launch, LayerNorm + modulate as one launch (the same kernel
-            # the blocks use, bf16 output); the [L, 3072] x [3072, 64] projection stays a plain library GEMM
+            # the blocks use, bf16 output), the [L, 3072] x [3072, 64] projection (+ Euler update) as one mma.sync launch
             shift, scale = ops.bf16_gemv(vec, lin.weight, lin.bias, silu_input=True).chunk(2, dim=1)
             _, xm = ops.ln_mod_quant(x, shift, scale, None, None, want_bf16=True, eps=self.norm_final.eps)
-            return self.linear(xm)
-        shift, scale = self.adaLN_modulation(vec).chunk(2, dim=1)
-        x = (1 + scale[:, None, :]) * self.norm_final(x) + shift[:, None, :]
-        return self.linear(x)
+            if _small_bf16_linear(xm, self.linear):
+                if euler is not None:
+                    img, dt, out = euler
+                    return ops.bf16_gemm_small(xm, self.linear.weight, self.linear.bias, euler_img=img, euler_dt=dt, out=out)
+                return ops.bf16_gemm_small(xm, self.linear.weight, self.linear.bias)
+            pred = self.linear(xm)
+        else:
+            shift, scale = self.adaLN_modulation(vec).chunk(2, dim=1)
+            x = (1 + scale[:, None, :]) * self.norm_final(x) + shift[:, None, :]
+            pred = self.linear(x)
+        if euler is not None:
+            img, dt, out = euler
+            if pred.dtype == BF16:
+                return ops.euler_update(img, pred, dt, out=out)
+            out.copy_(img + (dt * pred.float()).to(pred.dtype))
+            return out
+        return pred
 
 
 class _StepInvariantCache:
@@ -305,12 +328,23 @@ class Flux(nn.Module):
 
     def forward(self, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, timesteps: Tensor, y: Tensor,
                 guidance: Optional[Tensor] = None) -> Tensor:
+        return self._forward(img, img_ids, txt, txt_ids, timesteps, y, guidance)
+
+    def denoise_step(self, img: Tensor, img_ids: Tensor, txt: Tensor, txt_ids: Tensor, timesteps: Tensor, y: Tensor,
+                     guidance: Optional[Tensor], dt: Tensor, out: Tensor) -> Tensor:
+        """One Euler step of the flow (flux_pipeline.py:641-651): out = img + dt * forward(img, ...), with the update
+        fused into the final projection's launch.  `dt` is a 0-dim fp32 device tensor (t_prev - t_curr)."""
+        return self._forward(img, img_ids, txt, txt_ids, timesteps, y, guidance, euler=(img, dt, out))
+
+    def _forward(self, img, img_ids, txt, txt_ids, timesteps, y, guidance=None, euler=None) -> Tensor:
         if img.ndim != 3 or txt.ndim != 3:
             raise ValueError("Input img and txt tensors must have 3 dimensions.")
         cabi.require_cuda(img, txt)
         cache = self._cache if self._invariants_cacheable() else _StepInvariantCache()
+        latent = img
 
-        img = self.img_in(img)
+        img = ops.bf16_gemm_small(img, self.img_in.weight, self.img_in.bias) if _small_bf16_linear(img, self.img_in) \
+            else self.img_in(img)
 
         def t_emb(t: Tensor) -> Tensor:
             if t.dtype == BF16 and self.dtype == BF16 and t.is_cuda:
@@ -351,6 +385,8 @@ class Flux(nn.Module):
             for block in self.single_blocks:
                 x = block(x, vec=vec, pe=pe, mod=next(mods)[0], rope=rope)
         x = x[:, T:, ...]
+        if euler is not None:
+            return self.final_layer(x, vec, euler=(latent, euler[1], euler[2]))
         return self.final_layer(x, vec)
 
     @classmethod

@@ -138,6 +138,37 @@ def bf16_gemv(x: Tensor, weight: Tensor, bias: Optional[Tensor], silu_input: boo
     return out
 
 
+def bf16_gemm_small(x: Tensor, weight: Tensor, bias: Optional[Tensor], euler_img: Optional[Tensor] = None,
+                    euler_dt: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """F.linear(x, weight, bias) for the small un-quantised linears around the block stack (fluxb200_bf16_gemm_small);
+    with euler_img / euler_dt the result p becomes euler_img + euler_dt * p with eager torch's roundings."""
+    cabi.require_cuda(x, weight)
+    for t, what in ((x, "x"), (weight, "weight"), (bias, "bias"), (euler_img, "euler_img")):
+        _want(t, BF16, f"bf16_gemm_small: {what}")
+    _want(euler_dt, torch.float32, "bf16_gemm_small: euler_dt")
+    lead, K = x.shape[:-1], x.shape[-1]
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise ValueError(f"bf16_gemm_small: x {tuple(x.shape)} does not match weight {tuple(weight.shape)}")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    _contig(weight, "weight")
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty((*lead, N), dtype=BF16, device=x.device)
+    _contig(out, "out")
+    if euler_img is not None:
+        euler_img = euler_img.contiguous()
+        if euler_img.numel() != M * N:
+            raise ValueError("bf16_gemm_small: euler_img must have the output's shape")
+    _timed("bf16_gemm_small", 2.0 * M * N * K,
+           lambda: cabi.check(cabi.load().fluxb200_bf16_gemm_small(x2.data_ptr(), x2.stride(0), weight.data_ptr(), cabi.ptr(bias),
+                                                                   out.data_ptr(), N, cabi.ptr(euler_img), cabi.ptr(euler_dt),
+                                                                   M, N, K, cabi.stream_ptr()), "fluxb200_bf16_gemm_small"))
+    return out
+
+
 _freqs_cache = {}
 
 

@@ -321,14 +321,10 @@ class GraphedStep:
     def _step(self):
         r = self.req
         self.t_vec.copy_(self.scal[0].expand_as(self.t_vec))  # exact: scal[0] already holds a bf16 value
-        pred = self.model(img=self.img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
-                          timesteps=self.t_vec, guidance=r.get("guidance"))
-        # img + (t_prev - t_curr) * pred: eager torch multiplies in fp32 by the python scalar, rounds the product
-        # to bf16, then adds in bf16 -- fluxb200_euler_update with the fp32 0-dim `dt`
-        if pred.dtype == BF16:
-            ops.euler_update(self.img, pred, self.scal[1], out=self.out)
-        else:
-            self.out.copy_(self.img + (self.scal[1] * pred.float()).to(pred.dtype))
+        # img + (t_prev - t_curr) * pred: eager torch multiplies in fp32 by the python scalar, rounds the product to
+        # bf16, then adds in bf16 -- done inside the final projection's launch with the fp32 0-dim `dt`
+        self.model.denoise_step(img=self.img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
+                                timesteps=self.t_vec, guidance=r.get("guidance"), dt=self.scal[1], out=self.out)
         self.img.copy_(self.out)  # the next step's input, unless the caller supplies another latent
 
     @staticmethod

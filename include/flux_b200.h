@@ -180,6 +180,14 @@ int fluxb200_timestep_embedding(const void* t_bf16, const float* freqs, void* ou
                                 float time_factor, fluxb200_stream_t stream);
 int fluxb200_euler_update(const void* img_bf16, const void* pred_bf16, const float* dt, void* out_bf16, int64_t n,
                           fluxb200_stream_t stream);
+/* The two un-quantised linears around the block stack, as one small mma.sync kernel (a step then launches no library
+ * GEMM):  out[m,n] = bf16( sum_k x[m,k] W[n,k] + bias[n] )  -- Flux.img_in (modules/flux_model.py:686, K = 64) and
+ * LastLayer.linear (:502, N = 64).  With euler_img / euler_dt the Euler update of flux_pipeline.py:651 is applied to
+ * the result in the same launch:  out = bf16( euler_img[m,n] + bf16( (*euler_dt) * out[m,n] ) )  (euler_img has row
+ * stride ldo too).  K % 32 == 0, N even, x / W 16-byte aligned. */
+int fluxb200_bf16_gemm_small(const void* x_bf16, int64_t ldx, const void* w_bf16, const void* bias_bf16, void* out_bf16,
+                             int64_t ldo, const void* euler_img_bf16, const float* euler_dt, int M, int N, int K,
+                             fluxb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Modulation prologue: y = quantize( bf16(silu(x)), scale )   (modules/flux_model.py:249,252 +

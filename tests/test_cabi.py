@@ -117,3 +117,36 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "flux_oracle" not in text, f
+
+
+def test_a_plain_c_program_links_and_calls_the_library(tmp_path, lib):
+    """INTEGRATION.md option B: a C host includes include/flux_b200.h and links libflux_b200.so.  No GPU needed: the
+    program checks the version, that invalid arguments come back as FLUXB200_ERR_INVALID with a message (never a
+    crash), and that the measurement overrides validate their input."""
+    from flux_fp8_api_b200 import _cabi
+
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "flux_b200.h"
+int main(void) {
+  if (fluxb200_version() != FLUXB200_VERSION) return 1;
+  fluxb200_gemm_args g;
+  memset(&g, 0, sizeof g);
+  int rc = fluxb200_f8_gemm(&g, NULL);
+  if (rc != FLUXB200_ERR_INVALID || strlen(fluxb200_last_error()) == 0) return 2;
+  if (fluxb200_quantize(NULL, NULL, 16, NULL, FLUXB200_E4M3, NULL) != FLUXB200_ERR_INVALID) return 3;
+  if (fluxb200_gemm_force_tiling(7, 0) != FLUXB200_ERR_INVALID) return 4;
+  if (fluxb200_gemm_probe_mode(99) != FLUXB200_ERR_INVALID) return 5;
+  if (fluxb200_bf16_gemv(NULL, NULL, NULL, NULL, NULL, 0, NULL, 0, 1, 64, 64, 0, NULL) != FLUXB200_ERR_INVALID) return 6;
+  printf("ok %d %s\n", fluxb200_version(), fluxb200_last_error());
+  return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libflux_b200.so", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)]).decode()
+    assert out.startswith("ok 100 ")

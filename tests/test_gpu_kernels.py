@@ -455,3 +455,26 @@ def test_timestep_embedding_and_euler_update(ops):
     out = img.clone()
     ops.euler_update(out, pred, dtt, out=out)                        # in place
     assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 3072, 64), (4096, 64, 3072), (2 * 2304, 64, 3072), (100, 256, 64), (33, 6, 96)])
+def test_bf16_gemm_small_and_fused_euler(ops, M, N, K):
+    """Flux.img_in / LastLayer.linear shapes (and ragged ones) against F.linear; the fused Euler epilogue against the
+    eager expression of flux_pipeline.py:651 applied to OUR projection (so the comparison is exact)."""
+    g = gen(90)
+    x = torch.randn(M, K, device=DEV, generator=g).to(BF16)
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(BF16)
+    b = (torch.randn(N, device=DEV, generator=g) * 0.1).to(BF16)
+    y = ops.bf16_gemm_small(x, w, b)
+    ulp_check(y, F.linear(x, w, b), ulps=1, frac=0.05)
+    ulp_check(ops.bf16_gemm_small(x, w, None), F.linear(x, w), ulps=1, frac=0.05)
+    img = torch.randn(M, N, device=DEV, generator=g).to(BF16)
+    dt = torch.tensor(-0.0357142873108387, dtype=torch.float32, device=DEV)
+    out = torch.empty_like(img)
+    ops.bf16_gemm_small(x, w, b, euler_img=img, euler_dt=dt, out=out)
+    assert torch.equal(out, img + dt.item() * y)
+    # 3-D input with a row stride (a [B, L, K] slice of a wider tensor), as Flux.forward hands it over
+    wide = torch.randn(2, M // 2 if M % 2 == 0 else M, K + 32, device=DEV, generator=g).to(BF16)
+    xs = wide[..., :K]
+    if xs.stride(-2) % 8 == 0:
+        ulp_check(ops.bf16_gemm_small(xs, w, b), F.linear(xs, w, b), ulps=1, frac=0.05)

@@ -400,3 +400,44 @@ def test_layernorm_fused_into_the_gemm_launch_is_bit_identical(lib, res, batch):
             assert torch.equal(g.step_device(req["img"], sched[i], sched[i + 1]), e.step_device(req["img"], sched[i], sched[i + 1]))
     finally:
         ops.FUSE_LN_INTO_GEMM = prev
+
+
+def test_prequantised_safetensors_roundtrip_and_the_reference_loads_it(gold, golden_dir, tmp_path, cpu_semantics):
+    """pipeline.save_prequantized writes ONE safetensors file in the reference's key layout: load_prequantized brings
+    back a frozen, graph-capturable model with bit-identical outputs, and -- when the staged reference is present -- the
+    reference's own Flux(prequantized_flow=True) loads the same file the way util.load_flow_model does
+    (load_sft + load_state_dict(assign=True), util.py:245-256) and runs it on its library kernels."""
+    from safetensors.torch import load_file
+
+    from flux_fp8_api_b200 import model as M, pipeline as PL
+    from oracle import ref_loader as R
+
+    net = tiny_net(gold)
+    inp = {k: v.to(DEV) for k, v in gold["inputs"].items()}
+    spec = M.FluxSpec(params=M.FluxParams(**gold["tiny"]), prequantized_flow=True)
+    path = str(tmp_path / "tiny.f8.safetensors")
+    header = PL.save_prequantized(net, path, spec)
+    assert header["f8_layers"] == 13 and header["version"] == PL.PREQUANTIZED_VERSION
+    back = PL.load_prequantized(path, DEV)
+    assert PL.all_frozen(back)
+    with torch.inference_mode():
+        y = net(**inp)
+        assert torch.equal(back(**inp), y)
+        sched = PL.get_schedule(2, inp["img"].shape[1])
+        req = {k: v for k, v in inp.items() if k != "timesteps"}
+        assert torch.equal(PL.DenoiseSession(back, req).step_device(req["img"], sched[0], sched[1]),
+                           PL.DenoiseSession(net, req).step_device(req["img"], sched[0], sched[1]))
+    if not R.available():
+        pytest.skip("oracle/_ref not staged: the reference-side load is checked where it is")
+    ref = R.load()
+    with torch.device("meta"):
+        theirs = ref.fm.Flux(R.model_spec(ref, gold["tiny"], prequantized_flow=True), dtype=BF16)
+    sd = load_file(path, device="cpu")
+    missing, unexpected = theirs.load_state_dict(sd, strict=False, assign=True)
+    assert not missing and not unexpected
+    theirs = theirs.to(DEV).eval()
+    assert R.all_frozen(ref, theirs)
+    with torch.inference_mode():
+        y_ref = theirs(**inp)
+    assert maxdiff(y_ref, y) <= 2.0 ** -4
+    assert maxdiff(y_ref, gold["y_fp8"]) <= 2.0 ** -4
