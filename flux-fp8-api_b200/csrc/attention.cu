@@ -95,9 +95,15 @@ __device__ __forceinline__ void reg_dec() {
 // pipe while the softmax warps still exponentiate the second half: ~350 cycles of MMA and the first P store leave
 // the strictly serial S -> softmax -> P -> PV -> next S chain that bounds this kernel.
 // POLY (chunked path): how many of every 8 exponentials go to the FMA-pipe polynomial instead of the MUFU (2, 4 or 6).
-template <int NQ, bool TS, bool FAST = false, int SPLIT = 0, int POLY = 2>
+// EARLY (chunked path): the next step's QK product of a tile is issued as two N = 64 halves.  P(j) (bf16 pairs) only
+// occupies TMEM columns [0, 64) of the tile's S slot, so the half that lands in columns [64, 128) -- KV rows 64..127 of
+// K(j+1) -- is issued as soon as the softmax warps have pulled S(j) into registers (barrier s_cons), i.e. it runs
+// UNDER the exponentials; only the N = 64 half for columns [0, 64) still waits for PV(j) to retire.  That takes 4 of
+// the 12 N = 128 MMA-equivalents out of the strictly serial S -> softmax -> P -> PV -> QK -> S chain of a tile.
+template <int NQ, bool TS, bool FAST = false, int SPLIT = 0, int POLY = 2, bool EARLY = false>
 __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams P) {
   constexpr bool CHUNK = SPLIT != 0;
+  static_assert(!EARLY || (CHUNK && NQ == 2 && TS && FAST), "EARLY is a variant of the chunked two-tile kernel");
   static_assert(SPLIT == 0 || SPLIT == 64 || SPLIT == 96, "first hand-off: 64 or 96 KV columns");
   using C = AttnCfg<NQ, TS>;
   constexpr int KS = C::kStages;
@@ -113,7 +119,8 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
   uint64_t* p_ready = s_ready + 2;         // NQ
   uint64_t* o_done = p_ready + NQ;         // NQ
   uint64_t* p_lo = o_done + NQ;            // NQ (CHUNK: first half of P stored)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_lo + NQ);
+  uint64_t* s_cons = p_lo + NQ;            // NQ (EARLY: S(j) is in the softmax warps' registers)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_cons + NQ);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,6 +150,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
       mbar_init(&p_ready[g], 4);  // one arrive per softmax warp
       mbar_init(&o_done[g], 1);
       mbar_init(&p_lo[g], 4);
+      mbar_init(&s_cons[g], 4);
     }
     fence_mbar_init();
   }
@@ -224,6 +232,21 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
         }
         __syncwarp();
       };
+      // N = 64 half of QK: KV rows [64 half, 64 half + 64) of the K tile -> TMEM columns [64 half, +64) of the slot
+      constexpr uint32_t idesc_qk64 = make_idesc(kFmtBF16, kFmtBF16, kBQ, kBKV / 2, 0, 0);
+      auto issue_qk_half = [&](int g, int slot, int st, int half) {
+        const uint32_t d = tmem_base + slot * 128 + half * 64;
+        const uint64_t ad0 = desc_advance(q_desc0, g * kTileBytes);
+        const uint64_t bd0 = desc_advance(k_desc0, st * kTileBytes + half * (kBKV / 2) * 128);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
+            mma_f16_ss(d, desc_advance(ad0, off), desc_advance(bd0, off), idesc_qk64, kk != 0 ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      };
       auto issue_pv = [&](int g, int pslot, int st, bool first, int kk0 = 0, int kk1 = kBKV / 16) {
         const uint32_t d = tmem_base + 256 + g * 128;
         const uint64_t bd0 = desc_advance(v_desc0, st * kTileBytes);
@@ -256,6 +279,18 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
           const int st = j % KS;
           mbar_wait(&v_full[st], (j / KS) & 1);
           for (int g = 0; g < 2; ++g) {
+            if constexpr (EARLY) {
+              if (j + 1 < n) {
+                const int st1 = (j + 1) % KS;
+                if (g == 0) {
+                  mbar_wait(&k_full[st1], ((j + 1) / KS) & 1);
+                  tc_fence_after();
+                }
+                if (P.debug != 1) mbar_wait(&s_cons[g], j & 1);
+                tc_fence_after();
+                issue_qk_half(g, g, st1, 1);
+              }
+            }
             if constexpr (CHUNK) {
               if (P.debug != 1) mbar_wait(&p_lo[g], j & 1);
               tc_fence_after();
@@ -272,11 +307,15 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
             if (g == 1) commit(&v_empty[st]);
             if (j + 1 < n) {
               const int st1 = (j + 1) % KS;
-              if (g == 0) {
-                mbar_wait(&k_full[st1], ((j + 1) / KS) & 1);
-                tc_fence_after();
+              if constexpr (EARLY) {
+                issue_qk_half(g, g, st1, 0);
+              } else {
+                if (g == 0) {
+                  mbar_wait(&k_full[st1], ((j + 1) / KS) & 1);
+                  tc_fence_after();
+                }
+                issue_qk(g, g, st1);
               }
-              issue_qk(g, g, st1);
               commit(&s_ready[g]);
               if (g == 1) commit(&k_empty[st1]);
             }
@@ -354,6 +393,12 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
         tmem_ld32(lane_base + slot * 128 + 64, sv4[2]);
         tmem_ld32(lane_base + slot * 128 + 96, sv4[3]);
         tmem_ld_wait();
+      }
+      if constexpr (EARLY) {
+        // S(j) is in registers: columns [64, 128) of the slot may receive half of S(j+1) while we exponentiate
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_cons[g]);
       }
       if (dbg) { tB = clk(); d_ld += tB - tA; tA = tB; }
       const int kv_left = a.S - j * kBKV;  // columns >= kv_left are out of range (last tile only)
@@ -729,16 +774,379 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
 }
 
 
+// =====================================================================================================
+// cta_group::2 form of the default kernel: a CLUSTER OF TWO CTAs works on four query tiles of one head and shares
+// every K / V tile.  Each CTA keeps the single-CTA structure (two 128-row query tiles, S / P / O in its own TMEM, two
+// softmax warpgroups with the exponential token), but the MMAs are M = 256 instructions issued by the leader CTA over
+// the pair: tile g of CTA 0 and tile g of CTA 1 are the two M halves, and the B operand is split between the CTAs --
+// CTA r stages KV rows [64 r, 64 r + 64) of the K tile (N halves of QK) and head-dim columns [64 r, 64 r + 64) of the V
+// tile (N halves of PV).  Per MMA an SM reads 4 + 2 KB (QK) / 2 KB (PV) of shared memory instead of 8 / 4 KB -- the
+// single-CTA kernel's MMAs are bound by exactly that operand bandwidth (87-100 cycles per instruction against 64
+// nominal; splitting QK into N = 64 halves to shorten the S -> P -> PV -> S chain made the kernel 12 % SLOWER,
+// profiles/r2_attention.md) -- and the TMA fill per SM and KV tile halves (32 KB), so the ring is 3 deep.
+// Cross-CTA traffic: the leader's issuer needs P from both CTAs (remote mbarrier arrives), every commit is multicast.
+// =====================================================================================================
+struct AttnPairCfg {
+  static constexpr int kStages = 3;
+  static constexpr int kHalfBytes = kTileBytes / 2;  // one CTA's half of a K or V tile: 16 KB
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = 2 * kTileBytes;
+  static constexpr int kVOff = kKOff + kStages * kHalfBytes;
+  static constexpr int kBarOff = kVOff + kStages * kHalfBytes;
+  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr int kThreads = 384;
+};
+
+__global__ void __launch_bounds__(AttnPairCfg::kThreads, 1) attention_kernel_pair(const __grid_constant__ AttnParams P,
+                                                                                 const __grid_constant__ CUtensorMap tmap_k64) {
+  using C = AttnPairCfg;
+  constexpr int KS = C::kStages;
+  constexpr int SPLIT = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* q_full = bars;                 // leader: both CTAs' Q bytes
+  uint64_t* k_full = q_full + 1;           // KS, leader
+  uint64_t* k_empty = k_full + KS;         // KS, each CTA (multicast commit)
+  uint64_t* v_full = k_empty + KS;         // KS, leader
+  uint64_t* v_empty = v_full + KS;         // KS, each CTA
+  uint64_t* s_ready = v_empty + KS;        // 2, each CTA (multicast commit)
+  uint64_t* p_ready = s_ready + 2;         // 2, leader: 4 softmax warps x 2 CTAs
+  uint64_t* o_done = p_ready + 2;          // 2, each CTA
+  uint64_t* p_lo = o_done + 2;             // 2, leader
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_lo + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const fluxb200_attention_args& a = P.a;
+  const int q0 = (blockIdx.x >> 1) * (4 * kBQ) + rank * (2 * kBQ);  // this CTA's 256 query rows
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * a.H + h;
+  const int n = P.num_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmap_q);
+    tma_prefetch_desc(&tmap_k64);
+    tma_prefetch_desc(&P.tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_ready[g], 1);
+      mbar_init(&p_ready[g], 8);  // one arrive per softmax warp of both CTAs
+      mbar_init(&o_done[g], 1);
+      mbar_init(&p_lo[g], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_ptr, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // q, k, v come from the preceding QKV GEMMs
+
+  if (warp < 4) {
+    reg_dec<88>();
+    if (warp == 0) {
+      // ---------------- TMA producer (both CTAs; bytes are accounted on the leader's barriers) ----------------
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * 2 * kTileBytes);
+        for (int g = 0; g < 2; ++g) {
+          uint8_t* dst = smem + C::kQOff + g * kTileBytes;
+          tma_load_3d_2sm(dst, &P.tmap_q, q_full, 0, q0 + g * kBQ, bh, kEvictFirst);
+          tma_load_3d_2sm(dst + kChunkBytes, &P.tmap_q, q_full, 64, q0 + g * kBQ, bh, kEvictFirst);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < n; ++j) {
+        const int st = j % KS;
+        const uint32_t ph = (j / KS) & 1;
+        uint8_t* kd = smem + C::kKOff + st * C::kHalfBytes;   // [2 d-chunks][64 kv rows][128 B]
+        uint8_t* vd = smem + C::kVOff + st * C::kHalfBytes;   // [128 kv rows][128 B] = d columns [64 rank, +64)
+        mbar_wait(&k_empty[st], ph ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+          tma_load_3d_2sm(kd, &tmap_k64, &k_full[st], 0, j * kBKV + rank * 64, bh, kEvictLast);
+          tma_load_3d_2sm(kd + C::kHalfBytes / 2, &tmap_k64, &k_full[st], 64, j * kBKV + rank * 64, bh, kEvictLast);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], ph ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+          tma_load_3d_2sm(vd, &P.tmap_v, &v_full[st], rank * 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 && rank == 0) {
+      // ---------------- MMA issuer (leader CTA only) ----------------
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kFmtBF16, 2 * kBQ, kBKV, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kFmtBF16, 2 * kBQ, kD, 0, 1);  // V is MN-major
+      const uint64_t q_desc0 = make_desc_sw128(smem_u32(smem + C::kQOff), 16, 1024);
+      const uint64_t k_desc0 = make_desc_sw128(smem_u32(smem + C::kKOff), 16, 1024);
+      const uint64_t v_desc0 = make_desc_sw128(smem_u32(smem + C::kVOff), kChunkBytes, 1024);
+      auto commit = [&](uint64_t* bar) {  // both CTAs
+        if (elect_one()) tc_commit_2sm(bar, 3);
+        __syncwarp();
+      };
+      auto issue_qk = [&](int g, int st) {
+        const uint32_t d = tmem_base + g * 128;
+        const uint64_t ad0 = desc_advance(q_desc0, g * kTileBytes), bd0 = desc_advance(k_desc0, st * C::kHalfBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t aoff = (kk >> 2) * kChunkBytes + (kk & 3) * 32;          // Q: [2 chunks][128 rows][128 B]
+            const uint32_t boff = (kk >> 2) * (C::kHalfBytes / 2) + (kk & 3) * 32;  // K half: [2 chunks][64 rows][128 B]
+            mma_f16_ss_2sm(d, desc_advance(ad0, aoff), desc_advance(bd0, boff), idesc_qk, kk != 0 ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int g, int st, bool first, int kk0, int kk1) {
+        const uint32_t d = tmem_base + 256 + g * 128;
+        const uint64_t bd0 = desc_advance(v_desc0, st * C::kHalfBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = kk0; kk < kk1; ++kk)
+            mma_f16_ts_2sm(d, tmem_base + g * 128 + kk * 8, desc_advance(bd0, kk * 2048), idesc_pv,
+                           (!first || kk != 0) ? 1u : 0u);
+        }
+        __syncwarp();
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int g = 0; g < 2; ++g) {
+        issue_qk(g, 0);
+        commit(&s_ready[g]);
+      }
+      commit(&k_empty[0]);
+      for (int j = 0; j < n; ++j) {
+        const int st = j % KS;
+        mbar_wait(&v_full[st], (j / KS) & 1);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_lo[g], j & 1);
+          tc_fence_after();
+          issue_pv(g, st, j == 0, 0, SPLIT / 16);
+          mbar_wait(&p_ready[g], j & 1);
+          tc_fence_after();
+          issue_pv(g, st, j == 0, SPLIT / 16, kBKV / 16);
+          commit(&o_done[g]);
+          if (g == 1) commit(&v_empty[st]);
+          if (j + 1 < n) {
+            const int st1 = (j + 1) % KS;
+            if (g == 0) {
+              mbar_wait(&k_full[st1], ((j + 1) / KS) & 1);
+              tc_fence_after();
+            }
+            issue_qk(g, st1);
+            commit(&s_ready[g]);
+            if (g == 1) commit(&k_empty[st1]);
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax warpgroups (identical in both CTAs; P-ready arrives go to the leader) ----------------
+    reg_inc<208>();
+    const int g = (warp - 4) >> 2;
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int qrow = q0 + g * kBQ + r;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    const uint32_t o_taddr = lane_base + 256 + g * 128;
+    const float sl2 = P.scale_log2;
+    float m_used = -INFINITY;
+    float l = 0.f;
+    if (g == 1) named_bar_arrive(1, 256);  // hand the first exponential turn to warpgroup 0
+    for (int j = 0; j < n; ++j) {
+      if (j > 0) mbar_wait(&o_done[g], (j - 1) & 1);  // O stable, P region reusable
+      mbar_wait(&s_ready[g], j & 1);
+      tc_fence_after();
+      uint32_t sv[128];
+      {
+        uint32_t(*sv4)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+        tmem_ld32(lane_base + g * 128 + 0, sv4[0]);
+        tmem_ld32(lane_base + g * 128 + 32, sv4[1]);
+        tmem_ld32(lane_base + g * 128 + 64, sv4[2]);
+        tmem_ld32(lane_base + g * 128 + 96, sv4[3]);
+        tmem_ld_wait();
+      }
+      const int kv_left = a.S - j * kBKV;
+      if (kv_left < kBKV) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_left) sv[i] = __float_as_uint(-INFINITY);
+      }
+      float m0 = fmax3(__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]));
+      float m1 = fmax3(__uint_as_float(sv[3]), __uint_as_float(sv[4]), __uint_as_float(sv[5]));
+      float m2 = fmaxf(__uint_as_float(sv[6]), __uint_as_float(sv[7]));
+      float m3 = -INFINITY;
+#pragma unroll
+      for (int i = 8; i < 128; i += 8) {
+        m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+        m2 = fmax3(m2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+        m3 = fmax3(m3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+      }
+      const float m_cand = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+      const bool grow = m_cand > m_used + kRescaleThreshold;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_used, m_cand);
+        const float alpha = fast_exp2(m_used - m_new);  // exp2(-inf) = 0 on the first tile
+        m_used = m_new;
+        l *= alpha;
+        if (j > 0) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(o_taddr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(o_taddr + c * 32, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      named_bar_sync(1 + g, 256);  // wait for our turn
+      const float2 sl2v = make_float2(sl2, sl2), negmv = make_float2(-m_used, -m_used);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int i = hh * SPLIT; i < (hh == 0 ? SPLIT : 128); i += 8) {
+          const float2 t01 = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, negmv);
+          const float2 t23 = ffma2(make_float2(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2v, negmv);
+          const float2 t45 = ffma2(make_float2(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])), sl2v, negmv);
+          const float2 t67 = ffma2(make_float2(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])), sl2v, negmv);
+          const float p0 = fast_exp2_pinned(t01.x), p1 = fast_exp2_pinned(t01.y), p2 = fast_exp2_pinned(t23.x);
+          const float p3 = fast_exp2_pinned(t23.y), p4 = fast_exp2_pinned(t45.x), p5 = fast_exp2_pinned(t45.y);
+          const float p6 = fast_exp2_pinned(t67.x), p7 = fast_exp2_pinned(t67.y);
+          acc0 = fadd2(acc0, make_float2(p0, p1));
+          acc1 = fadd2(acc1, make_float2(p2, p3));
+          acc0 = fadd2(acc0, make_float2(p4, p5));
+          acc1 = fadd2(acc1, make_float2(p6, p7));
+          sv[i >> 1] = pack_bf16x2(p0, p1);
+          sv[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          sv[(i >> 1) + 2] = pack_bf16x2(p4, p5);
+          sv[(i >> 1) + 3] = pack_bf16x2(p6, p7);
+        }
+        uint32_t(*pk)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+        tmem_st32(lane_base + g * 128 + hh * 32, pk[hh]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(hh == 0 ? &p_lo[g] : &p_ready[g], 0);  // the leader's barrier
+      }
+      named_bar_arrive(1 + (g ^ 1), 256);  // pass the turn
+      const float2 acc = fadd2(acc0, acc1);
+      l += acc.x + acc.y;
+    }
+
+    // ---------------- epilogue: O / l -> bf16 -> (optional) fp8 ----------------
+    mbar_wait(&o_done[g], (n - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const bool valid = qrow < a.S;
+    const bool second = a.out1 != nullptr && qrow >= a.split_row;
+    void* const outp = second ? a.out1 : a.out;
+    const int64_t obase = second ? static_cast<int64_t>(b) * a.out1_batch_stride +
+                                       static_cast<int64_t>(qrow - a.split_row) * a.ldo1 + h * kD
+                                 : static_cast<int64_t>(b) * a.out_batch_stride + static_cast<int64_t>(qrow) * a.ldo + h * kD;
+    float oscale = 1.f;
+    if (a.out_kind == 1) oscale = __ldg(qrow < a.split_row ? a.out_scale0 : a.out_scale1);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t ov[32];
+      tmem_ld32(o_taddr + c * 32, ov);
+      tmem_ld_wait();
+      if (!valid) continue;
+      if (a.out_kind == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + obase + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(ov[q * 8 + 0]) * inv_l, __uint_as_float(ov[q * 8 + 1]) * inv_l);
+          o.y = pack_bf16x2(__uint_as_float(ov[q * 8 + 2]) * inv_l, __uint_as_float(ov[q * 8 + 3]) * inv_l);
+          o.z = pack_bf16x2(__uint_as_float(ov[q * 8 + 4]) * inv_l, __uint_as_float(ov[q * 8 + 5]) * inv_l);
+          o.w = pack_bf16x2(__uint_as_float(ov[q * 8 + 6]) * inv_l, __uint_as_float(ov[q * 8 + 7]) * inv_l);
+          dst[q] = o;
+        }
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(outp) + obase + c * 32);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float o = bf16r(__uint_as_float(ov[q * 16 + t * 4 + e]) * inv_l);
+              f[e] = a.out_fmt == FLUXB200_E5M2 ? quant_pre<1>(o, oscale) : quant_pre<0>(o, oscale);
+            }
+            if (a.out_fmt == FLUXB200_E5M2)
+              w[t] = to_fp8x2<1>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<1>(f[2], f[3])) << 16);
+            else
+              w[t] = to_fp8x2<0>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<0>(f[2], f[3])) << 16);
+          }
+          dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  pdl_launch_dependents();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+static int launch_attention_pair(const AttnParams& P, cudaStream_t stream) {
+  using C = AttnPairCfg;
+  static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
+  static bool attr_set = false;
+  if (!attr_set) {
+    FB_CUDA_OK(cudaFuncSetAttribute(attention_kernel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+    attr_set = true;
+  }
+  const fluxb200_attention_args& a = P.a;
+  CUtensorMap tmap_k64;
+  const uint64_t bhn = static_cast<uint64_t>(a.B) * a.H;
+  const uint64_t row_bytes = kD * 2;
+  int rc = make_tmap_3d(&tmap_k64, a.k, 2, kD, a.S, bhn, row_bytes, row_bytes * a.S, 64, kBKV / 2, 1);
+  if (rc) return rc;
+  dim3 grid(2 * ((a.S + 4 * kBQ - 1) / (4 * kBQ)), a.H, a.B);
+  FB_CUDA_OK(launch_kernel(attention_kernel_pair, grid, dim3(C::kThreads), C::kTotal, stream, 2, P, tmap_k64));
+  return 0;
+}
+
 #ifdef FLUXB200_ATTN_EXPERIMENTS
 #include "experiments/attention_variants.cuh"
 #endif
 
-template <int NQ, bool TS, bool FAST = false, int SPLIT = 0, int POLY = 2>
+template <int NQ, bool TS, bool FAST = false, int SPLIT = 0, int POLY = 2, bool EARLY = false>
 static int launch_attention(const AttnParams& P, cudaStream_t stream) {
   using C = AttnCfg<NQ, TS>;
   static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
   static bool attr_set = false;
-  auto kern = attention_kernel<NQ, TS, FAST, SPLIT, POLY>;
+  auto kern = attention_kernel<NQ, TS, FAST, SPLIT, POLY, EARLY>;
   if (!attr_set) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     attr_set = true;
@@ -790,7 +1198,25 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
 
   // The product library ships ONE attention kernel: 2 query tiles per CTA, P through TMEM, packed-fp32 softmax with
   // every exponential on the MUFU, P handed to the issuer in two 64-column halves.
-  if (a.variant == 0) return launch_attention<2, true, true, 64, 0>(P, stream);
+  // variant 0 = the library's choice between the two product kernels (same arithmetic, bit-identical results):
+  //   single  one CTA = two query tiles                                     (variant 17 forces it)
+  //   pair    a cluster of two CTAs = four query tiles sharing K / V tiles   (variant 16 forces it)
+  // The pair form wins once a head has enough KV tiles to amortise its cluster set-up (measured: -1.5 % at S = 4608,
+  // -3.5 % at S = 9728, +2 % at S = 2816; profiles/r2_attention.md).  FLUXB200_ATTN_PAIR=0|1 overrides.
+  if (a.variant == 0 || a.variant == 16 || a.variant == 17) {
+    static const int forced = [] {
+      const char* e = getenv("FLUXB200_ATTN_PAIR");
+      return e ? atoi(e) : -1;
+    }();
+    bool pair = a.S >= 4096;
+    if (forced >= 0) pair = forced != 0;
+    if (a.variant == 16) pair = true;
+    if (a.variant == 17) pair = false;
+    return pair ? launch_attention_pair(P, stream) : launch_attention<2, true, true, 64, 0>(P, stream);
+  }
+#ifdef FLUXB200_ATTN_EXPERIMENTS
+  if (a.variant == 15) return launch_attention<2, true, true, 64, 0, true>(P, stream);  // + early half-QK: 12 % slower
+#endif
 #ifdef FLUXB200_ATTN_EXPERIMENTS
   switch (a.variant) {
     case 7: return launch_attention<2, true, true>(P, stream);  // one whole-tile P hand-off, max fused into the exp pass

@@ -274,6 +274,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+                                                int32_t c2, uint64_t hint = kEvictNormal) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+
 // 2-SM form with cluster multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each
 // destination signals the transaction bytes on the barrier (same offset) of ITS pair's leader CTA.
 __device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
@@ -455,6 +464,29 @@ __device__ __forceinline__ void mma_f16_ss_c(uint32_t d_tmem, uint64_t a_desc, u
     asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
                  "l"(a_desc), "l"(b_desc), "r"(idesc)
                  : "memory");
+}
+// cta_group::2 forms (M = 256 over the SM pair; issued by the leader CTA)
+__device__ __forceinline__ void mma_f16_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // A operand from tensor memory (TS form).
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,

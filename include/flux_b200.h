@@ -259,7 +259,9 @@ typedef struct fluxb200_attention_args {
   int32_t out_kind;
   int32_t out_fmt;
   int32_t split_row;
-  int32_t variant; /* must be 0 (non-zero values exist only in -DFLUXB200_ATTN_EXPERIMENTS builds) */
+  int32_t variant; /* 0 = the library chooses between its two kernels (bit-identical results): 17 forces the single-CTA
+                      form, 16 the cta_group::2 pair form (A/B measurements, tests); other values exist only in
+                      -DFLUXB200_ATTN_EXPERIMENTS builds */
   const float* out_scale0;
   const float* out_scale1;
   /* Optional second destination: when out1 != NULL, rows s >= split_row are written to

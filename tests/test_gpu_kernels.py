@@ -480,3 +480,30 @@ def test_bf16_gemm_small_and_fused_euler(ops, M, N, K):
     if xs.stride(-2) % 8 == 0:
         assert torch.equal(ops.bf16_gemm_small(xs, w, b), ops.bf16_gemm_small(xs.contiguous(), w, b))
         ulp_check(ops.bf16_gemm_small(xs, w, b), F.linear(xs.contiguous(), w, b), ulps=1, frac=0.05)
+
+
+@pytest.mark.parametrize("B,H,S,T", [(1, 24, 4608, 512), (2, 3, 1000, 100), (1, 2, 513, 0), (1, 1, 129, 64), (1, 2, 4352, 256),
+                                     (1, 1, 1, 0)])
+def test_attention_pair_kernel_is_bit_identical_to_the_single_cta_kernel(ops, B, H, S, T):
+    """The cta_group::2 form (a cluster of two CTAs sharing every K / V tile; the library's choice for S >= 4096) and the
+    single-CTA form run the same arithmetic in the same order: bf16 output, ragged sequence lengths (last pair half empty,
+    last KV tile partial) and the fp8 two-destination epilogue of the double blocks agree bit for bit."""
+    from flux_fp8_api_b200.f8linear import mul_scale
+
+    g = gen(100 + S)
+    q = (torch.randn(B, H, S, 128, device=DEV, generator=g) * 1.5).to(BF16)
+    k = (torch.randn(B, H, S, 128, device=DEV, generator=g) * 1.5).to(BF16)
+    v = torch.randn(B, H, S, 128, device=DEV, generator=g).to(BF16)
+    single = ops.attention(q, k, v, variant=17)
+    pair = ops.attention(q, k, v, variant=16)
+    assert torch.isfinite(pair.float()).all() and torch.equal(pair, single)
+    if T:
+        s0, s1 = mul_scale(scalar(2048.0)), mul_scale(scalar(6000.0))
+        outs = []
+        for var in (17, 16):
+            o_txt = torch.zeros(B, T, H * 128, dtype=E5M2, device=DEV)
+            o_img = torch.zeros(B, S - T, H * 128, dtype=E5M2, device=DEV)
+            ops.attention(q, k, v, out=o_txt, out_scale0=s0, out_scale1=s1, split_row=T, out1=o_img, variant=var)
+            outs.append((o_txt, o_img))
+        assert torch.equal(outs[0][0].view(torch.uint8), outs[1][0].view(torch.uint8))
+        assert torch.equal(outs[0][1].view(torch.uint8), outs[1][1].view(torch.uint8))
