@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflux_b200.so")
+#: FLUXB200_LIB points measurements at an alternative build of the library (A/B runs); the product uses the in-tree one
+LIB_PATH = os.environ.get("FLUXB200_LIB") or os.path.join(_HERE, "libflux_b200.so")
 
 E4M3, E5M2 = 0, 1
 EPI_PLAIN, EPI_GATE_RESIDUAL, EPI_GELU_QUANT, EPI_QKV_ROPE, EPI_LINEAR1 = 0, 1, 2, 3, 4

@@ -786,8 +786,11 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
 // profiles/r2_attention.md) -- and the TMA fill per SM and KV tile halves (32 KB), so the ring is 3 deep.
 // Cross-CTA traffic: the leader's issuer needs P from both CTAs (remote mbarrier arrives), every commit is multicast.
 // =====================================================================================================
+#ifndef FLUXB200_ATTN_PAIR_STAGES
+#define FLUXB200_ATTN_PAIR_STAGES 3
+#endif
 struct AttnPairCfg {
-  static constexpr int kStages = 3;
+  static constexpr int kStages = FLUXB200_ATTN_PAIR_STAGES;
   static constexpr int kHalfBytes = kTileBytes / 2;  // one CTA's half of a K or V tile: 16 KB
   static constexpr int kQOff = 0;
   static constexpr int kKOff = 2 * kTileBytes;
