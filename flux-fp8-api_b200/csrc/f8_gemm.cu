@@ -138,9 +138,13 @@ __device__ __forceinline__ void dequant_bias(const uint32_t (&v)[32], float s, c
       uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float2 bf = unpack_bf16x2(w[t]);
-        y[q * 8 + t * 2 + 0] = bf16r(fmaf(__uint_as_float(v[q * 8 + t * 2 + 0]), s, bf.x));
-        y[q * 8 + t * 2 + 1] = bf16r(fmaf(__uint_as_float(v[q * 8 + t * 2 + 1]), s, bf.y));
+        const float2 bf = unpack_bf16x2(w[t]);
+        const float2 f = ffma2(make_float2(__uint_as_float(v[q * 8 + t * 2 + 0]), __uint_as_float(v[q * 8 + t * 2 + 1])),
+                               make_float2(s, s), bf);
+        // one F2FP rounds the pair to bf16; the halves are the two rounded values as fp32 bit patterns
+        const uint32_t pk = pack_bf16x2(f.x, f.y);
+        y[q * 8 + t * 2 + 0] = __uint_as_float(pk << 16);
+        y[q * 8 + t * 2 + 1] = __uint_as_float(pk & 0xffff0000u);
       }
     }
   } else {
@@ -161,9 +165,10 @@ __device__ __forceinline__ void dequant_bias_packed(const uint32_t (&v)[32], flo
       uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float2 bf = unpack_bf16x2(w[t]);
-        yp[q * 4 + t] = pack_bf16x2(fmaf(__uint_as_float(v[q * 8 + t * 2 + 0]), s, bf.x),
-                                    fmaf(__uint_as_float(v[q * 8 + t * 2 + 1]), s, bf.y));
+        const float2 bf = unpack_bf16x2(w[t]);
+        const float2 f = ffma2(make_float2(__uint_as_float(v[q * 8 + t * 2 + 0]), __uint_as_float(v[q * 8 + t * 2 + 1])),
+                               make_float2(s, s), bf);
+        yp[q * 4 + t] = pack_bf16x2(f.x, f.y);
       }
     }
   } else {
@@ -275,8 +280,9 @@ __device__ __forceinline__ void gelu_quant_store(uint8_t* dst, float oscale, boo
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const int j = t * 4;
-      w[t] = static_cast<uint32_t>(quant_pair_bf16scale<FMT>(gelu_tanh_fast(y[j]), gelu_tanh_fast(y[j + 1]), s2)) |
-             (static_cast<uint32_t>(quant_pair_bf16scale<FMT>(gelu_tanh_fast(y[j + 2]), gelu_tanh_fast(y[j + 3]), s2)) << 16);
+      const float2 g01 = gelu_tanh_fast2(make_float2(y[j], y[j + 1])), g23 = gelu_tanh_fast2(make_float2(y[j + 2], y[j + 3]));
+      w[t] = static_cast<uint32_t>(quant_pair_bf16scale<FMT>(g01.x, g01.y, s2)) |
+             (static_cast<uint32_t>(quant_pair_bf16scale<FMT>(g23.x, g23.y, s2)) << 16);
     }
     if (wide) {
       stg_v8(dst, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);

@@ -118,6 +118,16 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
   return d;
 }
 
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // Register re-partitioning between warpgroups (all four warps of a warpgroup execute it together).
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
@@ -607,6 +617,17 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float w = fmaf(x * x, kC1, kC0);
   const float e = exp2f_approx(x * w);
   return x * rcp_approx(1.f + e);
+}
+// The same on a pair with packed fp32 arithmetic (FMUL2 / FFMA2 / FADD2: each half rounds exactly like the scalar
+// instruction, so the result is bit-identical to two gelu_tanh_fast calls; 5 packed + 4 MUFU instructions per pair
+// instead of 10 + 4).
+__device__ __forceinline__ float2 gelu_tanh_fast2(float2 x) {
+  constexpr float kC0 = -2.f * 1.4426950408889634f * 0.7978845608028654f;
+  constexpr float kC1 = kC0 * 0.044715f;
+  const float2 w = ffma2(fmul2(x, x), make_float2(kC1, kC1), make_float2(kC0, kC0));
+  const float2 u = fmul2(x, w);
+  const float2 d = fadd2(make_float2(1.f, 1.f), make_float2(exp2f_approx(u.x), exp2f_approx(u.y)));
+  return fmul2(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
 }
 // nn.GELU(approximate="tanh") evaluated in fp32 (ATen opmath) on a bf16-exact input.
 __device__ __forceinline__ float gelu_tanh(float x) {
