@@ -275,6 +275,9 @@ def pick_threads(run, budget_s=40.0):
 def cpu_reference_measure(cfg, steps, warmup, tune=True):
     run, kind = cpu_sample_reference(cfg)
     threads = os.cpu_count() or 1
+    fixed = os.environ.get("FLUXB200_BENCH_THREADS")  # pin the pool size (skips the search)
+    if fixed:
+        threads, tune = max(1, min(int(fixed), threads)), False
     torch.set_num_threads(threads)
     if tune:
         threads, _ = pick_threads(run)

@@ -279,7 +279,9 @@ _grid_barrier_ws = {}
 def grid_barrier_ws(device) -> Tensor:
     """The two self-re-arming words of the fused LN -> GEMM launches' grid barrier: one pair per (device, stream) --
     launches that share a pair must be stream-ordered (include/flux_b200.h, fluxb200_f8_gemm_ln)."""
-    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(device).cuda_stream)
     ws = _grid_barrier_ws.get(key)
     if ws is None:
         with torch.cuda.stream(torch.cuda.default_stream(device)):

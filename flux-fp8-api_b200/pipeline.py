@@ -12,6 +12,7 @@ The reference's FluxPipeline.generate keeps the loop in Python and this stays so
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Callable, Dict, List, Optional
 
@@ -302,18 +303,19 @@ class GraphedStep:
 
         dev = self.img.device
         self.cache = _StepInvariantCache()  # strong references to everything step-invariant the kernels read
-        self.epoch = self.model._invariant_epoch
+        self.epoch = getattr(self.model, "_invariant_epoch", 0)
         keep = self.img.clone()
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(stream), torch.inference_mode(), self.model.use_request_cache(self.cache):
+        private = self.model.use_request_cache(self.cache) if hasattr(self.model, "use_request_cache") else contextlib.nullcontext()
+        with torch.cuda.stream(stream), torch.inference_mode(), private:
             for _ in range(self.warmup):
                 self._step()
                 self.img.copy_(keep)
         torch.cuda.current_stream(dev).wait_stream(stream)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.inference_mode(), self.model.use_request_cache(self.cache), \
-                torch.cuda.graph(self.graph, stream=stream):
+        private = self.model.use_request_cache(self.cache) if hasattr(self.model, "use_request_cache") else contextlib.nullcontext()
+        with torch.inference_mode(), private, torch.cuda.graph(self.graph, stream=stream):
             self._step()
         self.img.copy_(keep)
         self.captures += 1
@@ -323,8 +325,16 @@ class GraphedStep:
         self.t_vec.copy_(self.scal[0].expand_as(self.t_vec))  # exact: scal[0] already holds a bf16 value
         # img + (t_prev - t_curr) * pred: eager torch multiplies in fp32 by the python scalar, rounds the product to
         # bf16, then adds in bf16 -- done inside the final projection's launch with the fp32 0-dim `dt`
-        self.model.denoise_step(img=self.img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
-                                timesteps=self.t_vec, guidance=r.get("guidance"), dt=self.scal[1], out=self.out)
+        if hasattr(self.model, "denoise_step"):
+            self.model.denoise_step(img=self.img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
+                                    timesteps=self.t_vec, guidance=r.get("guidance"), dt=self.scal[1], out=self.out)
+        else:  # another container over the B200 blocks (e.g. the reference's own Flux, reference_binding replace_container=False)
+            pred = self.model(img=self.img, img_ids=r["img_ids"], txt=r["txt"], txt_ids=r["txt_ids"], y=r["y"],
+                              timesteps=self.t_vec, guidance=r.get("guidance"))
+            if pred.dtype == BF16:
+                ops.euler_update(self.img, pred, self.scal[1], out=self.out)
+            else:
+                self.out.copy_(self.img + (self.scal[1] * pred.float()).to(pred.dtype))
         self.img.copy_(self.out)  # the next step's input, unless the caller supplies another latent
 
     @staticmethod
@@ -334,7 +344,7 @@ class GraphedStep:
     def advance(self, t_curr: float, dt: float, latent: Optional[Tensor] = None, clone: bool = True) -> Tensor:
         """One step from the latent held in the static buffer (or `latent`, copied in first).  With clone=False the
         returned tensor IS the static output buffer: valid until the next call."""
-        if self.epoch != self.model._invariant_epoch:
+        if self.epoch != getattr(self.model, "_invariant_epoch", 0):
             self._capture()
         if latent is not None and latent is not self.out:
             self.img.copy_(latent)
@@ -347,7 +357,7 @@ class GraphedStep:
 
     def __call__(self, img: Tensor, t_vec: Tensor, dt: float, clone: bool = True) -> Tensor:
         """denoise(step_fn=...) signature: t_vec is the reference's filled bf16 timestep vector."""
-        if self.epoch != self.model._invariant_epoch:
+        if self.epoch != getattr(self.model, "_invariant_epoch", 0):
             self._capture()
         if img is not self.out:
             self.img.copy_(img)

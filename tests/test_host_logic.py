@@ -186,3 +186,34 @@ def test_lora_operands_reproduce_the_reference_delta(golden_dir):
         lora.lora_operands((torch.ones(5, 4), torch.ones(3, 2), None), None, "cpu")   # 5 rows do not chain with rank 2
     with pytest.raises(FileNotFoundError):   # a path is loaded as a BFL-layout .safetensors file
         lora.apply_lora_to_model(torch.nn.Linear(2, 2), "some/file.safetensors")
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the contract's keys, the
+    reference's own modules when oracle/_ref is staged, --steps / --warmup honoured, config identical to our arm's."""
+    import json
+    import subprocess
+    import sys
+
+    import bench
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FLUXB200_BENCH_THREADS=str(min(8, os.cpu_count() or 1)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "c4",
+                          "--steps", "2", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 0
+    assert line["metric"] == bench.metric_name(bench.CONFIGS["c4"]) and line["unit"] == "it/s" and line["higher_is_better"]
+    assert line["config"] == bench.config_block(bench.CONFIGS["c4"], "c4", 1)
+    cb = line["cpu_baseline"]
+    assert cb["value"] == line["value"] and cb["cores"] >= 1 and cb["kind"] in ("reference", "port")
+    from oracle import ref_loader as R
+
+    assert cb["kind"] == ("reference" if R.available() else "port")
+    assert line["e2e"] == {"value": line["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(line["value"] - 1000.0 / (19.0 * line["ms_per_step"])) < 1e-9 * line["value"] + 1e-12
+    # work accounting used by our arm
+    f8, attn, mod = bench.algorithmic_flops(bench.CONFIGS["c2"])
+    assert abs(f8 - (1.29101e10 * 4608 + 6.456e9)) < 1 and abs(attn - 700416.0 * 4608 ** 2) < 1 and mod == 0.0
+    assert bench.algorithmic_flops(bench.CONFIGS["c5"])[2] == 6.456e9

@@ -143,6 +143,14 @@ def test_reference_forward_over_b200_blocks_matches_our_flux_and_the_golden(boun
             b2 = theirs(**{**inp, "img_ids": ids2})
             assert torch.equal(a1, a2) and torch.equal(b1, b2) and not torch.equal(a1, b1)
         assert (y_ours.float().cpu() - gold["y_fp8"].float()).abs().max().item() <= 2.0 ** -4
+        # the reference container also runs under the CUDA-graph session (it has no denoise_step / request cache)
+        from flux_fp8_api_b200 import pipeline as PL
+
+        req = {k: v for k, v in inp.items() if k != "timesteps"}
+        sched = PL.get_schedule(3, req["img"].shape[1])
+        g = PL.DenoiseSession(theirs, req, use_graph=True).run(sched)
+        e = PL.DenoiseSession(theirs, req, use_graph=False).run(sched)
+        assert torch.isfinite(g.float()).all() and torch.equal(g, e)
     finally:
         f8.SCALE_SEMANTICS = "cuda"
 
