@@ -217,3 +217,59 @@ def test_bench_reference_arm_prints_the_contract_line():
     f8, attn, mod = bench.algorithmic_flops(bench.CONFIGS["c2"])
     assert abs(f8 - (1.29101e10 * 4608 + 6.456e9)) < 1 and abs(attn - 700416.0 * 4608 ** 2) < 1 and mod == 0.0
     assert bench.algorithmic_flops(bench.CONFIGS["c5"])[2] == 6.456e9
+
+
+def test_flux_from_pretrained_and_lora_bookkeeping(tmp_path, golden_dir):
+    """Flux.from_pretrained (reference modules/flux_model.py:718-734): a JSON spec whose ckpt_path names a safetensors
+    state dict -- bf16 master weights and a prequantised flow -- comes back on the CPU with the same keys and values
+    (meta-device construction + load_state_dict(assign=True)); get_lora / has_lora follow the reference's bookkeeping."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from flux_fp8_api_b200 import lora as L, model as M
+
+    gold = torch.load(os.path.join(golden_dir, "flux_tiny.pt"))
+    # (1) prequantised flow: the reference-minted golden state
+    ckpt = str(tmp_path / "tiny.f8.safetensors")
+    save_file({k: v.contiguous() for k, v in gold["state"].items()}, ckpt)
+    cfg = tmp_path / "tiny.json"
+    cfg.write_text(json.dumps({"params": gold["tiny"], "prequantized_flow": True, "ckpt_path": ckpt,
+                               "version": "flux-dev", "flow_dtype": "bfloat16"}))   # extra reference fields are ignored
+    net = M.Flux.from_pretrained(str(cfg), dtype=torch.bfloat16)
+    sd = net.state_dict()
+    assert set(sd) == set(gold["state"])
+    for k, v in gold["state"].items():
+        assert sd[k].dtype == v.dtype and sd[k].device.type == "cpu"
+        a, b = (sd[k].view(torch.uint8), v.view(torch.uint8)) if v.dtype.itemsize == 1 else (sd[k], v)
+        assert torch.equal(a, b), k
+    lin = net.double_blocks[0].img_attn.qkv
+    assert lin.frozen and lin.float8_data.dtype == torch.float8_e4m3fn
+    # (2) un-quantised bf16 flow
+    with torch.device("cpu"):
+        ref = M.Flux(M.FluxSpec(params=M.FluxParams(**gold["tiny"])), dtype=torch.bfloat16).to(torch.bfloat16)
+    ckpt2 = str(tmp_path / "tiny.bf16.safetensors")
+    save_file({k: v.contiguous() for k, v in ref.state_dict().items()}, ckpt2)
+    cfg2 = tmp_path / "tiny_bf16.json"
+    cfg2.write_text(json.dumps({"params": gold["tiny"], "prequantized_flow": False, "ckpt_path": ckpt2}))
+    net2 = M.Flux.from_pretrained(str(cfg2), dtype=torch.bfloat16)
+    assert all(torch.equal(v, ref.state_dict()[k]) for k, v in net2.state_dict().items())
+    with pytest.raises(ValueError):
+        M.Flux.from_pretrained(str(tmp_path / "missing.json"))
+    # LoRA bookkeeping (no device work): identifiers resolve by path or name, as in the reference
+    net.loras.append(L.LoraWeights({}, "/x/style.safetensors", None, 0.7))
+    assert net.has_lora("style.safetensors") and net.get_lora("/x/style.safetensors").scale == 0.7
+    assert not net.has_lora("other") and net.get_lora("other") is None
+    assert net.unload_lora("other") is False
+
+
+def test_dispatch_predicates_refuse_what_the_kernels_cannot_take():
+    """The own-kernel paths of the embedders / final layer are taken only for plain bf16 CUDA linears of supported
+    shapes; everything else (CPU tensors, fp32 layers, F8Linear embedders, K % 32 != 0) stays on the generic path."""
+    from flux_fp8_api_b200 import model as M
+
+    lin = torch.nn.Linear(64, 32).to(torch.bfloat16)
+    x = torch.zeros(2, 64, dtype=torch.bfloat16)
+    assert not M._skinny_bf16(x, lin) and not M._small_bf16_linear(x, lin)          # CPU tensors
+    assert not M._skinny_bf16(torch.zeros(2, 64), torch.nn.Linear(64, 32))             # fp32
+    assert not M._small_bf16_linear(torch.zeros(2, 48, dtype=torch.bfloat16), torch.nn.Linear(48, 32).to(torch.bfloat16))
