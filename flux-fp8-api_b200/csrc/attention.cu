@@ -54,6 +54,14 @@ struct AttnParams {
 // Phase timing (cycles) of CTA (0,0,0): [0..7] softmax warpgroup 0 / warp 4 lane 0, [8..15] MMA issuer.
 // Read back with fluxb200_debug_counters(); negligible cost (one predicated thread per role).
 __device__ unsigned long long g_attn_dbg[16];
+#ifdef FLUXB200_ATTN_PROBE
+// Event trace of CTA (0,0,0) of the step-interleaved kernel: [role 0 issuer, 1 / 2 softmax warpgroups][step < 24][event < 8]
+__device__ unsigned long long g_attn_trace[3 * 24 * 8];
+#define FB_TRACE(on, role, j, ev) \
+  do { if ((on) && (j) < 24) g_attn_trace[((role) * 24 + (j)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define FB_TRACE(on, role, j, ev) do { } while (0)
+#endif
 __device__ __forceinline__ unsigned long long clk() { return clock64(); }
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -1218,6 +1226,8 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
     return pair ? launch_attention_pair(P, stream) : launch_attention<2, true, true, 64, 0>(P, stream);
   }
 #ifdef FLUXB200_ATTN_EXPERIMENTS
+  if (a.variant == 18) return launch_attention_step<true>(P, stream);  // step-interleaved pair kernel
+  if (a.variant == 19) return launch_attention_step<false>(P, stream);  // ... without the exclusive exp turns
   if (a.variant == 15) return launch_attention<2, true, true, 64, 0, true>(P, stream);  // + early half-QK: 12 % slower
 #endif
 #ifdef FLUXB200_ATTN_EXPERIMENTS
@@ -1244,6 +1254,13 @@ extern "C" int fluxb200_attention(const fluxb200_attention_args* args, fluxb200_
 }
 
 // Diagnostics: copies the 16 phase counters of the last attention launch (CTA 0) to host memory.
+#ifdef FLUXB200_ATTN_PROBE
+extern "C" int fluxb200_debug_trace(unsigned long long* host_out576) {
+  FB_CUDA_OK(cudaDeviceSynchronize());
+  FB_CUDA_OK(cudaMemcpyFromSymbol(host_out576, fb::g_attn_trace, sizeof(unsigned long long) * 576));
+  return 0;
+}
+#endif
 extern "C" int fluxb200_debug_counters(unsigned long long* host_out16) {
   FB_CUDA_OK(cudaDeviceSynchronize());
   FB_CUDA_OK(cudaMemcpyFromSymbol(host_out16, fb::g_attn_dbg, sizeof(unsigned long long) * 16));

@@ -7,6 +7,9 @@
 //   9  attention_kernel_wide     8 softmax warps per query tile (640 threads)
 //   12 attention_kernel_one      1 query tile per CTA, 8 softmax warps, S double-buffered
 //   14 attention_kernel_coop     both tiles' softmax split over all 8 softmax warps
+//   18 attention_kernel_step     (round 2, end of file) cta_group::2, ONE query tile per CTA, the two softmax warpgroups
+//                                take alternate KV steps, S / P double-buffered separately, two MMA-issuing threads;
+//                                19 = the same without the exclusive exponential turns (profiles/r2_attention.md)
 #pragma once
 
 // =====================================================================================================
@@ -1950,4 +1953,448 @@ static int launch_attention_one(const AttnParams& P, cudaStream_t stream) {
   return 0;
 }
 
+// =====================================================================================================
+// "Step-interleaved" cta_group::2 kernel: ONE 128-row query tile per CTA (a cluster of two CTAs = 256 query rows of one
+// head sharing every K / V tile), and the two softmax warpgroups of a CTA work on ALTERNATE KV STEPS of that tile
+// instead of on two different tiles.  TMEM then has room for S and P double-buffered SEPARATELY:
+//     S[0] S[1] (2 x 128 columns, step parity)   P[0] P[1] (2 x 64)   O (128)   = 512 columns
+// so P(j) no longer lives on top of S(j) and the serial chain  S -> softmax -> P -> PV -> QK -> S  of the two-tile kernels
+// disappears: QK(j+2) is issued right after PV(j) into the slot whose S(j) is already in registers, S(j+1) has been
+// waiting since step j-1, and warpgroup (j+1)&1 exponentiates step j+1 while warpgroup j&1 is still storing P(j).  The MUFU
+// sees two warps per sub-partition in different phases (no exclusive turns), the tensor pipe is only ever waiting for P.
+// Online-softmax state crosses warpgroups: step j needs the reference maximum of step j-1, published per row through
+// shared memory (m_pub) with a one-directional named-barrier hand-off; each warpgroup keeps its own partial row sum in
+// the units of the maximum it last used; whoever raises the maximum rescales O (after PV(j-1) has retired and before
+// it releases P(j)).  The epilogue splits the head dimension between the warpgroups.
+// =====================================================================================================
+struct AttnStepCfg {
+  static constexpr int kKStages = 6;  // K runs three steps ahead of V (QK(j+3) is issued before PV(j))
+  static constexpr int kVStages = 4;
+  static constexpr int kHalfBytes = kTileBytes / 2;  // one CTA's half of a K or V tile: 16 KB
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = kTileBytes;
+  static constexpr int kVOff = kKOff + kKStages * kHalfBytes;
+  static constexpr int kBarOff = kVOff + kVStages * kHalfBytes;
+  static constexpr int kPubOff = kBarOff + 512;                 // m_pub[2][128] + l_pub[2][128] + mfin[2][128] fp32
+  static constexpr int kTotal = kPubOff + 6 * kBQ * 4 + 1024;
+  static constexpr int kThreads = 384;
+};
+
+template <bool TURN>
+__global__ void __launch_bounds__(AttnStepCfg::kThreads, 1) attention_kernel_step(const __grid_constant__ AttnParams P,
+                                                                                 const __grid_constant__ CUtensorMap tmap_k64) {
+  using C = AttnStepCfg;
+  constexpr int KK = C::kKStages, KV = C::kVStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* q_full = bars;                 // leader
+  uint64_t* k_full = q_full + 1;           // KK, leader
+  uint64_t* k_empty = k_full + KK;         // KK, each CTA
+  uint64_t* v_full = k_empty + KK;         // KV, leader
+  uint64_t* v_empty = v_full + KV;         // KV, each CTA
+  uint64_t* s_ready = v_empty + KV;        // 2 (S slot = step parity), each CTA
+  uint64_t* p_ready = s_ready + 2;         // 2, leader: 4 warps x 2 CTAs
+  uint64_t* p_lo = p_ready + 2;            // 2, leader
+  uint64_t* o_done = p_lo + 2;             // 2 (step parity), each CTA
+  uint64_t* s_free = o_done + 2;           // 2, leader: S slot read into registers by 4 warps x 2 CTAs
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + 2);
+  float* m_pub = reinterpret_cast<float*>(smem + C::kPubOff);  // [2][128]
+  float* l_pub = m_pub + 2 * kBQ;                              // [2][128] (final exchange)
+  float* mf_pub = l_pub + 2 * kBQ;                             // [2][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const fluxb200_attention_args& a = P.a;
+  const int q0 = (blockIdx.x >> 1) * (2 * kBQ) + rank * kBQ;  // this CTA's 128 query rows
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * a.H + h;
+  const int n = P.num_kv_tiles;
+  constexpr uint32_t kSCol = 0, kPCol = 256, kOCol = 384;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tmap_q);
+    tma_prefetch_desc(&tmap_k64);
+    tma_prefetch_desc(&P.tmap_v);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KK; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < KV; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(&s_ready[w], 1);
+      mbar_init(&p_ready[w], 8);
+      mbar_init(&p_lo[w], 8);
+      mbar_init(&o_done[w], 1);
+      mbar_init(&s_free[w], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_ptr, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp < 4) {
+    reg_dec<88>();
+    if (warp == 0) {
+      // ---------------- TMA producer ----------------
+      if (elect_one()) {
+        if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+        uint8_t* dst = smem + C::kQOff;
+        tma_load_3d_2sm(dst, &P.tmap_q, q_full, 0, q0, bh, kEvictFirst);
+        tma_load_3d_2sm(dst + kChunkBytes, &P.tmap_q, q_full, 64, q0, bh, kEvictFirst);
+      }
+      __syncwarp();
+      // load order = the issuer's consumption order: K(0) K(1) K(2), then K(j+3) V(j) for every step j
+      auto load_k = [&](int i) {
+        const int st = i % KK;
+        uint8_t* kd = smem + C::kKOff + st * C::kHalfBytes;
+        mbar_wait(&k_empty[st], ((i / KK) & 1) ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&k_full[st], kTileBytes);
+          tma_load_3d_2sm(kd, &tmap_k64, &k_full[st], 0, i * kBKV + rank * 64, bh, kEvictLast);
+          tma_load_3d_2sm(kd + C::kHalfBytes / 2, &tmap_k64, &k_full[st], 64, i * kBKV + rank * 64, bh, kEvictLast);
+        }
+        __syncwarp();
+      };
+      for (int i = 0; i < 3 && i < n; ++i) load_k(i);
+      for (int j = 0; j < n; ++j) {
+        if (j + 3 < n) load_k(j + 3);
+        const int st = j % KV;
+        uint8_t* vd = smem + C::kVOff + st * C::kHalfBytes;
+        mbar_wait(&v_empty[st], ((j / KV) & 1) ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&v_full[st], kTileBytes);
+          tma_load_3d_2sm(vd, &P.tmap_v, &v_full[st], rank * 64, j * kBKV, bh, kEvictLast);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 && rank == 0 && lane == 0) {
+      // ---------------- QK issuer (leader CTA, one thread): S(i) = Q K(i)^T into slot i & 1 ----------------
+      // Two issuing threads (this one and the PV issuer below) so that neither the ~45 cycles an MMA costs its issuing
+      // thread nor the barrier round trips of one product sit in front of the other product's MMAs.
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kFmtBF16, 2 * kBQ, kBKV, 0, 0);
+      const uint64_t q_desc0 = make_desc_sw128(smem_u32(smem + C::kQOff), 16, 1024);
+      const uint64_t k_desc0 = make_desc_sw128(smem_u32(smem + C::kKOff), 16, 1024);
+#ifdef FLUXB200_ATTN_PROBE
+      const bool itr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#endif
+      mbar_wait(q_full, 0);
+      for (int i = 0; i < n; ++i) {
+        const int st = i % KK, slot = i & 1;
+        FB_TRACE(itr, 0, i, 0);
+        if (i >= 2) mbar_wait(&s_free[slot], ((i - 2) >> 1) & 1);  // S(i-2) has been pulled into registers
+        FB_TRACE(itr, 0, i, 1);
+        mbar_wait(&k_full[st], (i / KK) & 1);
+        tc_fence_after();
+        FB_TRACE(itr, 0, i, 2);
+        const uint32_t d = tmem_base + kSCol + slot * 128;
+        const uint64_t bd0 = desc_advance(k_desc0, st * C::kHalfBytes);
+#pragma unroll
+        for (int kk = 0; kk < kD / 16; ++kk) {
+          const uint32_t aoff = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
+          const uint32_t boff = (kk >> 2) * (C::kHalfBytes / 2) + (kk & 3) * 32;
+          mma_f16_ss_2sm(d, desc_advance(q_desc0, aoff), desc_advance(bd0, boff), idesc_qk, kk != 0 ? 1u : 0u);
+        }
+        tc_commit_2sm(&s_ready[slot], 3);
+        tc_commit_2sm(&k_empty[st], 3);
+        FB_TRACE(itr, 0, i, 3);
+      }
+    } else if (warp == 3 && rank == 0 && lane == 0) {
+      // ---------------- PV issuer (leader CTA, one thread): O += P(j) V(j), in two K halves ----------------
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kFmtBF16, 2 * kBQ, kD, 0, 1);
+      const uint64_t v_desc0 = make_desc_sw128(smem_u32(smem + C::kVOff), kChunkBytes, 1024);
+#ifdef FLUXB200_ATTN_PROBE
+      const bool itr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#endif
+      for (int j = 0; j < n; ++j) {
+        const int w = j & 1, st = j % KV;
+        const uint32_t par = (j >> 1) & 1;
+        const uint64_t bd0 = desc_advance(v_desc0, st * C::kHalfBytes);
+        const uint32_t pcol = tmem_base + kPCol + w * 64;
+        mbar_wait(&v_full[st], (j / KV) & 1);
+        mbar_wait(&p_lo[w], par);
+        tc_fence_after();
+        FB_TRACE(itr, 0, j, 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          mma_f16_ts_2sm(tmem_base + kOCol, pcol + kk * 8, desc_advance(bd0, kk * 2048), idesc_pv, (j != 0 || kk != 0) ? 1u : 0u);
+        FB_TRACE(itr, 0, j, 5);
+        mbar_wait(&p_ready[w], par);
+        tc_fence_after();
+        FB_TRACE(itr, 0, j, 6);
+#pragma unroll
+        for (int kk = 4; kk < 8; ++kk)
+          mma_f16_ts_2sm(tmem_base + kOCol, pcol + kk * 8, desc_advance(bd0, kk * 2048), idesc_pv, 1u);
+        tc_commit_2sm(&o_done[w], 3);
+        tc_commit_2sm(&v_empty[st], 3);
+        FB_TRACE(itr, 0, j, 7);
+      }
+    }
+  } else {
+    // ---------------- softmax warpgroups: warpgroup w takes the KV steps j = w, w + 2, ... ----------------
+    reg_inc<208>();
+    const int w = (warp - 4) >> 2;
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int qrow = q0 + r;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    const uint32_t o_taddr = lane_base + kOCol;
+    const float sl2 = P.scale_log2;
+#ifdef FLUXB200_ATTN_PROBE
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    const bool tr = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lg == 0 && lane == 0;
+#else
+    [[maybe_unused]] constexpr bool tr = false;
+    constexpr bool dbg = false;
+#endif
+    unsigned long long d_wait_s = 0, d_ld = 0, d_max = 0, d_exp = 0, d_wait_o = 0, d_st = 0, tA = 0, tB = 0;
+    int nsteps = 0;
+    if (TURN && w == 1) named_bar_arrive(4, 256);  // the first turn is warpgroup 0's
+    float m_mine = -INFINITY;  // reference maximum (log2 units) this warpgroup's row sum is expressed in
+    float l = 0.f;
+    for (int j = w; j < n; j += 2) {
+      const uint32_t par = (j >> 1) & 1;
+      if (dbg) tA = clk();
+      FB_TRACE(tr, 1 + w, j, 0);
+      mbar_wait(&s_ready[w], par);
+      tc_fence_after();
+      FB_TRACE(tr, 1 + w, j, 1);
+      if (dbg) { tB = clk(); d_wait_s += tB - tA; tA = tB; ++nsteps; }
+      uint32_t sv[128];
+      {
+        uint32_t(*sv4)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+        tmem_ld32(lane_base + kSCol + w * 128 + 0, sv4[0]);
+        tmem_ld32(lane_base + kSCol + w * 128 + 32, sv4[1]);
+        tmem_ld32(lane_base + kSCol + w * 128 + 64, sv4[2]);
+        tmem_ld32(lane_base + kSCol + w * 128 + 96, sv4[3]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(&s_free[w], 0);  // QK(j+2) may overwrite the slot from here on
+      }
+      if (dbg) { tB = clk(); d_ld += tB - tA; tA = tB; }
+      FB_TRACE(tr, 1 + w, j, 2);
+      const int kv_left = a.S - j * kBKV;
+      if (kv_left < kBKV) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_left) sv[i] = __float_as_uint(-INFINITY);
+      }
+      float m0 = fmax3(__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]));
+      float m1 = fmax3(__uint_as_float(sv[3]), __uint_as_float(sv[4]), __uint_as_float(sv[5]));
+      float m2 = fmaxf(__uint_as_float(sv[6]), __uint_as_float(sv[7]));
+      float m3 = -INFINITY;
+#pragma unroll
+      for (int i = 8; i < 128; i += 8) {
+        m0 = fmax3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        m1 = fmax3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+        m2 = fmax3(m2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+        m3 = fmax3(m3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+      }
+      const float m_cand = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+      // reference maximum of the previous step (the other warpgroup's), then ours, then hand it on
+      float m_prev = -INFINITY;
+      if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
+      FB_TRACE(tr, 1 + w, j, 3);
+      if (j > 0) {
+        named_bar_sync(1 + ((j - 1) & 1), 256);  // the other warpgroup has published m_ref(j-1)
+        m_prev = m_pub[((j - 1) & 1) * kBQ + r];
+      }
+      if (dbg) { tB = clk(); d_st += tB - tA; tA = tB; }  // wait for the other warpgroup's maximum
+      FB_TRACE(tr, 1 + w, j, 4);
+      const bool grow = __any_sync(0xffffffffu, m_cand > m_prev + kRescaleThreshold);
+      const float m_ref = grow ? fmaxf(m_prev, m_cand) : m_prev;
+      if (j + 1 < n) {
+        m_pub[(j & 1) * kBQ + r] = m_ref;
+        named_bar_arrive(1 + (j & 1), 256);
+      }
+      if (m_ref != m_mine) {
+        l *= fast_exp2(m_mine - m_ref);  // exp2(-inf) = 0 (first step: l = 0 anyway)
+        m_mine = m_ref;
+      }
+      if (j >= 2) {
+        // PV(j-2) retired: P[w] may be overwritten.  Also keeps the parity wait on the OTHER slot's barrier below
+        // sound: PV(j-3) has retired too (in order), so that barrier is at most one phase behind what we ask for.
+        mbar_wait(&o_done[w], par ^ 1);
+        tc_fence_after();
+      }
+      if (grow && j > 0) {
+        // O (which holds PV(0..j-1)) moves to the new reference: wait for PV(j-1) to retire, rescale, THEN release P(j)
+        mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const float alpha = fast_exp2(m_prev - m_ref);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t ov[32];
+          tmem_ld32(o_taddr + c * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st32(o_taddr + c * 32, ov);
+        }
+        tmem_st_wait();
+      }
+      if (dbg) { tB = clk(); d_wait_o += tB - tA; tA = tB; }
+      FB_TRACE(tr, 1 + w, j, 5);
+      // x = s * scale * log2(e) - m for the whole row BEFORE the turn: FMA-pipe work that runs under the other
+      // warpgroup's exponentials instead of inside this warpgroup's exclusive MUFU window (the empty volatile asm pins
+      // the results in front of the barrier; ptxas otherwise sinks them between the first MUFU instructions).
+      {
+        const float2 sl2v = make_float2(sl2, sl2), negmv = make_float2(-m_ref, -m_ref);
+#pragma unroll
+        for (int i = 0; i < 128; i += 2) {
+          const float2 t = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, negmv);
+          sv[i] = __float_as_uint(t.x);
+          sv[i + 1] = __float_as_uint(t.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 128; i += 16)
+          asm volatile("" : "+r"(sv[i]), "+r"(sv[i + 1]), "+r"(sv[i + 2]), "+r"(sv[i + 3]), "+r"(sv[i + 4]), "+r"(sv[i + 5]),
+                            "+r"(sv[i + 6]), "+r"(sv[i + 7]), "+r"(sv[i + 8]), "+r"(sv[i + 9]), "+r"(sv[i + 10]),
+                            "+r"(sv[i + 11]), "+r"(sv[i + 12]), "+r"(sv[i + 13]), "+r"(sv[i + 14]), "+r"(sv[i + 15]));
+      }
+      // The exponentials of the two warpgroups take turns on the MUFU (named barriers 4 / 5): run concurrently both
+      // take twice as long and the warpgroups fall into phase (TMEM load + max of both, then both exponentiate).
+      if constexpr (TURN) named_bar_sync(4 + w, 256);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int i = hh * 64; i < hh * 64 + 64; i += 8) {
+          const float p0 = fast_exp2_pinned(__uint_as_float(sv[i])), p1 = fast_exp2_pinned(__uint_as_float(sv[i + 1]));
+          const float p2 = fast_exp2_pinned(__uint_as_float(sv[i + 2])), p3 = fast_exp2_pinned(__uint_as_float(sv[i + 3]));
+          const float p4 = fast_exp2_pinned(__uint_as_float(sv[i + 4])), p5 = fast_exp2_pinned(__uint_as_float(sv[i + 5]));
+          const float p6 = fast_exp2_pinned(__uint_as_float(sv[i + 6])), p7 = fast_exp2_pinned(__uint_as_float(sv[i + 7]));
+          acc0 = fadd2(acc0, make_float2(p0, p1));
+          acc1 = fadd2(acc1, make_float2(p2, p3));
+          acc0 = fadd2(acc0, make_float2(p4, p5));
+          acc1 = fadd2(acc1, make_float2(p6, p7));
+          sv[i >> 1] = pack_bf16x2(p0, p1);
+          sv[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          sv[(i >> 1) + 2] = pack_bf16x2(p4, p5);
+          sv[(i >> 1) + 3] = pack_bf16x2(p6, p7);
+        }
+        uint32_t(*pk)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+        tmem_st32(lane_base + kPCol + w * 64 + hh * 32, pk[hh]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(hh == 0 ? &p_lo[w] : &p_ready[w], 0);
+        FB_TRACE(tr, 1 + w, j, 6 + hh);
+      }
+      if constexpr (TURN) named_bar_arrive(4 + (w ^ 1), 256);
+      const float2 acc = fadd2(acc0, acc1);
+      l += acc.x + acc.y;
+      if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
+    }
+    if (dbg) {
+      g_attn_dbg[0] = d_wait_s, g_attn_dbg[1] = d_ld, g_attn_dbg[2] = d_max, g_attn_dbg[3] = d_exp;
+      g_attn_dbg[4] = d_wait_o, g_attn_dbg[5] = d_st, g_attn_dbg[6] = nsteps;
+    }
+    // ---------------- combine the two partial row sums ----------------
+    l_pub[w * kBQ + r] = l;
+    mf_pub[w * kBQ + r] = m_mine;
+    named_bar_sync(3, 256);
+    const float l_o = l_pub[(w ^ 1) * kBQ + r], m_o = mf_pub[(w ^ 1) * kBQ + r];
+    const float m_fin = fmaxf(m_mine, m_o);  // = the reference maximum of the last step (it never decreases)
+    float l_tot = 0.f;
+    if (m_mine != -INFINITY) l_tot += l * fast_exp2(m_mine - m_fin);
+    if (m_o != -INFINITY) l_tot += l_o * fast_exp2(m_o - m_fin);
+
+    // ---------------- epilogue: warpgroup w writes head-dim columns [64 w, 64 w + 64) ----------------
+    mbar_wait(&o_done[(n - 1) & 1], ((n - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_tot;
+    const bool valid = qrow < a.S;
+    const bool second = a.out1 != nullptr && qrow >= a.split_row;
+    void* const outp = second ? a.out1 : a.out;
+    const int64_t obase = second ? static_cast<int64_t>(b) * a.out1_batch_stride +
+                                       static_cast<int64_t>(qrow - a.split_row) * a.ldo1 + h * kD
+                                 : static_cast<int64_t>(b) * a.out_batch_stride + static_cast<int64_t>(qrow) * a.ldo + h * kD;
+    float oscale = 1.f;
+    if (a.out_kind == 1) oscale = __ldg(qrow < a.split_row ? a.out_scale0 : a.out_scale1);
+#pragma unroll 1
+    for (int c = w * 2; c < w * 2 + 2; ++c) {
+      uint32_t ov[32];
+      tmem_ld32(o_taddr + c * 32, ov);
+      tmem_ld_wait();
+      if (!valid) continue;
+      if (a.out_kind == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + obase + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(ov[q * 8 + 0]) * inv_l, __uint_as_float(ov[q * 8 + 1]) * inv_l);
+          o.y = pack_bf16x2(__uint_as_float(ov[q * 8 + 2]) * inv_l, __uint_as_float(ov[q * 8 + 3]) * inv_l);
+          o.z = pack_bf16x2(__uint_as_float(ov[q * 8 + 4]) * inv_l, __uint_as_float(ov[q * 8 + 5]) * inv_l);
+          o.w = pack_bf16x2(__uint_as_float(ov[q * 8 + 6]) * inv_l, __uint_as_float(ov[q * 8 + 7]) * inv_l);
+          dst[q] = o;
+        }
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(outp) + obase + c * 32);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t wd[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float o = bf16r(__uint_as_float(ov[q * 16 + t * 4 + e]) * inv_l);
+              f[e] = a.out_fmt == FLUXB200_E5M2 ? quant_pre<1>(o, oscale) : quant_pre<0>(o, oscale);
+            }
+            if (a.out_fmt == FLUXB200_E5M2)
+              wd[t] = to_fp8x2<1>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<1>(f[2], f[3])) << 16);
+            else
+              wd[t] = to_fp8x2<0>(f[0], f[1]) | (static_cast<uint32_t>(to_fp8x2<0>(f[2], f[3])) << 16);
+          }
+          dst[q] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        }
+      }
+    }
+  }
+
+  pdl_launch_dependents();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+template <bool TURN>
+static int launch_attention_step(const AttnParams& P, cudaStream_t stream) {
+  using C = AttnStepCfg;
+  static_assert(C::kTotal <= 227 * 1024, "attention smem budget");
+  static bool attr_set = false;
+  if (!attr_set) {
+    FB_CUDA_OK(cudaFuncSetAttribute(attention_kernel_step<TURN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+    attr_set = true;
+  }
+  const fluxb200_attention_args& a = P.a;
+  CUtensorMap tmap_k64;
+  const uint64_t bhn = static_cast<uint64_t>(a.B) * a.H;
+  const uint64_t row_bytes = kD * 2;
+  int rc = make_tmap_3d(&tmap_k64, a.k, 2, kD, a.S, bhn, row_bytes, row_bytes * a.S, 64, kBKV / 2, 1);
+  if (rc) return rc;
+  dim3 grid(2 * ((a.S + 2 * kBQ - 1) / (2 * kBQ)), a.H, a.B);
+  FB_CUDA_OK(launch_kernel(attention_kernel_step<TURN>, grid, dim3(C::kThreads), C::kTotal, stream, 2, P, tmap_k64));
+  return 0;
+}
 
