@@ -44,6 +44,11 @@ EXPORTS = (
     "fluxb200_qknorm_rope",
     "fluxb200_attention",
     "fluxb200_lora_fuse",
+    "fluxb200_conv2d_nhwc",
+    "fluxb200_group_norm_nhwc",
+    "fluxb200_upsample2x_nhwc",
+    "fluxb200_softmax_rows",
+    "fluxb200_vae_latent_prep",
     "fluxb200_debug_counters",
     "fluxb200_gemm_probe_mode",
     "fluxb200_gemm_force_tiling",
@@ -65,6 +70,30 @@ class LnArgs(C.Structure):
         ("mod_batch_stride", C.c_int64),
         ("B", C.c_int32),
         ("L", C.c_int32),
+    ]
+
+
+class ConvArgs(C.Structure):
+    """struct fluxb200_conv_args"""
+
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("w", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("out", C.c_void_p),
+        ("ldx", C.c_int64),
+        ("ldw", C.c_int64),
+        ("ld_res", C.c_int64),
+        ("ldo", C.c_int64),
+        ("B", C.c_int32),
+        ("H", C.c_int32),
+        ("W", C.c_int32),
+        ("Cin", C.c_int32),
+        ("N", C.c_int32),
+        ("taps", C.c_int32),
+        ("out_mode", C.c_int32),
+        ("alpha", C.c_float),
     ]
 
 
@@ -209,6 +238,13 @@ def load() -> C.CDLL:
         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
     ]
+    lib.fluxb200_conv2d_nhwc.argtypes = [C.POINTER(ConvArgs), C.c_void_p]
+    lib.fluxb200_group_norm_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                             C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.fluxb200_upsample2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.fluxb200_softmax_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
+    lib.fluxb200_vae_latent_prep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,
+                                             C.c_float, C.c_void_p]
     lib.fluxb200_debug_counters.argtypes = [C.POINTER(C.c_ulonglong)]
     lib.fluxb200_gemm_probe_mode.argtypes = [C.c_int]
     lib.fluxb200_gemm_force_tiling.argtypes = [C.c_int, C.c_int]

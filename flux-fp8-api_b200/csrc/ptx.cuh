@@ -293,6 +293,16 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const void* tmap
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+                                                int32_t c2, int32_t c3, uint64_t hint = kEvictNormal) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "l"(hint)
+      : "memory");
+}
+
 // 2-SM form with cluster multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and each
 // destination signals the transaction bytes on the barrier (same offset) of ITS pair's leader CTA.
 __device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,

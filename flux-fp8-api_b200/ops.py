@@ -546,3 +546,119 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Optional[Tensor] = None, out
     _timed("attention", 4.0 * B * H * S * S * D,
            lambda: cabi.check(cabi.load().fluxb200_attention(C.byref(a), cabi.stream_ptr()), "fluxb200_attention"))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# VAE decoder ops.  Activations are channels-last bf16 tensors [B, H, W, C] between these calls.
+# ---------------------------------------------------------------------------------------------------------------------
+def pack_conv_weight(weight: Tensor, cin_pad: Optional[int] = None) -> Tensor:
+    """nn.Conv2d weight [N, C, kh, kw] (kh = kw = 1 or 3) -> the kernel's bf16 [N, kh*kw*Cp] with
+    w[n, (ky*kw + kx)*Cp + c] = weight[n, c, ky, kx]; Cp = C rounded up to a multiple of 64 (zero filled)."""
+    N, Cin, kh, kw = weight.shape
+    if (kh, kw) not in ((1, 1), (3, 3)):
+        raise ValueError(f"pack_conv_weight: kernel {kh}x{kw} is not supported (1x1 or 3x3)")
+    cp = cin_pad or ((Cin + 63) // 64) * 64
+    w = torch.zeros((N, kh * kw, cp), dtype=BF16, device=weight.device)
+    w[:, :, :Cin] = weight.detach().to(BF16).permute(0, 2, 3, 1).reshape(N, kh * kw, Cin)
+    return w.reshape(N, kh * kw * cp)
+
+
+def conv2d_nhwc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], taps: int, residual: Optional[Tensor] = None,
+                out: Optional[Tensor] = None, out_mode: int = 0, alpha: float = 1.0, nchw_plane: Optional[int] = None) -> Tensor:
+    """fluxb200_conv2d_nhwc.  x bf16 [B, H, W, Cin] (Cin % 64 == 0); w_packed from pack_conv_weight.
+    out_mode 0 -> bf16 [B, H, W, N] (+ bias, + residual); 1 -> fp32 [B, H, W, N] = alpha * acc; 2 -> bf16 NCHW [B, N, H, W]."""
+    cabi.require_cuda(x, w_packed)
+    _want(x, BF16, "conv2d_nhwc: x"), _want(w_packed, BF16, "conv2d_nhwc: w"), _want(bias, BF16, "conv2d_nhwc: bias")
+    _want(residual, BF16, "conv2d_nhwc: residual")
+    if x.dim() != 4 or x.stride(3) != 1:
+        raise ValueError("conv2d_nhwc: x must be [B, H, W, C] with contiguous channels")
+    B, H, W, Cin = x.shape
+    if (H > 1 and x.stride(1) != W * x.stride(2)) or (B > 1 and x.stride(0) != H * W * x.stride(2)):
+        raise ValueError("conv2d_nhwc: x must have dense B / H / W strides (a pixel stride >= C is allowed)")
+    N = w_packed.shape[0]
+    if w_packed.shape[1] != taps * Cin or w_packed.stride(1) != 1:
+        raise ValueError(f"conv2d_nhwc: packed weight {tuple(w_packed.shape)} does not match taps={taps} Cin={Cin}")
+    if out is None:
+        if out_mode == 0:
+            out = torch.empty((B, H, W, N), dtype=BF16, device=x.device)
+        elif out_mode == 1:
+            out = torch.empty((B, H, W, N), dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty((B, N, H, W), dtype=BF16, device=x.device)
+    _contig(out, "conv2d_nhwc: out")
+    _want(out, torch.float32 if out_mode == 1 else BF16, "conv2d_nhwc: out")
+    a = cabi.ConvArgs()
+    a.x, a.w, a.bias, a.out = x.data_ptr(), w_packed.data_ptr(), cabi.ptr(bias), out.data_ptr()
+    a.ldx, a.ldw = x.stride(2), w_packed.stride(0)
+    if residual is not None:
+        _contig(residual, "conv2d_nhwc: residual")
+        if residual.numel() != B * H * W * N:
+            raise ValueError("conv2d_nhwc: residual must have the output's shape")
+        a.residual, a.ld_res = residual.data_ptr(), N
+    a.ldo = N if out_mode != 2 else (nchw_plane or H * W)
+    a.B, a.H, a.W, a.Cin, a.N, a.taps, a.out_mode, a.alpha = B, H, W, Cin, N, taps, out_mode, alpha
+    _timed("conv2d", 2.0 * B * H * W * N * taps * Cin,
+           lambda: cabi.check(cabi.load().fluxb200_conv2d_nhwc(C.byref(a), cabi.stream_ptr()), "fluxb200_conv2d_nhwc"),
+           f"{B}x{H}x{W} {Cin}->{N} taps {taps}" if KERNEL_TIMELINE is not None else "")
+    return out
+
+
+_gn_ws = {}
+
+
+def group_norm_nhwc(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, swish: bool, out: Optional[Tensor] = None) -> Tensor:
+    """nn.GroupNorm(32, C, eps) (+ x * sigmoid(x)) on a channels-last bf16 tensor, fp32 arithmetic, bf16 result."""
+    cabi.require_cuda(x, gamma, beta)
+    _want(x, BF16, "group_norm_nhwc: x"), _want(gamma, BF16, "group_norm_nhwc: weight"), _want(beta, BF16, "group_norm_nhwc: bias")
+    _contig(x, "group_norm_nhwc: x")
+    B, H, W, Cn = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    ws = _gn_ws.get((x.device, B))
+    if ws is None:
+        ws = _gn_ws[(x.device, B)] = torch.zeros(64 * B, dtype=torch.float64, device=x.device)
+    _timed("group_norm", 0.0,
+           lambda: cabi.check(cabi.load().fluxb200_group_norm_nhwc(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                                                   ws.data_ptr(), B, H * W, Cn, eps, int(swish), cabi.stream_ptr()),
+                              "fluxb200_group_norm_nhwc"))
+    return out
+
+
+def upsample2x_nhwc(x: Tensor) -> Tensor:
+    cabi.require_cuda(x)
+    _want(x, BF16, "upsample2x_nhwc: x")
+    _contig(x, "upsample2x_nhwc: x")
+    B, H, W, Cn = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, Cn), dtype=BF16, device=x.device)
+    _timed("upsample2x", 0.0,
+           lambda: cabi.check(cabi.load().fluxb200_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, Cn, cabi.stream_ptr()),
+                              "fluxb200_upsample2x_nhwc"))
+    return out
+
+
+def softmax_rows(scores: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """bf16(softmax(scores, -1)) of an fp32 [rows, n] matrix."""
+    cabi.require_cuda(scores)
+    _want(scores, torch.float32, "softmax_rows: scores")
+    if scores.dim() != 2 or scores.stride(1) != 1:
+        raise ValueError("softmax_rows: scores must be a 2-D row-major matrix")
+    rows, n = scores.shape
+    if out is None:
+        out = torch.empty((rows, n), dtype=BF16, device=scores.device)
+    _timed("softmax_rows", 0.0,
+           lambda: cabi.check(cabi.load().fluxb200_softmax_rows(scores.data_ptr(), scores.stride(0), out.data_ptr(), out.stride(0),
+                                                                rows, n, cabi.stream_ptr()), "fluxb200_softmax_rows"))
+    return out
+
+
+def vae_latent_prep(z: Tensor, scale_factor: float, shift_factor: float, cpad: int = 64) -> Tensor:
+    """z fp32 [B, C, H, W] -> bf16 [B, H, W, cpad] = z / scale_factor + shift_factor, extra channels zero."""
+    cabi.require_cuda(z)
+    _want(z, torch.float32, "vae_latent_prep: z")
+    _contig(z, "vae_latent_prep: z")
+    B, Cn, H, W = z.shape
+    out = torch.empty((B, H, W, cpad), dtype=BF16, device=z.device)
+    _timed("latent_prep", 0.0,
+           lambda: cabi.check(cabi.load().fluxb200_vae_latent_prep(z.data_ptr(), out.data_ptr(), B, Cn, H * W, cpad, scale_factor,
+                                                                   shift_factor, cabi.stream_ptr()), "fluxb200_vae_latent_prep"))
+    return out

@@ -190,6 +190,48 @@ int fluxb200_bf16_gemm_small(const void* x_bf16, int64_t ldx, const void* w_bf16
                              fluxb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * VAE decode: modules/autoencoder.py:203-283 `Decoder.forward`, as flux_pipeline.py:423-438 runs it
+ * (under torch.autocast(bfloat16): convolutions and attention in bf16 with fp32 accumulation, GroupNorm and swish in
+ * fp32).  Activations are NHWC bf16 between these calls; the Python host (`autoencoder.py`) mirrors the reference's
+ * module tree and state-dict keys and packs the Conv2d weights once.
+ *
+ * fluxb200_conv2d_nhwc: nn.Conv2d(kernel 3 stride 1 padding 1) (taps = 9) or kernel 1 (taps = 1) as an implicit GEMM on
+ *   tcgen05 (autoencoder.py:33-36 q/k/v/proj_out, :65-79 conv1/conv2/nin_shortcut, :115-117 Upsample.conv, :216 conv_in,
+ *   :249 conv_out).  x: bf16 [B, H, W, Cin] (pixel stride ldx elements, 0 = Cin; Cin % 64 == 0, zero-pad otherwise),
+ *   w: bf16 [N][taps * Cin] with w[n][(ky * 3 + kx) * Cin + c] = weight[n, c, ky, kx] (row stride ldw, 0 = taps * Cin).
+ *   out_mode 0: out bf16 [B*H*W][ldo] = bf16( residual + bf16( bf16(acc) + bias ) )   (bias / residual optional: the
+ *               roundings are cuDNN's bf16 output, at::_convolution's bias add, ResnetBlock's `x + h` :94);
+ *   out_mode 1: out fp32 [B*H*W][ldo] = alpha * acc       (attention scores q k^T / sqrt(C), AttnBlock.attention :47);
+ *   out_mode 2: out bf16 NCHW [B, N, ldo >= H*W] = bf16( bf16(acc) + bias )   (the decoder's image; v^T of the attention,
+ *               whose rows are zero-padded to a multiple of 64 positions by the caller).
+ *   With H = 1, taps = 1 this is the dense GEMM out[W x N] = x[W x Cin] w[N x Cin]^T.
+ * fluxb200_group_norm_nhwc: nn.GroupNorm(32, C, eps, affine) (:27-29, :62-70, :245-247) then (swish != 0) x*sigmoid(x)
+ *   (:18-19); fp32 arithmetic on fp64-accumulated statistics, one rounding to bf16.  stats_ws: 64 * B doubles.
+ * fluxb200_upsample2x_nhwc: F.interpolate(scale_factor=2.0, mode="nearest") (:121).
+ * fluxb200_softmax_rows: p[r, :] = bf16(softmax(scores[r, :])) for the single-head attention of the mid block (:47).
+ * fluxb200_vae_latent_prep: AutoEncoder.decode's `z / scale_factor + shift_factor` (:331-332) on the fp32 NCHW latent,
+ *   written as bf16 NHWC with the channel dimension zero-padded to Cpad.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fluxb200_conv_args {
+  const void* x;        /* bf16 NHWC */
+  const void* w;        /* bf16 packed weights */
+  const void* bias;     /* bf16 [N] or NULL */
+  const void* residual; /* bf16 [B*H*W][ld_res] or NULL (out_mode 0) */
+  void* out;
+  int64_t ldx, ldw, ld_res, ldo;
+  int32_t B, H, W, Cin, N, taps, out_mode;
+  float alpha;          /* out_mode 1 */
+} fluxb200_conv_args;
+int fluxb200_conv2d_nhwc(const fluxb200_conv_args* args, fluxb200_stream_t stream);
+int fluxb200_group_norm_nhwc(const void* x_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
+                             double* stats_ws, int B, int64_t HW, int C, float eps, int swish, fluxb200_stream_t stream);
+int fluxb200_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int B, int H, int W, int C, fluxb200_stream_t stream);
+int fluxb200_softmax_rows(const float* scores, int64_t lds, void* p_bf16, int64_t ldp, int rows, int n,
+                          fluxb200_stream_t stream);
+int fluxb200_vae_latent_prep(const float* z_nchw, void* y_nhwc_bf16, int B, int C, int64_t HW, int Cpad,
+                             float scale_factor, float shift_factor, fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Modulation prologue: y = quantize( bf16(silu(x)), scale )   (modules/flux_model.py:249,252 +
  * float8_quantize.py:274-276).  y_bf16 (optional) receives bf16(silu(x)) for unquantised lins.
  * ------------------------------------------------------------------------------------------- */

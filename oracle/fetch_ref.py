@@ -5,12 +5,13 @@ reference / cpu_baseline legs may import what this stages.  The product path nev
 
 The reference (aredden/flux-fp8-api) is pure Python over PyTorch: there is nothing to compile, and it has no
 setup.py / pyproject, so `pip install --target baseline/_ref /root/reference` has nothing to install.  The
-"reference build" for this repository is therefore a byte-for-byte staging of the three files SURVEY.md
-section 8(a) cites,
+"reference build" for this repository is therefore a byte-for-byte staging of the files SURVEY.md
+section 8(a) / 8(f) cite,
 
     float8_quantize.py        F8Linear, recursive_swap_linears, quantize_flow_transformer_and_dispatch_float8
     modules/flux_model.py     Flux, DoubleStreamBlock, SingleStreamBlock, Modulation, attention, rope, QKNorm ...
     lora_loading.py           apply_lora_to_model / remove_lora_from_module (config c4 merges a LoRA with it)
+    modules/autoencoder.py    AutoEncoder / Decoder (the VAE decode that follows the denoise loop)
 
 into the git-ignored directory oracle/_ref/ (listed in .gitignore, NOT in .gpurunignore: it ships with the
 gpurun snapshot exactly like the built libflux_b200.so), plus MANIFEST.json with the sha256 of every file so a
@@ -31,7 +32,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref")
-FILES = ("float8_quantize.py", "modules/flux_model.py", "lora_loading.py")
+FILES = ("float8_quantize.py", "modules/flux_model.py", "lora_loading.py", "modules/autoencoder.py")
 
 
 def sha256(path: str) -> str:

@@ -377,6 +377,46 @@ def golden_lora():
     torch.save(cases, os.path.join(OUT, "lora.pt"))
 
 
+VAE_TINY = dict(resolution=64, in_channels=3, ch=64, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=16,
+                scale_factor=0.3611, shift_factor=0.1159)
+
+
+def golden_vae():
+    """tests/golden/vae_tiny.pt: the UNMODIFIED reference AutoEncoder.decode (fp32) on a seeded tiny configuration, the
+    oracle pinned against it, and the oracle's CUDA-autocast restatement of the same decode (the kernels' CPU target)."""
+    from modules import autoencoder as ref_ae  # noqa: E402  (reference)
+
+    from oracle import vae_oracle as V
+
+    print("vae_tiny.pt")
+    ae = ref_ae.AutoEncoder(ref_ae.AutoEncoderParams(**VAE_TINY))
+    sd = V.synthetic_state(ae, seed=31)
+    missing, unexpected = ae.load_state_dict({k: v.float() for k, v in sd.items()}, strict=False)
+    assert not unexpected and all(k.startswith("encoder.") for k in missing), (missing, unexpected)
+    ae = ae.float().eval()
+    g = torch.Generator().manual_seed(32)
+    z = torch.randn(2, 16, 8, 8, generator=g) * 1.2
+    with torch.inference_mode():
+        y_ref = ae.decode(z)  # reference, fp32
+        y_ora32 = V.decode(z, sd, VAE_TINY["ch_mult"], VAE_TINY["num_res_blocks"], VAE_TINY["scale_factor"],
+                           VAE_TINY["shift_factor"], policy="fp32")
+        y_auto = V.decode(z, sd, VAE_TINY["ch_mult"], VAE_TINY["num_res_blocks"], VAE_TINY["scale_factor"],
+                          VAE_TINY["shift_factor"], policy="autocast")
+        # intermediate taps of the reference for the kernel tests: mid-block input / output, fp32
+        h0 = ae.decoder.conv_in(z / VAE_TINY["scale_factor"] + VAE_TINY["shift_factor"])
+        h1 = ae.decoder.mid.block_1(h0)
+        h2 = ae.decoder.mid.attn_1(h1)
+    d = maxdiff(y_ref, y_ora32)
+    print(f"  oracle(fp32) vs reference(fp32): max|d| {d:.3g} on amax {y_ref.abs().max().item():.3g}")
+    assert d <= 2e-4 * max(1.0, y_ref.abs().max().item()), d
+    da = maxdiff(y_ref, y_auto)
+    print(f"  oracle(autocast) vs reference(fp32): max|d| {da:.3g}  mean|d| {(y_ref - y_auto.float()).abs().mean().item():.3g}")
+    # the 12 M parameters are not stored: tests regenerate them with V.synthetic_state(<any module with the reference's
+    # decoder keys>, seed=31) and check the fingerprint
+    torch.save({"params": VAE_TINY, "state_seed": 31, "state_checksum": V.state_checksum(sd), "z": z, "y_ref_fp32": y_ref, "y_oracle_autocast": y_auto,
+                "h_conv_in": h0, "h_mid_block_1": h1, "h_mid_attn_1": h2}, os.path.join(OUT, "vae_tiny.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -387,4 +427,5 @@ if __name__ == "__main__":
     golden_flux()
     golden_flux_variants()
     golden_lora()
+    golden_vae()
     print("golden fixtures written to", OUT)

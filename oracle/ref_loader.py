@@ -86,6 +86,10 @@ def load():
         ns.lora = importlib.import_module("lora_loading")
     except Exception as ex:  # noqa: BLE001  (optional third-party imports of that file)
         ns.lora, ns.lora_error = None, repr(ex)
+    try:
+        ns.ae = importlib.import_module("modules.autoencoder")
+    except Exception as ex:  # noqa: BLE001  (staged by newer fetch_ref only)
+        ns.ae, ns.ae_error = None, repr(ex)
     ns.dir = REF_DIR
     _cached = ns
     return ns

@@ -39,6 +39,7 @@ def test_struct_layout_matches_c(tmp_path):
     fields_a = [f[0] for f in _cabi.AttentionArgs._fields_]
     fields_l = [f[0] for f in _cabi.LnArgs._fields_]
     fields_v = [f[0] for f in _cabi.GemvLayer._fields_]
+    fields_c = [f[0] for f in _cabi.ConvArgs._fields_]
     body = ['#include <stdio.h>', '#include <stddef.h>', '#include "flux_b200.h"', "int main(void){"]
     body.append('printf("%zu\\n", sizeof(fluxb200_gemm_args));')
     body += [f'printf("%zu\\n", offsetof(fluxb200_gemm_args, {f}));' for f in fields_g]
@@ -48,6 +49,8 @@ def test_struct_layout_matches_c(tmp_path):
     body += [f'printf("%zu\\n", offsetof(fluxb200_ln_args, {f}));' for f in fields_l]
     body.append('printf("%zu\\n", sizeof(fluxb200_gemv_layer));')
     body += [f'printf("%zu\\n", offsetof(fluxb200_gemv_layer, {f}));' for f in fields_v]
+    body.append('printf("%zu\\n", sizeof(fluxb200_conv_args));')
+    body += [f'printf("%zu\\n", offsetof(fluxb200_conv_args, {f}));' for f in fields_c]
     body.append("return 0;}")
     src.write_text("\n".join(body))
     exe = tmp_path / "layout"
@@ -63,7 +66,10 @@ def test_struct_layout_matches_c(tmp_path):
     assert rest[1:1 + len(fields_l)] == [getattr(_cabi.LnArgs, f).offset for f in fields_l]
     rest = rest[1 + len(fields_l):]
     assert rest[0] == C.sizeof(_cabi.GemvLayer)
-    assert rest[1:] == [getattr(_cabi.GemvLayer, f).offset for f in fields_v]
+    assert rest[1:1 + len(fields_v)] == [getattr(_cabi.GemvLayer, f).offset for f in fields_v]
+    rest = rest[1 + len(fields_v):]
+    assert rest[0] == C.sizeof(_cabi.ConvArgs)
+    assert rest[1:] == [getattr(_cabi.ConvArgs, f).offset for f in fields_c]
 
 
 def test_invalid_arguments_fail_loudly(lib):

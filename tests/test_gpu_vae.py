@@ -1,0 +1,236 @@
+"""GPU (-m gpu): the VAE decode kernels against torch fp32 references of the same ops, the oracle's
+golden vectors, and the UNMODIFIED reference AutoEncoder (staged under oracle/_ref) run on the same B200 under
+torch.autocast("cuda", torch.bfloat16) exactly as flux_pipeline.py:423-438 runs it."""
+import json
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from flux_fp8_api_b200 import autoencoder as A
+from flux_fp8_api_b200 import ops
+from oracle import ref_loader as R
+from oracle import vae_oracle as V
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ULP = 2.0 ** -7  # one bf16 ulp relative to a value's binade top
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randn(shape, device=DEV, generator=g) * scale).to(BF16)
+
+
+def _conv_ref(x_nhwc, weight, bias, residual_nhwc, pad):
+    """The arithmetic the kernel promises, from an fp32-accumulated torch convolution of the same bf16 operands."""
+    acc = F.conv2d(x_nhwc.permute(0, 3, 1, 2).float(), weight.float(), None, padding=pad)
+    h = acc.to(BF16)
+    if bias is not None:
+        h = (h.float() + bias.float().view(1, -1, 1, 1)).to(BF16)
+    if residual_nhwc is not None:
+        h = (h.float() + residual_nhwc.permute(0, 3, 1, 2).float()).to(BF16)
+    return acc, h  # NCHW
+
+
+def _close_in_ulps(out, ref, acc_scale, what, max_ulps=2.0, max_frac=0.02):
+    d = (out.float() - ref.float()).abs()
+    tol = max_ulps * ULP * max(acc_scale, 1e-6)
+    frac = (d > 0).float().mean().item()
+    assert d.max().item() <= tol, f"{what}: max|d| {d.max().item():.4g} > {tol:.4g}"
+    assert frac <= max_frac, f"{what}: {frac:.4f} of the elements differ"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N,k,res", [
+    (1, 8, 8, 64, 64, 3, False),        # one partial tile, BN = 64
+    (2, 16, 16, 128, 256, 3, True),     # two images, residual, BN = 256
+    (1, 12, 96, 64, 128, 3, False),     # W = 96 (768 px images): 32-wide strips; H not a multiple of the strip height
+    (3, 20, 24, 64, 192, 3, True),      # nothing divides anything: clipped tiles in x, y and N (192 of a 256 tile)
+    (1, 64, 64, 256, 256, 1, True),     # 1x1 (nin_shortcut / q / k / v / proj_out)
+    (1, 128, 128, 512, 512, 3, False),  # the decoder's 128 x 128 x 512 convolutions at full size
+    (1, 256, 256, 128, 128, 3, True),   # 128-channel level
+])
+def test_conv2d_nhwc_matches_fp32_convolution_of_the_same_bf16_operands(B, H, W, Cin, N, k, res):
+    x = _rand((B, H, W, Cin), 1)
+    w = _rand((N, Cin, k, k), 2, 1.0 / math.sqrt(Cin * k * k))
+    b = _rand((N,), 3, 0.1)
+    r = _rand((B, H, W, N), 4) if res else None
+    out = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), b, k * k, residual=r)
+    acc, ref = _conv_ref(x, w, b, r, k // 2)
+    _close_in_ulps(out.permute(0, 3, 1, 2), ref, ref.float().abs().max().item(), f"conv {B}x{H}x{W} {Cin}->{N} k{k}")
+
+
+def test_conv2d_padded_input_channels_and_nchw_output():
+    """conv_in (16 latent channels zero-padded to 64) and conv_out (3 output channels, NCHW image)."""
+    z = torch.randn(2, 16, 24, 40, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    x = ops.vae_latent_prep(z, 0.3611, 0.1159)
+    expect = (z / 0.3611 + 0.1159).to(BF16)  # eager torch on the same GPU: AutoEncoder.decode's first line
+    assert torch.equal(x[..., :16].permute(0, 3, 1, 2), expect) and not x[..., 16:].any()
+    w = _rand((512, 16, 3, 3), 6, 1.0 / 12.0)
+    b = _rand((512,), 7, 0.1)
+    out = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), b, 9)
+    _, ref = _conv_ref(x[..., :16], w, b, None, 1)
+    _close_in_ulps(out.permute(0, 3, 1, 2), ref, ref.float().abs().max().item(), "conv_in")
+
+    h = _rand((2, 24, 40, 128), 8)
+    w3 = _rand((3, 128, 3, 3), 9, 1.0 / 34.0)
+    b3 = _rand((3,), 10, 0.1)
+    img = ops.conv2d_nhwc(h, ops.pack_conv_weight(w3), b3, 9, out_mode=2)
+    _, ref3 = _conv_ref(h, w3, b3, None, 1)
+    assert img.shape == (2, 3, 24, 40)
+    _close_in_ulps(img, ref3, ref3.float().abs().max().item(), "conv_out")
+
+
+def test_dense_gemm_modes_scores_fp32_and_transposed_operand():
+    """The attention block's three products: q k^T scaled (fp32 out), v^T (NCHW out with padded rows), P v."""
+    S, Cn = 320, 256  # 320 positions: not a multiple of 128; K of the P v product padded to 320 -> 320 (already % 64)
+    q, k = _rand((S, Cn), 11), _rand((S, Cn), 12)
+    sc = ops.conv2d_nhwc(q.view(1, 1, S, Cn), k, None, 1, out_mode=1, alpha=0.0625).view(S, S)
+    ref = (q.float() @ k.float().t()) * 0.0625
+    assert (sc - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    p = ops.softmax_rows(sc)
+    pref = torch.softmax(ref, -1)
+    assert (p.float() - pref).abs().max().item() <= ULP * pref.max().item() * 1.5
+    v = _rand((S, Cn), 13)
+    o = ops.conv2d_nhwc(p.view(1, 1, S, S), v.t().contiguous(), None, 1).view(S, Cn)
+    oref = p.float() @ v.float()
+    _close_in_ulps(o, oref.to(BF16), oref.abs().max().item(), "P v")
+
+
+@pytest.mark.parametrize("C,swish", [(64, True), (128, True), (256, False), (512, True)])
+def test_group_norm_swish_is_the_fp32_formula_rounded_once(C, swish):
+    x = _rand((2, 24, 20, C), 20, 2.0) + 0.5
+    gamma, beta = (1 + 0.1 * _rand((C,), 21).float()).to(BF16), _rand((C,), 22, 0.1)
+    y = ops.group_norm_nhwc(x, gamma, beta, 1e-6, swish)
+    ref = F.group_norm(x.permute(0, 3, 1, 2).float(), 32, gamma.float(), beta.float(), eps=1e-6)
+    if swish:
+        ref = ref * torch.sigmoid(ref)
+    ref = ref.to(BF16).permute(0, 2, 3, 1)
+    d = (y.float() - ref.float()).abs()
+    assert d.max().item() <= 2 * ULP * ref.float().abs().max().item()
+    assert (d > 0).float().mean().item() < 0.03  # a few results sit on a rounding boundary
+
+
+def test_upsample2x_is_nearest():
+    x = _rand((2, 6, 10, 64), 30)
+    y = ops.upsample2x_nhwc(x)
+    ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").to(BF16).permute(0, 2, 3, 1)
+    assert torch.equal(y, ref)
+
+
+def _tiny(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "vae_tiny.pt"))
+    m = A.AutoEncoder(A.AutoEncoderParams(**g["params"]))
+    sd = V.synthetic_state(m, g["state_seed"])
+    assert V.state_checksum(sd) == g["state_checksum"]
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    return g, m.to(DEV, BF16).eval(), sd
+
+
+def test_tiny_decoder_against_the_golden_vectors(golden_dir):
+    """ours vs (a) the oracle's CUDA-autocast restatement, (b) the reference's own fp32 output: our distance to the fp32
+    reference must not exceed the autocast arithmetic's own distance to it."""
+    g, m, _ = _tiny(golden_dir)
+    with torch.inference_mode():
+        y = m.decode(g["z"].to(DEV)).float().cpu()
+    ref32, auto = g["y_ref_fp32"], g["y_oracle_autocast"].float()
+    floor = (auto - ref32).abs().mean().item()
+    ours = (y - ref32).abs().mean().item()
+    vs_auto = (y - auto).abs()
+    print(f"tiny VAE: ours-vs-fp32 {ours:.4g}, autocast-oracle-vs-fp32 {floor:.4g}, ours-vs-oracle mean {vs_auto.mean().item():.4g} "
+          f"max {vs_auto.max().item():.4g}")
+    assert torch.isfinite(y).all()
+    assert ours <= 1.25 * floor
+    assert vs_auto.mean().item() <= floor
+
+
+def test_tiny_blocks_teacher_forced_on_the_reference_activations(golden_dir):
+    """mid.block_1 and mid.attn_1 on the reference's own (fp32) inputs: one block deep, so the bound is bf16 arithmetic."""
+    g, m, _ = _tiny(golden_dir)
+    h0, h1, h2 = g["h_conv_in"].to(DEV), g["h_mid_block_1"].to(DEV), g["h_mid_attn_1"].to(DEV)
+    with torch.inference_mode():
+        o1 = m.decoder.mid.block_1(h0.to(BF16)).float()
+        o2 = m.decoder.mid.attn_1(h1.to(BF16)).float()
+    for name, o, ref in (("mid.block_1", o1, h1), ("mid.attn_1", o2, h2)):
+        d = (o - ref).abs()
+        print(f"{name}: mean|d| {d.mean().item():.4g} max {d.max().item():.4g} on amax {ref.abs().max().item():.4g}")
+        assert d.max().item() <= 6 * ULP * ref.abs().max().item()
+        assert d.mean().item() <= 0.6 * ULP * ref.abs().max().item()
+
+
+def test_loud_failures():
+    x = _rand((1, 8, 8, 48), 40)
+    with pytest.raises(ValueError):
+        ops.conv2d_nhwc(x, _rand((64, 9 * 48), 41), None, 9)  # Cin not a multiple of 64
+    with pytest.raises(ValueError):
+        ops.conv2d_nhwc(_rand((1, 8, 8, 64), 42), _rand((64, 9 * 64), 43).float(), None, 9)  # fp32 weights
+    m = A.AutoEncoder(A.AutoEncoderParams(resolution=64, in_channels=3, ch=64, out_ch=3, ch_mult=[1, 2], num_res_blocks=1,
+                                          z_channels=16, scale_factor=1.0, shift_factor=0.0))
+    with pytest.raises(NotImplementedError):
+        m.encode(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(ValueError):
+        m.to(DEV, BF16).decode(torch.zeros(1, 4, 8, 8, device=DEV))
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not staged (python oracle/fetch_ref.py)")
+@pytest.mark.parametrize("res", [1024, 768])
+def test_full_size_decode_against_the_reference_on_this_gpu(res):
+    """Flux's VAE (ch 128, ch_mult 1-2-4-4) at full resolution: ours vs the staged reference under CUDA autocast, with the
+    reference's own bf16-vs-fp32 distance as the floor; both timed with CUDA events."""
+    ref = R.load()
+    if ref.ae is None:
+        pytest.skip("modules/autoencoder.py not staged (re-run oracle/fetch_ref.py)")
+    params = dict(resolution=256, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=16,
+                  scale_factor=0.3611, shift_factor=0.1159)
+    rae = ref.ae.AutoEncoder(ref.ae.AutoEncoderParams(**params))
+    sd = V.synthetic_state(rae, seed=77)
+    rae.load_state_dict(sd, strict=False)
+    rae = rae.to(DEV, BF16).eval()  # util.py:287: the reference keeps the VAE in bf16
+    ours = A.AutoEncoder(A.AutoEncoderParams(**params))
+    ours.load_state_dict(sd, strict=True)
+    ours = ours.to(DEV, BF16).eval()
+    z = torch.randn(1, 16, res // 8, res // 8, device=DEV, generator=torch.Generator(device=DEV).manual_seed(78)) * 1.2
+
+    def timed(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            out = fn()
+        e.record()
+        torch.cuda.synchronize()
+        return out, s.elapsed_time(e) / n
+
+    with torch.inference_mode():
+        def run_ref():
+            with torch.autocast(device_type="cuda", dtype=BF16, cache_enabled=False):  # flux_pipeline.py:431-434
+                return rae.decode(z)
+
+        y_ref, ms_ref = timed(run_ref)
+        y_ours, ms_ours = timed(lambda: ours.decode(z))
+        rae32 = rae.float()
+        y32 = rae32.decode(z)
+    assert y_ours.shape == y_ref.shape == (1, 3, res, res) and y_ours.dtype == BF16
+    floor = (y_ref.float() - y32).abs()
+    d_ref = (y_ours.float() - y_ref.float()).abs()
+    d_32 = (y_ours.float() - y32).abs()
+    rep = {"res": res, "amax": y32.abs().max().item(), "rms": y32.pow(2).mean().sqrt().item(),
+           "reference_autocast_vs_fp32": {"mean": floor.mean().item(), "max": floor.max().item()},
+           "ours_vs_fp32": {"mean": d_32.mean().item(), "max": d_32.max().item()},
+           "ours_vs_reference_autocast": {"mean": d_ref.mean().item(), "max": d_ref.max().item()},
+           "ms_reference_autocast": ms_ref, "ms_ours": ms_ours}
+    print(json.dumps(rep))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"vae_parity_{res}.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    assert torch.isfinite(y_ours).all()
+    # as close to the fp32 answer as the reference's own bf16 run is (25 % slack: two bf16 runs are not the same run)
+    assert d_32.mean().item() <= 1.25 * floor.mean().item()
+    assert d_32.max().item() <= 1.5 * floor.max().item()
+    # and no further from the reference's bf16 run than that run is from fp32 (both are bf16 perturbations of the same thing)
+    assert d_ref.mean().item() <= 1.5 * floor.mean().item()

@@ -273,3 +273,39 @@ def test_dispatch_predicates_refuse_what_the_kernels_cannot_take():
     assert not M._skinny_bf16(x, lin) and not M._small_bf16_linear(x, lin)          # CPU tensors
     assert not M._skinny_bf16(torch.zeros(2, 64), torch.nn.Linear(64, 32))             # fp32
     assert not M._small_bf16_linear(torch.zeros(2, 48, dtype=torch.bfloat16), torch.nn.Linear(48, 32).to(torch.bfloat16))
+
+
+def test_vae_host_side_keys_packing_and_loud_failure():
+    """AutoEncoder mirrors the reference's decoder state dict (138 tensors for Flux's VAE), packs Conv2d weights into the
+    kernel layout, and refuses to compute without the CUDA library path (no CPU fallback)."""
+    from flux_fp8_api_b200 import autoencoder as A
+    from flux_fp8_api_b200 import ops
+
+    m = A.AutoEncoder(A.AutoEncoderParams(resolution=256, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
+                                          z_channels=16, scale_factor=0.3611, shift_factor=0.1159))
+    keys = set(m.state_dict())
+    assert len(keys) == 138 and all(k.startswith("decoder.") for k in keys)
+    for k in ("decoder.conv_in.weight", "decoder.mid.attn_1.q.weight", "decoder.mid.block_1.norm1.weight",
+              "decoder.up.0.block.0.nin_shortcut.weight", "decoder.up.3.upsample.conv.bias", "decoder.up.1.block.2.conv2.weight",
+              "decoder.norm_out.bias", "decoder.conv_out.weight"):
+        assert k in keys, k
+    assert "decoder.up.0.upsample.conv.weight" not in keys  # the highest resolution level has no upsampler
+    assert m.state_dict()["decoder.conv_in.weight"].shape == (512, 16, 3, 3)
+    assert m.state_dict()["decoder.up.1.block.0.nin_shortcut.weight"].shape == (256, 512, 1, 1)
+
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    pk = ops.pack_conv_weight(w)
+    assert pk.shape == (2, 9 * 64) and pk.dtype == torch.bfloat16
+    for n in range(2):
+        for ky in range(3):
+            for kx in range(3):
+                row = pk[n, (ky * 3 + kx) * 64:(ky * 3 + kx + 1) * 64].float()
+                assert torch.equal(row[:3], w[n, :, ky, kx]) and not row[3:].any()
+    with pytest.raises(ValueError):
+        ops.pack_conv_weight(torch.zeros(4, 4, 5, 5))
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception) as ei:
+            m.decode(torch.zeros(1, 16, 8, 8))
+        assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
+    with pytest.raises(NotImplementedError):
+        m.encode(torch.zeros(1, 3, 64, 64))

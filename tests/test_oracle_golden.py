@@ -180,3 +180,21 @@ def test_lora_fuse_and_unfuse_are_bit_exact(golden_dir):
         w0 = c["before"]["float8_data"].float() * c["before"]["scale_reciprocal"]
         w2 = c["unfused"]["float8_data"].float() * c["unfused"]["scale_reciprocal"]
         assert (w0 - w2).abs().max() <= 0.13 * w0.abs().max()
+
+
+def test_vae_oracle_reproduces_the_reference_decode(golden_dir):
+    """oracle/vae_oracle.py (fp32 policy) against the UNMODIFIED reference AutoEncoder.decode output committed in
+    tests/golden/vae_tiny.pt; the CUDA-autocast policy stays within bf16 distance of it."""
+    from flux_fp8_api_b200 import autoencoder as A
+    from oracle import vae_oracle as V
+
+    g = torch.load(os.path.join(golden_dir, "vae_tiny.pt"))
+    p = g["params"]
+    shapes = A.AutoEncoder(A.AutoEncoderParams(**p))  # only its state-dict keys / shapes are used
+    sd = V.synthetic_state(shapes, g["state_seed"])
+    assert V.state_checksum(sd) == g["state_checksum"]
+    y32 = V.decode(g["z"], sd, p["ch_mult"], p["num_res_blocks"], p["scale_factor"], p["shift_factor"], policy="fp32")
+    assert (y32 - g["y_ref_fp32"]).abs().max().item() <= 2e-4 * g["y_ref_fp32"].abs().max().item()
+    ya = V.decode(g["z"], sd, p["ch_mult"], p["num_res_blocks"], p["scale_factor"], p["shift_factor"], policy="autocast")
+    assert torch.equal(ya, g["y_oracle_autocast"])
+    assert (ya.float() - g["y_ref_fp32"]).abs().mean().item() <= 0.01 * g["y_ref_fp32"].abs().max().item()

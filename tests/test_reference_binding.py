@@ -32,7 +32,7 @@ def bound():
 @needs_ref
 def test_staged_reference_is_the_unmodified_reference():
     m = R.verify_manifest()  # sha256 vs MANIFEST.json, and vs /root/reference where that exists
-    assert set(m["files"]) == {"float8_quantize.py", "modules/flux_model.py", "lora_loading.py"}
+    assert set(m["files"]) == {"float8_quantize.py", "modules/flux_model.py", "lora_loading.py", "modules/autoencoder.py"}
     ref = R.load()
     assert ref.fm.__file__.startswith(R.REF_DIR) and ref.f8.__file__.startswith(R.REF_DIR)
     # nothing of it is tracked by git
@@ -41,6 +41,31 @@ def test_staged_reference_is_the_unmodified_reference():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     tracked = subprocess.run(["git", "ls-files", "oracle/_ref"], cwd=root, capture_output=True, text=True).stdout.strip()
     assert tracked == ""
+
+
+@needs_ref
+def test_autoencoder_surface_matches_the_reference():
+    """Constructor signatures, state-dict keys and shapes of the decode half."""
+    import inspect
+
+    from flux_fp8_api_b200 import autoencoder as A
+
+    ref = R.load()
+    assert ref.ae is not None, getattr(ref, "ae_error", "")
+    for name in ("AttnBlock", "ResnetBlock", "Upsample", "Decoder", "AutoEncoder"):
+        ours, theirs = getattr(A, name), getattr(ref.ae, name)
+        assert [p.name for p in inspect.signature(ours.__init__).parameters.values()] == \
+               [p.name for p in inspect.signature(theirs.__init__).parameters.values()], name
+    assert set(A.AutoEncoderParams.model_fields) == set(ref.ae.AutoEncoderParams.model_fields)
+    params = dict(resolution=64, in_channels=3, ch=64, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=16,
+                  scale_factor=0.3611, shift_factor=0.1159)
+    theirs = ref.ae.AutoEncoder(ref.ae.AutoEncoderParams(**params)).state_dict()
+    ours = A.AutoEncoder(A.AutoEncoderParams(**params)).state_dict()
+    dec = {k: v.shape for k, v in theirs.items() if k.startswith("decoder.")}
+    assert {k: v.shape for k, v in ours.items()} == dec
+    # a reference checkpoint loads the way util.py:285 loads it (strict=False: the encoder half is not ours)
+    missing, unexpected = A.AutoEncoder(A.AutoEncoderParams(**params)).load_state_dict(theirs, strict=False)
+    assert not missing and all(k.startswith("encoder.") for k in unexpected)
 
 
 @needs_ref
