@@ -21,6 +21,8 @@ One JSON line on stdout (rank 0):
   e2e           the same through DenoiseSession.step_host (pinned host latents, H2D + step + D2H per step)
   roofline      tcgen05 FP8 GEMM kernels: algorithmic FLOP/s from CUDA events around every launch of an instrumented
                 pass, against the FP8 tensor-pipe ceiling MEASURED on this box in the same run (fluxb200_fp8_mma_probe)
+  vae_decode    one AutoEncoder.decode of the config's image size through our kernels, with the reference's
+                cuDNN decode on the same GPU beside it when gpu_reference ran
   gpu_reference the UNMODIFIED reference modules (oracle/_ref) timed on the same GPU: eager, and torch.compile'd blocks
   cpu_baseline  the reference's bf16 blocks on the host cores (bounded sample)
 
@@ -322,6 +324,88 @@ def run_reference_arm(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
+VAE_PARAMS = dict(resolution=256, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=16,
+                  scale_factor=0.3611, shift_factor=0.1159)  # util.py:178-188
+
+
+def vae_decode_flops(res):
+    """Multiply-add flops of Decoder.forward (modules/autoencoder.py:256-283) for a res x res image, convolutions and the
+    mid-block attention (conv_in from the 16 real latent channels, conv_out to the 3 real image channels)."""
+    h = res // 8
+    ch, mult = VAE_PARAMS["ch"], VAE_PARAMS["ch_mult"]
+    c = ch * mult[-1]
+    px = h * h
+    f = 2 * px * 16 * c * 9  # conv_in
+    res_block = lambda cin, cout, p: 2 * p * 9 * (cin * cout + cout * cout) + (2 * p * cin * cout if cin != cout else 0)
+    f += 2 * res_block(c, c, px) + 4 * 2 * px * c * c + 4 * px * px * c  # mid: two ResnetBlocks, q/k/v/proj_out, QK^T + PV
+    for lvl in reversed(range(len(mult))):
+        cout = ch * mult[lvl]
+        for _ in range(VAE_PARAMS["num_res_blocks"] + 1):
+            f += res_block(c, cout, px)
+            c = cout
+        if lvl != 0:
+            px *= 4
+            f += 2 * px * 9 * c * c  # Upsample.conv
+    return f + 2 * px * 9 * c * 3  # conv_out
+
+
+def time_cuda(fn, iters, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def vae_latent(cfg, dev):
+    g = torch.Generator(device=dev).manual_seed(5)
+    return torch.randn(1, 16, cfg["res"] // 8, cfg["res"] // 8, device=dev, generator=g) * 1.2
+
+
+def measure_vae_ours(cfg, dev):
+    """SURVEY.md 8f N4 beside the headline metric: one AutoEncoder.decode of the config's image size through this package's
+    kernels (seeded synthetic VAE weights)."""
+    from flux_fp8_api_b200 import _cabi as cabi, autoencoder as A, pipeline as PL
+
+    ae = A.AutoEncoder(A.AutoEncoderParams(**VAE_PARAMS))
+    PL.init_synthetic_vae_weights(ae, seed=77)
+    ae = ae.to(dev, torch.bfloat16).eval()
+    z = vae_latent(cfg, dev)
+    with torch.inference_mode():
+        ae.decode(z)
+        n0 = cabi.LAUNCHES
+        ae.decode(z)
+        calls = cabi.LAUNCHES - n0
+        ms = time_cuda(lambda: ae.decode(z), 5)
+    fl = vae_decode_flops(cfg["res"])
+    return {"workload": f"AutoEncoder.decode, 1 x {cfg['res']}x{cfg['res']} (modules/autoencoder.py:330-333 under bf16 autocast)",
+            "ms": ms, "tflops": fl / (ms * 1e-3) / 1e12, "flop": fl, "c_abi_calls": calls, "dtype": "bf16, fp32 accumulate"}
+
+
+def measure_vae_reference(ref, cfg, dev):
+    """The unmodified reference AutoEncoder on the same GPU, as flux_pipeline.py:431-434 runs it."""
+    from oracle import vae_oracle as V
+
+    if ref.ae is None:
+        return None
+    rae = ref.ae.AutoEncoder(ref.ae.AutoEncoderParams(**VAE_PARAMS))
+    rae.load_state_dict(V.synthetic_state(rae, seed=77), strict=False)
+    rae = rae.to(dev, torch.bfloat16).eval()
+    z = vae_latent(cfg, dev)
+
+    def run():
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, cache_enabled=False):
+            return rae.decode(z)
+
+    with torch.inference_mode():
+        return time_cuda(run, 3)
+
+
 def run_reference_gpu_arm(args, cfg):
     """--impl reference-gpu: the unmodified reference fp8 modules on cuda:0 -- F8Linear (torch._scaled_mm), eager
     elementwise ops, F.scaled_dot_product_attention -- in the denoise loop of flux_pipeline.py:627-651; mode `compiled`
@@ -396,6 +480,13 @@ def run_reference_gpu_arm(args, cfg):
     line = {"impl": "reference-gpu", "mode": args.mode, "metric": metric_name(cfg), "unit": "it/s", "steps": args.steps,
             "warmup": max(3, args.warmup), "setup_s": round(setup_s, 1), "torch": torch.__version__,
             "config": config_block(cfg, args.config, 1)}
+    if args.mode == "eager":
+        try:
+            del net
+            torch.cuda.empty_cache()
+            line["vae_decode_ms"] = measure_vae_reference(ref, cfg, dev)
+        except Exception as ex:  # noqa: BLE001
+            line["vae_decode_error"] = f"{type(ex).__name__}: {str(ex)[:200]}"
     if err is None:
         line.update(value=1000.0 / ms, ms_per_step=ms)
     else:
@@ -503,6 +594,7 @@ def main():
     ap.add_argument("--gpu-reference", default="both", choices=["none", "eager", "compiled", "both"],
                     help="time the unmodified reference modules on the same GPU after our arm (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode measurement (SURVEY 8f N4) beside the metric")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -688,6 +780,9 @@ def main():
     # ---- the unmodified reference on the same GPU (rank 0, N=1 only): the GPU-vs-GPU number SURVEY 8(d) asks for
     gpu_ref = None
     h2d_bytes, d2h_bytes = sess.h2d_bytes_per_step, sess.d2h_bytes_per_step
+    vae = None
+    if rank == 0 and world == 1 and not args.no_vae:
+        vae = measure_vae_ours(cfg, dev)
     if rank == 0 and world == 1 and args.gpu_reference != "none":
         del sess
         torch.cuda.empty_cache()
@@ -695,6 +790,10 @@ def main():
         for mode, r in gpu_ref.items():
             if r.get("value"):
                 r["speedup_ours_over_reference"] = value / r["value"]
+        ref_vae = (gpu_ref.get("eager") or {}).get("vae_decode_ms")
+        if vae is not None and ref_vae:
+            vae["reference_gpu_ms"] = ref_vae
+            vae["speedup_ours_over_reference"] = ref_vae / vae["ms"]
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu = None
@@ -723,6 +822,7 @@ def main():
             "clocks": clock_info,
             "roofline": roof,
             "gpu_reference": gpu_ref,
+            "vae_decode": vae,
             "cpu_baseline": cpu,
             "broadcast": {"bytes": bcast_bytes, "ms": bcast_ms},
         }

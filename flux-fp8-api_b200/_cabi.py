@@ -94,6 +94,7 @@ class ConvArgs(C.Structure):
         ("taps", C.c_int32),
         ("out_mode", C.c_int32),
         ("alpha", C.c_float),
+        ("gn_stats", C.c_void_p),
     ]
 
 
@@ -239,8 +240,8 @@ def load() -> C.CDLL:
         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
     ]
     lib.fluxb200_conv2d_nhwc.argtypes = [C.POINTER(ConvArgs), C.c_void_p]
-    lib.fluxb200_group_norm_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
-                                             C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.fluxb200_group_norm_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int64, C.c_int, C.c_float, C.c_int, C.c_void_p]
     lib.fluxb200_upsample2x_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.fluxb200_softmax_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
     lib.fluxb200_vae_latent_prep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,

@@ -70,16 +70,23 @@ class _Packed:
         return self.w, self.b
 
 
-def _conv(conv: nn.Conv2d, cache: _Packed, x: Tensor, residual: Optional[Tensor] = None, out_mode: int = 0) -> Tensor:
+def _conv(conv: nn.Conv2d, cache: _Packed, x: Tensor, residual: Optional[Tensor] = None, out_mode: int = 0,
+          want_stats: bool = False):
+    """The convolution through the C ABI.  want_stats: also return the fp64 GroupNorm sums of the output, accumulated by the
+    epilogue (None when the shape is outside what the fused path takes; the GroupNorm then reduces by itself)."""
     w, b = cache.get(conv)
     taps = conv.kernel_size[0] * conv.kernel_size[1]
-    return ops.conv2d_nhwc(x, w, b, taps, residual=residual, out_mode=out_mode)
+    stats = None
+    if want_stats and out_mode == 0 and ops.conv_can_fuse_gn_stats(x.shape[0], w.shape[0]):
+        stats = torch.empty((x.shape[0], 32, 2), dtype=torch.float64, device=x.device)
+    y = ops.conv2d_nhwc(x, w, b, taps, residual=residual, out_mode=out_mode, gn_stats=stats)
+    return (y, stats) if want_stats else y
 
 
-def _norm(gn: nn.GroupNorm, x: Tensor, swish: bool) -> Tensor:
+def _norm(gn: nn.GroupNorm, x: Tensor, swish: bool, stats: Optional[Tensor] = None) -> Tensor:
     if gn.num_groups != 32:
         raise ValueError("the GroupNorm kernel is built for 32 groups (modules/autoencoder.py:27, :62, :68, :245)")
-    return ops.group_norm_nhwc(x, gn.weight.detach().to(BF16), gn.bias.detach().to(BF16), gn.eps, swish)
+    return ops.group_norm_nhwc(x, gn.weight.detach().to(BF16), gn.bias.detach().to(BF16), gn.eps, swish, stats=stats)
 
 
 class AttnBlock(nn.Module):
@@ -99,13 +106,13 @@ class AttnBlock(nn.Module):
         self.proj_out = nn.Conv2d(in_channels, in_channels, kernel_size=1)
         self._pq, self._pk, self._pv, self._pp = _Packed(), _Packed(), _Packed(), _Packed()
 
-    def attention_nhwc(self, x: Tensor) -> Tensor:
+    def attention_nhwc(self, x: Tensor, stats: Optional[Tensor] = None) -> Tensor:
         B, H, W, Cn = x.shape
         S = H * W
         if S % 4:
             raise ValueError(f"AttnBlock: H*W = {S} must be a multiple of 4")
         Sp = ((S + 63) // 64) * 64  # K extent of the P @ V product (zero padded)
-        h = _norm(self.norm, x, swish=False)
+        h = _norm(self.norm, x, swish=False, stats=stats)
         q = _conv(self.q, self._pq, h)
         k = _conv(self.k, self._pk, h)
         wv, bv = self._pv.get(self.v)
@@ -127,14 +134,15 @@ class AttnBlock(nn.Module):
                 ops.conv2d_nhwc(p[:rows].view(1, 1, rows, Sp), vt[b], None, 1, out=ob[r0:r0 + rows].view(1, 1, rows, Cn))
         return o
 
-    def forward_nhwc(self, x: Tensor) -> Tensor:
-        return _conv(self.proj_out, self._pp, self.attention_nhwc(x), residual=x)
+    def forward_nhwc(self, x: Tensor, stats: Optional[Tensor] = None):
+        """(x, GroupNorm sums of x or None) -> (x + proj_out(attention(x)), sums of the result)."""
+        return _conv(self.proj_out, self._pp, self.attention_nhwc(x, stats), residual=x, want_stats=True)
 
     def attention(self, h_: Tensor) -> Tensor:
         return _to_nchw(self.attention_nhwc(_to_nhwc(h_)))
 
     def forward(self, x: Tensor) -> Tensor:
-        return _to_nchw(self.forward_nhwc(_to_nhwc(x)))
+        return _to_nchw(self.forward_nhwc(_to_nhwc(x))[0])
 
 
 class ResnetBlock(nn.Module):
@@ -153,16 +161,18 @@ class ResnetBlock(nn.Module):
             self.nin_shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
         self._p1, self._p2, self._ps = _Packed(), _Packed(), _Packed()
 
-    def forward_nhwc(self, x: Tensor) -> Tensor:
-        h = _norm(self.norm1, x, swish=True)
-        h = _conv(self.conv1, self._p1, h)
-        h = _norm(self.norm2, h, swish=True)
+    def forward_nhwc(self, x: Tensor, stats: Optional[Tensor] = None):
+        """(x, GroupNorm sums of x or None) -> (block output, its sums): every convolution that feeds a GroupNorm leaves
+        that GroupNorm's statistics behind, so the normalisation reads its input once."""
+        h = _norm(self.norm1, x, swish=True, stats=stats)
+        h, hs = _conv(self.conv1, self._p1, h, want_stats=True)
+        h = _norm(self.norm2, h, swish=True, stats=hs)
         if self.in_channels != self.out_channels:
             x = _conv(self.nin_shortcut, self._ps, x)
-        return _conv(self.conv2, self._p2, h, residual=x)
+        return _conv(self.conv2, self._p2, h, residual=x, want_stats=True)
 
     def forward(self, x: Tensor) -> Tensor:
-        return _to_nchw(self.forward_nhwc(_to_nhwc(x)))
+        return _to_nchw(self.forward_nhwc(_to_nhwc(x))[0])
 
 
 class Upsample(nn.Module):
@@ -173,11 +183,11 @@ class Upsample(nn.Module):
         self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
         self._p = _Packed()
 
-    def forward_nhwc(self, x: Tensor) -> Tensor:
-        return _conv(self.conv, self._p, ops.upsample2x_nhwc(x))
+    def forward_nhwc(self, x: Tensor, stats: Optional[Tensor] = None):
+        return _conv(self.conv, self._p, ops.upsample2x_nhwc(x), want_stats=True)
 
     def forward(self, x: Tensor) -> Tensor:
-        return _to_nchw(self.forward_nhwc(_to_nhwc(x)))
+        return _to_nchw(self.forward_nhwc(_to_nhwc(x))[0])
 
 
 class Decoder(nn.Module):
@@ -221,18 +231,18 @@ class Decoder(nn.Module):
 
     def forward_nhwc(self, h: Tensor) -> Tensor:
         """h: bf16 [B, H, W, 64-padded z channels] -> bf16 NCHW image [B, out_ch, 8H, 8W]."""
-        h = _conv(self.conv_in, self._pin, h)
-        h = self.mid.block_1.forward_nhwc(h)
-        h = self.mid.attn_1.forward_nhwc(h)
-        h = self.mid.block_2.forward_nhwc(h)
+        h, st = _conv(self.conv_in, self._pin, h, want_stats=True)
+        h, st = self.mid.block_1.forward_nhwc(h, st)
+        h, st = self.mid.attn_1.forward_nhwc(h, st)
+        h, st = self.mid.block_2.forward_nhwc(h, st)
         for i_level in reversed(range(self.num_resolutions)):
             for i_block in range(self.num_res_blocks + 1):
-                h = self.up[i_level].block[i_block].forward_nhwc(h)
+                h, st = self.up[i_level].block[i_block].forward_nhwc(h, st)
                 if len(self.up[i_level].attn) > 0:
-                    h = self.up[i_level].attn[i_block].forward_nhwc(h)
+                    h, st = self.up[i_level].attn[i_block].forward_nhwc(h, st)
             if i_level != 0:
-                h = self.up[i_level].upsample.forward_nhwc(h)
-        h = _norm(self.norm_out, h, swish=True)
+                h, st = self.up[i_level].upsample.forward_nhwc(h)
+        h = _norm(self.norm_out, h, swish=True, stats=st)
         return _conv(self.conv_out, self._pout, h, out_mode=2)
 
     def forward(self, z: Tensor) -> Tensor:

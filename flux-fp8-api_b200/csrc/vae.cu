@@ -15,6 +15,9 @@
 //   latent_prep         z / scale_factor + shift_factor (fp32, autoencoder.py:331-332) -> NHWC bf16, channels zero-padded to 64.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -37,21 +40,36 @@ struct ConvParams {
   void* out;
   int64_t ldo;
   int out_mode;  // 0 bf16 NHWC, 1 fp32 row-major scaled by alpha, 2 bf16 NCHW
+  int wide;      // out_mode 0: 32-byte accesses (N % 16 == 0, 32-byte aligned rows)
   float alpha;
+  double* gn_stats;  // out_mode 0, optional: [B][32][2] sums / sums of squares of the stored output (next GroupNorm)
+  int gn_cg;         // channels per group of that GroupNorm (N / 32)
 };
 
-template <int BN>
+constexpr int kConvStatsBatch = 4;  // the epilogue statistics are accumulated per CTA for up to this many images
+
+// HALO (3x3, 128-pixel row strips): one pipeline stage holds the 130 pixels [x0 - 1, x0 + 129) of ONE input row and
+// 64 channels, and the weights of the three horizontal taps of that row: the dx = -1 / 0 / +1 operands of the MMAs are
+// the SAME shared-memory rows read from a start address 0 / 1 / 2 rows into the tile, so a 3x3 convolution fetches each
+// input row three times instead of nine (the L2 -> shared-memory stream is what bounds the 128- and 256-channel levels).
+constexpr int kHaloRows = 130;
+constexpr int kHaloABytes = 17 * 1024;  // 130 x 128 B, rounded up so the weight tiles stay 1024-byte aligned
+
+template <int BN, bool HALO>
 struct ConvSmem {
   static constexpr int kBRows = BN / 2;  // this CTA's half of the weight rows
-  static constexpr int kStage = kConvABytes + kBRows * 128;
-  static constexpr int kStages = BN == 256 ? 6 : 8;
+  static constexpr int kA = HALO ? kHaloABytes : kConvABytes;
+  static constexpr int kBTile = kBRows * 128;
+  static constexpr int kStage = kA + (HALO ? 3 : 1) * kBTile;
+  static constexpr int kTxBytes = (HALO ? kHaloRows * 128 : kConvABytes) + (HALO ? 3 : 1) * kBTile;  // per CTA and stage
+  static constexpr int kStages = HALO ? (BN == 256 ? 3 : 4) : (BN == 256 ? 6 : 8);
   static constexpr int kBarOff = kStages * kStage;
   static constexpr int kTotal = kBarOff + 512 + 1024;
 };
 
-template <int BN>
+template <int BN, bool HALO>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams P) {
-  using S = ConvSmem<BN>;
+  using S = ConvSmem<BN, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
@@ -59,6 +77,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint64_t* tfull_bar = empty_bar + S::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  __shared__ double gn_acc[8][kConvStatsBatch][32][2];  // per epilogue warp: no shared-memory atomics
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,6 +105,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     tmem_alloc_2sm(tmem_ptr, 2 * BN);
     tmem_relinquish_2sm();
   }
+  if (P.gn_stats != nullptr)
+    for (int i = threadIdx.x; i < 8 * kConvStatsBatch * 64; i += kConvThreads) (&gn_acc[0][0][0][0])[i] = 0.0;
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -94,7 +115,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   pdl_launch_dependents();
 
   const int num_tiles = P.num_tiles;
-  const int kiters = P.taps * P.kchunks;
+  const int kiters = (HALO ? 3 : P.taps) * P.kchunks;  // pipeline stages per tile
 
   // pixel tile `mt` -> (batch, first row, first column); tiles past the end are clamped (their rows are never stored)
   auto tile_origin = [&](int mt, int& b, int& y0, int& x0) {
@@ -117,16 +138,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       int b, y0, x0;
       tile_origin(mt, b, y0, x0);
       const int n0 = n_blk * BN + static_cast<int>(rank) * S::kBRows;
-      for (int tap = 0; tap < P.taps; ++tap) {
-        const int dy = P.taps == 9 ? tap / 3 - 1 : 0;
-        const int dx = P.taps == 9 ? tap % 3 - 1 : 0;
+      for (int tap = 0; tap < (HALO ? 3 : P.taps); ++tap) {
+        const int dy = HALO ? tap - 1 : (P.taps == 9 ? tap / 3 - 1 : 0);
+        const int dx = HALO ? -1 : (P.taps == 9 ? tap % 3 - 1 : 0);  // HALO: the box starts one pixel to the left
         for (int kc = 0; kc < P.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStage;
           if (elect_one()) {
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStage);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kTxBytes);
             tma_load_4d_2sm(sa, &P.tmap_a, &full_bar[stage], kc * 64, x0 + dx, y0 + dy, b);
-            tma_load_2d_2sm(sa + kConvABytes, &P.tmap_b, &full_bar[stage], (tap * P.kchunks + kc) * 64, n0, kEvictLast);
+            if constexpr (HALO) {
+#pragma unroll
+              for (int t = 0; t < 3; ++t)
+                tma_load_2d_2sm(sa + S::kA + t * S::kBTile, &P.tmap_b, &full_bar[stage], ((tap * 3 + t) * P.kchunks + kc) * 64, n0,
+                                kEvictLast);
+            } else {
+              tma_load_2d_2sm(sa + S::kA, &P.tmap_b, &full_bar[stage], (tap * P.kchunks + kc) * 64, n0, kEvictLast);
+            }
           }
           __syncwarp();
           if (++stage == S::kStages) {
@@ -145,7 +173,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       int as = 0;
       uint32_t aphase = 0;
       const uint64_t a_desc0 = make_desc_sw128(smem_u32(smem), 16, 1024);
-      const uint64_t b_desc0 = make_desc_sw128(smem_u32(smem) + kConvABytes, 16, 1024);
+      const uint64_t b_desc0 = make_desc_sw128(smem_u32(smem) + S::kA, 16, 1024);
       for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
@@ -156,9 +184,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           const uint64_t ad = desc_advance(a_desc0, stage * S::kStage);
           const uint64_t bd = desc_advance(b_desc0, stage * S::kStage);
           if (elect_one()) {
+            if constexpr (HALO) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_f16_ss_2sm(d_tmem, desc_advance(ad, k * 32), desc_advance(bd, k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int t = 0; t < 3; ++t) {
+                // tap dx = t - 1 reads rows [t, t + 128) of the 130-row tile: the descriptor simply starts t rows (t * 128
+                // bytes) into it.  MEASURED: the 128-byte swizzle is a function of the absolute shared-memory address on
+                // both sides (TMA write, MMA read), so a start that is not aligned to the 8-row atom needs NO "base offset"
+                // in descriptor bits 49-51 -- with the field set to the start row's phase the results are wrong.
+                const uint64_t at = desc_advance(ad, t * 128);
+                const uint64_t bt = desc_advance(bd, t * S::kBTile);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  mma_f16_ss_2sm(d_tmem, desc_advance(at, k * 32), desc_advance(bt, k * 32), idesc, (kb | t | k) != 0 ? 1u : 0u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_f16_ss_2sm(d_tmem, desc_advance(ad, k * 32), desc_advance(bd, k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             tc_commit_2sm(&empty_bar[stage], 3);
             if (kb == kiters - 1) tc_commit_2sm(&tfull_bar[as], 3);
           }
@@ -191,11 +234,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       const int y = y0 + hh, x = x0 + ww;
       const bool valid = mt < P.m_tiles && y < P.H && x < P.W;
       const int64_t pix = (static_cast<int64_t>(b) * P.H + y) * P.W + x;
+      const int col0 = n_blk * BN + part * kPartCols;
+      // the residual rows of this tile do not depend on the accumulator: fetch them while the MMAs are still running
+      // (issued just in time they put one DRAM round trip per 8 channels in front of every store)
+      u32x8 rpre[kPartCols / 16];
+      const bool wide_res = P.wide && P.residual != nullptr && P.out_mode == 0 && valid;
+      if (wide_res) {
+        const __nv_bfloat16* res = P.residual + pix * P.ld_res + col0;
+#pragma unroll
+        for (int i = 0; i < kPartCols / 16; ++i)
+          if (col0 + i * 16 < P.N) rpre[i] = ldg_v8(res + i * 16);
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN + part * kPartCols;
-      const int col0 = n_blk * BN + part * kPartCols;
-#pragma unroll 1
+      // Fused GroupNorm statistics of the STORED output: per thread 16 granules (kG adjacent channels) x {sum, sum of
+      // squares} for its pixel, reduced over the warp's 32 pixels once per tile by a transposing butterfly (31 shuffles
+      // for all 32 values), then added by single lanes to this warp's private fp64 accumulators.
+      constexpr int kG = BN >= 256 ? 8 : 4;
+      float gacc[32];
+      const bool do_stats = P.gn_stats != nullptr;
+      if (do_stats) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gacc[j] = 0.f;
+      }
+#pragma unroll
       for (int c = 0; c < kPartCols / 32; ++c) {
         uint32_t v[32];
         const int col = col0 + c * 32;
@@ -217,6 +280,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           // h = bf16(bf16(acc) + bias)  (cuDNN convolution, then the bias add of at::_convolution), out = bf16(residual + h)
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + pix * P.ldo + col;
           const __nv_bfloat16* res = P.residual ? P.residual + pix * P.ld_res + col : nullptr;
+          uint32_t ow[16];  // the chunk's 32 outputs, packed
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (col + q * 8 >= P.N) break;
@@ -234,8 +298,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
               }
             }
             if (res) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(res + q * 8);
-              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+              uint32_t rw[4];
+              if (wide_res) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rw[j] = rpre[c * 2 + (q >> 1)].v[(q & 1) * 4 + j];
+              } else {
+                const uint4 rv = *reinterpret_cast<const uint4*>(res + q * 8);
+                rw[0] = rv.x, rw[1] = rv.y, rw[2] = rv.z, rw[3] = rv.w;
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 rf = unpack_bf16x2(rw[j]);
@@ -243,8 +313,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 h[2 * j + 1] += rf.y;
               }
             }
-            *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
-                                                                pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ow[q * 4 + j] = pack_bf16x2(h[2 * j], h[2 * j + 1]);
+            if (P.wide) {  // 32-byte stores: one full sector per thread and instruction
+              if (q & 1)
+                stg_v8(dst + (q - 1) * 8, ow[q * 4 - 4], ow[q * 4 - 3], ow[q * 4 - 2], ow[q * 4 - 1], ow[q * 4], ow[q * 4 + 1],
+                       ow[q * 4 + 2], ow[q * 4 + 3]);
+            } else {
+              *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(ow[q * 4], ow[q * 4 + 1], ow[q * 4 + 2], ow[q * 4 + 3]);
+            }
+            if (do_stats) {
+              const float2 f0 = unpack_bf16x2(ow[q * 4]), f1 = unpack_bf16x2(ow[q * 4 + 1]);
+              const float2 f2 = unpack_bf16x2(ow[q * 4 + 2]), f3 = unpack_bf16x2(ow[q * 4 + 3]);
+              const float slo = (f0.x + f0.y) + (f1.x + f1.y), shi = (f2.x + f2.y) + (f3.x + f3.y);
+              const float qlo = (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y);
+              const float qhi = (f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y);
+              if constexpr (kG == 8) {
+                gacc[2 * (c * 4 + q)] += slo + shi;
+                gacc[2 * (c * 4 + q) + 1] += qlo + qhi;
+              } else if constexpr (kPartCols / 4 <= 16) {
+                gacc[2 * (c * 8 + q * 2)] += slo;
+                gacc[2 * (c * 8 + q * 2) + 1] += qlo;
+                gacc[2 * (c * 8 + q * 2 + 1)] += shi;
+                gacc[2 * (c * 8 + q * 2 + 1) + 1] += qhi;
+              }
+            }
           }
         } else {
           // NCHW: out[(b * N + n) * ldo + y * W + x]; a warp's lanes are adjacent pixels of one row
@@ -260,12 +353,45 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           }
         }
       }
+      if (do_stats) {
+        __syncwarp();
+#pragma unroll
+        for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int j = 0; j < cnt; ++j) {
+            const float send = upper ? gacc[j] : gacc[j + cnt];
+            const float keep = upper ? gacc[j + cnt] : gacc[j];
+            gacc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        // lane L now owns value L = granule (L >> 1), {sum, squares} (L & 1), summed over the warp's pixels
+        float val = gacc[0];
+        const int ratio = P.gn_cg / kG;  // granules per group: 1, 2 or 4 ...
+        for (int o = 1; o < ratio; o <<= 1) val += __shfl_xor_sync(0xffffffffu, val, o * 2);
+        const int granule = lane >> 1;
+        const int gcol = col0 + granule * kG;
+        if ((granule & (ratio - 1)) == 0 && granule * kG < kPartCols && gcol < P.N) {
+          const int bslot = b < kConvStatsBatch ? b : kConvStatsBatch - 1;
+          gn_acc[warp - kConvEpiWarp0][bslot][gcol / P.gn_cg][lane & 1] += static_cast<double>(val);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(&tempty_bar[as], 0);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
+      }
+    }
+    if (P.gn_stats != nullptr) {
+      named_bar_sync(1, kEpiWarps * 32);  // every epilogue warp of this CTA has added its last tile
+      const int nb = P.B < kConvStatsBatch ? P.B : kConvStatsBatch;
+      for (int i = threadIdx.x - kConvEpiWarp0 * 32; i < nb * 64; i += kEpiWarps * 32) {
+        double v = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) v += (&gn_acc[w8][0][0][0])[i];
+        if (v != 0.0) atomicAdd(P.gn_stats + i, v);
       }
     }
   }
@@ -278,12 +404,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   }
 }
 
-template <int BN>
+template <int BN, bool HALO = false>
 static int launch_conv(const ConvParams& P, cudaStream_t stream) {
-  using S = ConvSmem<BN>;
-  static_assert(S::kTotal <= 227 * 1024, "conv smem budget");
+  using S = ConvSmem<BN, HALO>;
+  static_assert(S::kTotal + 18 * 1024 <= 227 * 1024, "conv smem budget (dynamic + the static statistics accumulators)");
   static bool attr_set = false;
-  auto kern = conv_igemm_kernel<BN>;
+  auto kern = conv_igemm_kernel<BN, HALO>;
   if (!attr_set) {
     FB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
@@ -341,43 +467,55 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
               static_cast<double>(acc[threadIdx.x >> 1][threadIdx.x & 1]));
 }
 
-// y = bf16( f( (x - mean) * rstd * gamma + beta ) ), f = swish (x * sigmoid(x)) or identity; optional 2x nearest
-// upsampling of the OUTPUT is not done here (the decoder upsamples residual sums, not normalised tensors).
+// y = bf16( f( x * a_c + b_c ) ), a_c = rstd * gamma_c, b_c = beta_c - mean * a_c (the form torch's CUDA GroupNorm
+// evaluates), f = swish (x * sigmoid(x)) or identity.  grid (pixel blocks, B); a thread owns one 8-channel vector
+// position and walks the block's pixels, so the per-channel affine lives in 16 registers.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const double* __restrict__ stats,
                                                        const __nv_bfloat16* __restrict__ gamma,
                                                        const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                                                       int64_t HW, int C, float eps, int swish, int64_t total_vec) {
+                                                       int64_t HW, int C, float eps, int swish, int pix_per_block) {
+  __shared__ float sa[2048], sb[2048];
+  const int b = blockIdx.y;
   const int vec_per_pix = C >> 3;
   const int cg = C >> 5;
   const double inv_n = 1.0 / (static_cast<double>(HW) * cg);
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < total_vec; i += static_cast<int64_t>(gridDim.x) * 256) {
-    const int vc = static_cast<int>(i % vec_per_pix);
-    const int64_t pix = i / vec_per_pix;
-    const int b = static_cast<int>(pix / HW);
-    const int c0 = vc * 8;
-    const uint4 v = *reinterpret_cast<const uint4*>(x + i * 8);
-    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + c0));
-    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(beta + c0));
-    const uint32_t xw[4] = {v.x, v.y, v.z, v.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const double* st = stats + (static_cast<int64_t>(b) * 32 + c / cg) * 2;
+    const double mean_d = st[0] * inv_n;
+    const double var_d = fmax(st[1] * inv_n - mean_d * mean_d, 0.0);
+    const float rstd = static_cast<float>(1.0 / sqrt(var_d + static_cast<double>(eps)));
+    const float a = rstd * __bfloat162float(gamma[c]);
+    sa[c] = a;
+    sb[c] = __bfloat162float(beta[c]) - static_cast<float>(mean_d) * a;
+  }
+  __syncthreads();
+  const int vc = threadIdx.x % vec_per_pix;
+  const int prow = threadIdx.x / vec_per_pix;
+  const int rows = 256 / vec_per_pix;
+  float ca[8], cb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ca[j] = sa[vc * 8 + j], cb[j] = sb[vc * 8 + j];
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
+  const __nv_bfloat16* xb = x + static_cast<int64_t>(b) * HW * C + vc * 8;
+  __nv_bfloat16* yb = y + static_cast<int64_t>(b) * HW * C + vc * 8;
+#pragma unroll 4
+  for (int64_t p = p0 + prow; p < p1; p += rows) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xb + p * C);
+    const uint32_t xw[4] = {v.x, v.y, v.z, v.w};
     uint32_t ow[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int g = (c0 + 2 * j) / cg;  // both channels of a pair are in the same group (cg is even)
-      const double* st = stats + (static_cast<int64_t>(b) * 32 + g) * 2;
-      const double mean_d = st[0] * inv_n;
-      const double var_d = fmax(st[1] * inv_n - mean_d * mean_d, 0.0);
-      const float mean = static_cast<float>(mean_d);
-      const float rstd = static_cast<float>(1.0 / sqrt(var_d + static_cast<double>(eps)));
-      const float2 xf = unpack_bf16x2(xw[j]), gf = unpack_bf16x2(gw[j]), bf = unpack_bf16x2(bw[j]);
-      float o0 = (xf.x - mean) * rstd * gf.x + bf.x;
-      float o1 = (xf.y - mean) * rstd * gf.y + bf.y;
+      const float2 xf = unpack_bf16x2(xw[j]);
+      float o0 = fmaf(xf.x, ca[2 * j], cb[2 * j]);
+      float o1 = fmaf(xf.y, ca[2 * j + 1], cb[2 * j + 1]);
       if (swish) {
-        o0 = o0 / (1.f + __expf(-o0));
-        o1 = o1 / (1.f + __expf(-o1));
+        o0 = __fdividef(o0, 1.f + __expf(-o0));
+        o1 = __fdividef(o1, 1.f + __expf(-o1));
       }
       ow[j] = pack_bf16x2(o0, o1);
     }
-    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    *reinterpret_cast<uint4*>(yb + p * C) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 
@@ -510,41 +648,57 @@ int fluxb200_conv2d_nhwc(const fluxb200_conv_args* a, fluxb200_stream_t stream_)
   P.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   P.ld_res = a->ld_res;
   P.out = a->out, P.ldo = a->ldo, P.out_mode = a->out_mode, P.alpha = a->alpha;
+  P.wide = a->out_mode == 0 && a->N % 16 == 0 && a->ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 31) == 0 &&
+           (a->residual == nullptr || (a->ld_res % 16 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 31) == 0));
+  P.gn_stats = a->gn_stats;
+  P.gn_cg = a->N / 32;
+  if (a->gn_stats != nullptr) {
+    FB_REQUIRE(a->out_mode == 0 && (a->N == 128 || a->N == 256 || a->N == 512 || a->N == 1024) &&
+                   a->B <= kConvStatsBatch,
+               "fluxb200_conv2d_nhwc: fused GroupNorm statistics need out_mode 0, N in {128, 256, 512, 1024}, B <= %d",
+               kConvStatsBatch);
+    FB_CUDA_OK(cudaMemsetAsync(a->gn_stats, 0, sizeof(double) * 64 * a->B, stream));
+  }
   const int64_t ldx = a->ldx > 0 ? a->ldx : a->Cin;  // channel stride of a pixel (elements)
   FB_REQUIRE(ldx % 8 == 0, "fluxb200_conv2d_nhwc: ldx must be a multiple of 8");
   const uint64_t dims[4] = {static_cast<uint64_t>(a->Cin), static_cast<uint64_t>(a->W), static_cast<uint64_t>(a->H),
                             static_cast<uint64_t>(a->B)};
   const uint64_t strides[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(ldx) * 2 * a->W,
                                static_cast<uint64_t>(ldx) * 2 * a->W * a->H};
-  const uint32_t box[4] = {64, static_cast<uint32_t>(P.tw), static_cast<uint32_t>(P.th), 1};
+  // 3x3 on 128-pixel row strips: the halo form (one 130-pixel row box serves the three horizontal taps)
+  static const bool halo_on = [] { const char* e = getenv("FLUXB200_CONV_HALO"); return e == nullptr || atoi(e) != 0; }();
+  const bool halo = halo_on && a->taps == 9 && P.tw == 128 && bn >= 128;
+  const uint32_t box[4] = {64, static_cast<uint32_t>(halo ? kHaloRows : P.tw), static_cast<uint32_t>(P.th), 1};
   int rc = make_tmap_4d(&P.tmap_a, a->x, 2, dims, strides, box);
   if (rc) return rc;
   const int64_t K = static_cast<int64_t>(a->taps) * a->Cin;
   const int64_t ldw = a->ldw > 0 ? a->ldw : K;
   rc = make_tmap_2d(&P.tmap_b, a->w, 2, a->N, K, ldw * 2, bn / 2, 64);
   if (rc) return rc;
+  if (halo) return bn == 256 ? launch_conv<256, true>(P, stream) : launch_conv<128, true>(P, stream);
   if (bn == 256) return launch_conv<256>(P, stream);
   if (bn == 128) return launch_conv<128>(P, stream);
   return launch_conv<64>(P, stream);
 }
 
 int fluxb200_group_norm_nhwc(const void* x_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16, double* stats_ws,
-                             int B, int64_t HW, int C, float eps, int swish, fluxb200_stream_t stream_) {
+                             int stats_ready, int B, int64_t HW, int C, float eps, int swish, fluxb200_stream_t stream_) {
   using namespace fb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FB_REQUIRE(x_bf16 && gamma_bf16 && beta_bf16 && y_bf16 && stats_ws, "fluxb200_group_norm_nhwc: null operand");
   FB_REQUIRE(B > 0 && HW > 0 && C >= 64 && C % 64 == 0 && 2048 % C == 0, "fluxb200_group_norm_nhwc: C=%d must be 64 .. 2048, a power-of-two multiple of 64", C);
-  FB_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 64 * B, stream));
-  const int pix_per_block = 256;
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
+  if (!stats_ready) {
+    FB_CUDA_OK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 64 * B, stream));
+    const int spb = 512;
+    dim3 sgrid(static_cast<unsigned>((HW + spb - 1) / spb), B);
+    gn_stats_kernel<<<sgrid, 256, 0, stream>>>(xp, stats_ws, HW, C, spb);
+  }
+  const int pix_per_block = HW >= (1 << 18) ? 1024 : 256;
   dim3 grid(static_cast<unsigned>((HW + pix_per_block - 1) / pix_per_block), B);
-  gn_stats_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), stats_ws, HW, C, pix_per_block);
-  const int64_t total_vec = static_cast<int64_t>(B) * HW * (C / 8);
-  const int64_t want = (total_vec + 255) / 256;
-  const int blocks = static_cast<int>(want < sm_count() * 16 ? want : sm_count() * 16);
-  gn_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), stats_ws,
-                                              reinterpret_cast<const __nv_bfloat16*>(gamma_bf16),
-                                              reinterpret_cast<const __nv_bfloat16*>(beta_bf16),
-                                              reinterpret_cast<__nv_bfloat16*>(y_bf16), HW, C, eps, swish, total_vec);
+  gn_apply_kernel<<<grid, 256, 0, stream>>>(xp, stats_ws, reinterpret_cast<const __nv_bfloat16*>(gamma_bf16),
+                                            reinterpret_cast<const __nv_bfloat16*>(beta_bf16),
+                                            reinterpret_cast<__nv_bfloat16*>(y_bf16), HW, C, eps, swish, pix_per_block);
   FB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -564,9 +564,11 @@ def pack_conv_weight(weight: Tensor, cin_pad: Optional[int] = None) -> Tensor:
 
 
 def conv2d_nhwc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], taps: int, residual: Optional[Tensor] = None,
-                out: Optional[Tensor] = None, out_mode: int = 0, alpha: float = 1.0, nchw_plane: Optional[int] = None) -> Tensor:
+                out: Optional[Tensor] = None, out_mode: int = 0, alpha: float = 1.0, nchw_plane: Optional[int] = None,
+                gn_stats: Optional[Tensor] = None) -> Tensor:
     """fluxb200_conv2d_nhwc.  x bf16 [B, H, W, Cin] (Cin % 64 == 0); w_packed from pack_conv_weight.
-    out_mode 0 -> bf16 [B, H, W, N] (+ bias, + residual); 1 -> fp32 [B, H, W, N] = alpha * acc; 2 -> bf16 NCHW [B, N, H, W]."""
+    out_mode 0 -> bf16 [B, H, W, N] (+ bias, + residual); 1 -> fp32 [B, H, W, N] = alpha * acc; 2 -> bf16 NCHW [B, N, H, W].
+    gn_stats (fp64 [B, 32, 2], out_mode 0): filled with the GroupNorm(32) sums of the stored output by the epilogue."""
     cabi.require_cuda(x, w_packed)
     _want(x, BF16, "conv2d_nhwc: x"), _want(w_packed, BF16, "conv2d_nhwc: w"), _want(bias, BF16, "conv2d_nhwc: bias")
     _want(residual, BF16, "conv2d_nhwc: residual")
@@ -597,30 +599,45 @@ def conv2d_nhwc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], taps: int, 
         a.residual, a.ld_res = residual.data_ptr(), N
     a.ldo = N if out_mode != 2 else (nchw_plane or H * W)
     a.B, a.H, a.W, a.Cin, a.N, a.taps, a.out_mode, a.alpha = B, H, W, Cin, N, taps, out_mode, alpha
+    if gn_stats is not None:
+        _want(gn_stats, torch.float64, "conv2d_nhwc: gn_stats")
+        if gn_stats.numel() != B * 64 or not gn_stats.is_contiguous():
+            raise ValueError("conv2d_nhwc: gn_stats must be a contiguous fp64 [B, 32, 2]")
+        a.gn_stats = gn_stats.data_ptr()
     _timed("conv2d", 2.0 * B * H * W * N * taps * Cin,
            lambda: cabi.check(cabi.load().fluxb200_conv2d_nhwc(C.byref(a), cabi.stream_ptr()), "fluxb200_conv2d_nhwc"),
            f"{B}x{H}x{W} {Cin}->{N} taps {taps}" if KERNEL_TIMELINE is not None else "")
     return out
 
 
-_gn_ws = {}
+#: the fused statistics of fluxb200_conv2d_nhwc are kept per CTA for at most this many images
+CONV_STATS_MAX_BATCH = 4
 
 
-def group_norm_nhwc(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, swish: bool, out: Optional[Tensor] = None) -> Tensor:
-    """nn.GroupNorm(32, C, eps) (+ x * sigmoid(x)) on a channels-last bf16 tensor, fp32 arithmetic, bf16 result."""
+def conv_can_fuse_gn_stats(B: int, N: int) -> bool:
+    return B <= CONV_STATS_MAX_BATCH and N in (128, 256, 512, 1024)
+
+
+def group_norm_nhwc(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, swish: bool, out: Optional[Tensor] = None,
+                    stats: Optional[Tensor] = None) -> Tensor:
+    """nn.GroupNorm(32, C, eps) (+ x * sigmoid(x)) on a channels-last bf16 tensor, fp32 arithmetic, bf16 result.
+    stats: the fp64 [B, 32, 2] sums a producing conv2d_nhwc(gn_stats=...) already left behind (skips the reduction pass)."""
     cabi.require_cuda(x, gamma, beta)
     _want(x, BF16, "group_norm_nhwc: x"), _want(gamma, BF16, "group_norm_nhwc: weight"), _want(beta, BF16, "group_norm_nhwc: bias")
+    _want(stats, torch.float64, "group_norm_nhwc: stats")
     _contig(x, "group_norm_nhwc: x")
     B, H, W, Cn = x.shape
     if out is None:
         out = torch.empty_like(x)
-    ws = _gn_ws.get((x.device, B))
-    if ws is None:
-        ws = _gn_ws[(x.device, B)] = torch.zeros(64 * B, dtype=torch.float64, device=x.device)
+    ready = stats is not None
+    if ready and (stats.numel() != B * 64 or not stats.is_contiguous()):
+        raise ValueError("group_norm_nhwc: stats must be a contiguous fp64 [B, 32, 2]")
+    ws = stats if ready else torch.empty(64 * B, dtype=torch.float64, device=x.device)
     _timed("group_norm", 0.0,
            lambda: cabi.check(cabi.load().fluxb200_group_norm_nhwc(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-                                                                   ws.data_ptr(), B, H * W, Cn, eps, int(swish), cabi.stream_ptr()),
-                              "fluxb200_group_norm_nhwc"))
+                                                                   ws.data_ptr(), int(ready), B, H * W, Cn, eps, int(swish),
+                                                                   cabi.stream_ptr()), "fluxb200_group_norm_nhwc"),
+           f"{B}x{H}x{W}x{Cn}{' (stats from the conv)' if ready else ''}" if KERNEL_TIMELINE is not None else "")
     return out
 
 

@@ -50,6 +50,49 @@ def patchify(latent: Tensor) -> Tensor:
     return x.reshape(x.shape[0], -1, x.shape[3] * x.shape[4] * x.shape[5])
 
 
+def unpack(x: Tensor, height: int, width: int) -> Tensor:
+    """[B, (h w), (c 2 2)] denoised tokens -> [B, c, 2h, 2w] latent (flux_pipeline.py:440-448: the inverse of patchify;
+    h = ceil(height / 16), w = ceil(width / 16))."""
+    h, w = math.ceil(height / 16), math.ceil(width / 16)
+    B, L, D = x.shape
+    if L != h * w or D % 4:
+        raise ValueError(f"unpack: {tuple(x.shape)} is not a {h} x {w} token grid of 2x2 patches")
+    c = D // 4
+    return x.reshape(B, h, w, c, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, c, 2 * h, 2 * w)
+
+
+def vae_decode(ae, x: Tensor, height: int, width: int) -> Tensor:
+    """FluxPipeline.vae_decode (flux_pipeline.py:422-438): tokens -> fp32 latent -> `ae.decode` (this package's AutoEncoder: the
+    autocast region of the reference is what its kernels implement) -> bf16 image [B, 3, height, width] in [-1, 1]."""
+    with torch.inference_mode():
+        return ae.decode(unpack(x.float(), height, width).contiguous())
+
+
+def init_synthetic_vae_weights(ae: nn.Module, seed: int = 77, dtype=BF16) -> None:
+    """Seeded parameters for an AutoEncoder (there are no weights to download): N(0, 1/fan_in) convolutions, GroupNorm affine
+    1 + 0.1 N / 0.1 N, biases 0.05 N, the attention's q / k projections x3 so its softmax is not uniform.  Keys are visited in
+    sorted order, so the same seed gives the same tensors to any module with the reference's decoder keys."""
+    g = torch.Generator().manual_seed(seed)
+    full = ae.state_dict()
+    new = {}
+    for k in sorted(full):
+        if not k.startswith("decoder."):
+            continue
+        shape = full[k].shape
+        if ".norm" in k and k.endswith(".weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif ".norm" in k and k.endswith(".bias"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif k.endswith(".weight"):
+            t = torch.randn(shape, generator=g) * (1.0 / math.sqrt(full[k][0].numel()))
+            if ".attn_1.q." in k or ".attn_1.k." in k:
+                t = t * 3.0
+        else:
+            t = 0.05 * torch.randn(shape, generator=g)
+        new[k] = t.to(dtype)
+    ae.load_state_dict(new, strict=False)
+
+
 def make_img_ids(batch: int, h2: int, w2: int, device, dtype=BF16) -> Tensor:
     """Position ids (0, row, col) of the token grid (flux_pipeline.py:280-292)."""
     ids = torch.zeros(h2, w2, 3, device=device, dtype=dtype)

@@ -221,10 +221,14 @@ typedef struct fluxb200_conv_args {
   int64_t ldx, ldw, ld_res, ldo;
   int32_t B, H, W, Cin, N, taps, out_mode;
   float alpha;          /* out_mode 1 */
+  double* gn_stats;     /* optional (out_mode 0, B <= 4, N % 64 == 0): receives the GroupNorm(32) statistics of the STORED
+                           output, [B][32]{sum, sum of squares} -- pass it to fluxb200_group_norm_nhwc with stats_ready = 1
+                           and the normalisation of this tensor skips its own reduction pass */
 } fluxb200_conv_args;
 int fluxb200_conv2d_nhwc(const fluxb200_conv_args* args, fluxb200_stream_t stream);
 int fluxb200_group_norm_nhwc(const void* x_bf16, const void* gamma_bf16, const void* beta_bf16, void* y_bf16,
-                             double* stats_ws, int B, int64_t HW, int C, float eps, int swish, fluxb200_stream_t stream);
+                             double* stats_ws, int stats_ready, int B, int64_t HW, int C, float eps, int swish,
+                             fluxb200_stream_t stream);
 int fluxb200_upsample2x_nhwc(const void* x_bf16, void* y_bf16, int B, int H, int W, int C, fluxb200_stream_t stream);
 int fluxb200_softmax_rows(const float* scores, int64_t lds, void* p_bf16, int64_t ldp, int rows, int n,
                           fluxb200_stream_t stream);

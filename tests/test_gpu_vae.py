@@ -115,6 +115,27 @@ def test_group_norm_swish_is_the_fp32_formula_rounded_once(C, swish):
     assert (d > 0).float().mean().item() < 0.03  # a few results sit on a rounding boundary
 
 
+def test_conv_epilogue_statistics_equal_the_standalone_reduction():
+    """GroupNorm fed by the producing convolution's fused sums == GroupNorm reducing the stored tensor itself."""
+    for (B, H, W, Cin, N) in ((2, 40, 24, 128, 256), (4, 20, 36, 64, 1024), (3, 16, 48, 256, 512), (1, 128, 128, 128, 128)):
+        x = _rand((B, H, W, Cin), 50)
+        w = _rand((N, Cin, 3, 3), 51, 1.0 / math.sqrt(Cin * 9))
+        b, r = _rand((N,), 52, 0.3), _rand((B, H, W, N), 53)
+        st = torch.empty((B, 32, 2), dtype=torch.float64, device=DEV)
+        y = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), b, 9, residual=r, gn_stats=st)
+        yf = y.float().reshape(B, H * W, 32, N // 32)
+        ref = torch.stack([yf.double().sum((1, 3)), (yf.double() ** 2).sum((1, 3))], -1)
+        assert torch.allclose(st, ref, rtol=1e-6, atol=1e-3), (st - ref).abs().max()
+        gamma, beta = (1 + 0.1 * _rand((N,), 54).float()).to(BF16), _rand((N,), 55, 0.1)
+        fused = ops.group_norm_nhwc(y, gamma, beta, 1e-6, True, stats=st)
+        alone = ops.group_norm_nhwc(y, gamma, beta, 1e-6, True)
+        d = (fused.float() - alone.float()).abs()
+        assert d.max().item() <= ULP * alone.float().abs().max().item() and (d > 0).float().mean().item() < 1e-3
+    with pytest.raises(ValueError):
+        ops.conv2d_nhwc(_rand((5, 8, 8, 64), 56), ops.pack_conv_weight(_rand((64, 64, 3, 3), 57)), None, 9,
+                        gn_stats=torch.empty((5, 32, 2), dtype=torch.float64, device=DEV))  # more images than the epilogue keeps
+
+
 def test_upsample2x_is_nearest():
     x = _rand((2, 6, 10, 64), 30)
     y = ops.upsample2x_nhwc(x)

@@ -309,3 +309,31 @@ def test_vae_host_side_keys_packing_and_loud_failure():
         assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
     with pytest.raises(NotImplementedError):
         m.encode(torch.zeros(1, 3, 64, 64))
+
+
+def test_unpack_inverts_patchify_like_the_reference_rearrange():
+    """pipeline.unpack == einops `b (h w) (c ph pw) -> b c (h ph) (w pw)` (flux_pipeline.py:440-448)."""
+    from einops import rearrange
+
+    from flux_fp8_api_b200 import pipeline as PL
+
+    lat = torch.randn(2, 16, 12, 20)
+    tok = PL.patchify(lat)
+    assert torch.equal(PL.unpack(tok, 96, 160), lat)
+    assert torch.equal(PL.unpack(tok, 96, 160), rearrange(tok, "b (h w) (c ph pw) -> b c (h ph) (w pw)", h=6, w=10, ph=2, pw=2))
+    with pytest.raises(ValueError):
+        PL.unpack(tok, 96, 176)
+
+
+def test_synthetic_vae_weights_match_the_oracle_generator():
+    """The package's seeded VAE parameters (bench.py's own arm) are the oracle's (the reference arm's): same tensors."""
+    from flux_fp8_api_b200 import autoencoder as A, pipeline as PL
+    from oracle import vae_oracle as V
+
+    p = dict(resolution=64, in_channels=3, ch=64, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, z_channels=16, scale_factor=1.0,
+             shift_factor=0.0)
+    ae = A.AutoEncoder(A.AutoEncoderParams(**p))
+    want = V.synthetic_state(ae, seed=5)
+    PL.init_synthetic_vae_weights(ae, seed=5)
+    got = ae.state_dict()
+    assert set(got) == set(want) and all(torch.equal(got[k].to(torch.bfloat16), want[k]) for k in want)
