@@ -267,7 +267,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         if (col >= P.N || !valid) continue;
         if (P.out_mode == 1) {
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + pix * P.ldo + col);
-          if (col + 32 <= P.N) {
+          if (col + 32 <= P.N && (P.ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(P.out) & 31) == 0) {
+            // full 32-byte sectors per thread and instruction (rows are ldo * 4 bytes apart: no two lanes share a sector)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint32_t o8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o8[j] = __float_as_uint(__uint_as_float(v[8 * q + j]) * P.alpha);
+              stg_v8(reinterpret_cast<float*>(dst) + 8 * q, o8[0], o8[1], o8[2], o8[3], o8[4], o8[5], o8[6], o8[7]);
+            }
+          } else if (col + 32 <= P.N) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               dst[q] = make_float4(__uint_as_float(v[4 * q]) * P.alpha, __uint_as_float(v[4 * q + 1]) * P.alpha,
@@ -467,6 +476,19 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
               static_cast<double>(acc[threadIdx.x >> 1][threadIdx.x & 1]));
 }
 
+// x * sigmoid(x) with ONE transcendental: e = 2^(-x log2 e) on the MUFU, 1 / (1 + e) by three Newton steps on the FMA pipe
+// from the integer-subtraction seed (relative error 0.12 -> 1.5e-2 -> 2e-4 -> 5e-8).  The normalisation pass is otherwise
+// MUFU-bound: two MUFU operations per element (ex2 + rcp) at 16 per clock and SM take longer than streaming the tensor.
+__device__ __forceinline__ float swish_f32(float x) {
+  const float e = exp2f_approx(fminf(-1.4426950408889634f * x, 120.f));  // clamp: 1 + 2^120 stays finite
+  const float d = 1.f + e;
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  r = r * fmaf(-d, r, 2.f);
+  return x * r;
+}
+
 // y = bf16( f( x * a_c + b_c ) ), a_c = rstd * gamma_c, b_c = beta_c - mean * a_c (the form torch's CUDA GroupNorm
 // evaluates), f = swish (x * sigmoid(x)) or identity.  grid (pixel blocks, B); a thread owns one 8-channel vector
 // position and walks the block's pixels, so the per-channel affine lives in 16 registers.
@@ -499,23 +521,32 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
   const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
   const __nv_bfloat16* xb = x + static_cast<int64_t>(b) * HW * C + vc * 8;
   __nv_bfloat16* yb = y + static_cast<int64_t>(b) * HW * C + vc * 8;
-#pragma unroll 4
-  for (int64_t p = p0 + prow; p < p1; p += rows) {
-    const uint4 v = *reinterpret_cast<const uint4*>(xb + p * C);
-    const uint32_t xw[4] = {v.x, v.y, v.z, v.w};
-    uint32_t ow[4];
+  // four independent 16-byte loads in flight per thread before any arithmetic (left to the compiler, the swish variant
+  // of this loop interleaves load - ~120 instructions - store and keeps barely one load in flight)
+  constexpr int kU = 4;
+  for (int64_t p = p0 + prow; p < p1; p += kU * rows) {
+    uint4 v[kU];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 xf = unpack_bf16x2(xw[j]);
-      float o0 = fmaf(xf.x, ca[2 * j], cb[2 * j]);
-      float o1 = fmaf(xf.y, ca[2 * j + 1], cb[2 * j + 1]);
-      if (swish) {
-        o0 = __fdividef(o0, 1.f + __expf(-o0));
-        o1 = __fdividef(o1, 1.f + __expf(-o1));
+    for (int u = 0; u < kU; ++u)
+      if (p + u * rows < p1) v[u] = __ldcs(reinterpret_cast<const uint4*>(xb + (p + u * rows) * C));
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (p + u * rows >= p1) break;
+      const uint32_t xw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16x2(xw[j]);
+        float o0 = fmaf(xf.x, ca[2 * j], cb[2 * j]);
+        float o1 = fmaf(xf.y, ca[2 * j + 1], cb[2 * j + 1]);
+        if (swish) {
+          o0 = swish_f32(o0);
+          o1 = swish_f32(o1);
+        }
+        ow[j] = pack_bf16x2(o0, o1);
       }
-      ow[j] = pack_bf16x2(o0, o1);
+      *reinterpret_cast<uint4*>(yb + (p + u * rows) * C) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
-    *reinterpret_cast<uint4*>(yb + p * C) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 
@@ -667,7 +698,7 @@ int fluxb200_conv2d_nhwc(const fluxb200_conv_args* a, fluxb200_stream_t stream_)
                                static_cast<uint64_t>(ldx) * 2 * a->W * a->H};
   // 3x3 on 128-pixel row strips: the halo form (one 130-pixel row box serves the three horizontal taps)
   static const bool halo_on = [] { const char* e = getenv("FLUXB200_CONV_HALO"); return e == nullptr || atoi(e) != 0; }();
-  const bool halo = halo_on && a->taps == 9 && P.tw == 128 && bn >= 128;
+  const bool halo = halo_on && a->taps == 9 && P.tw == 128;
   const uint32_t box[4] = {64, static_cast<uint32_t>(halo ? kHaloRows : P.tw), static_cast<uint32_t>(P.th), 1};
   int rc = make_tmap_4d(&P.tmap_a, a->x, 2, dims, strides, box);
   if (rc) return rc;
@@ -675,7 +706,8 @@ int fluxb200_conv2d_nhwc(const fluxb200_conv_args* a, fluxb200_stream_t stream_)
   const int64_t ldw = a->ldw > 0 ? a->ldw : K;
   rc = make_tmap_2d(&P.tmap_b, a->w, 2, a->N, K, ldw * 2, bn / 2, 64);
   if (rc) return rc;
-  if (halo) return bn == 256 ? launch_conv<256, true>(P, stream) : launch_conv<128, true>(P, stream);
+  if (halo)
+    return bn == 256 ? launch_conv<256, true>(P, stream) : (bn == 128 ? launch_conv<128, true>(P, stream) : launch_conv<64, true>(P, stream));
   if (bn == 256) return launch_conv<256>(P, stream);
   if (bn == 128) return launch_conv<128>(P, stream);
   return launch_conv<64>(P, stream);

@@ -198,7 +198,7 @@ def test_loud_failures():
 
 
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref not staged (python oracle/fetch_ref.py)")
-@pytest.mark.parametrize("res", [1024, 768])
+@pytest.mark.parametrize("res", [1024, 768, 1536])
 def test_full_size_decode_against_the_reference_on_this_gpu(res):
     """Flux's VAE (ch 128, ch_mult 1-2-4-4) at full resolution: ours vs the staged reference under CUDA autocast, with the
     reference's own bf16-vs-fp32 distance as the floor; both timed with CUDA events."""

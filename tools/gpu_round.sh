@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU session.  usage: tools/gpu_round.sh [tests] [bench] [configs] [shapes] [ncu]   (default: tests bench)
+# One GPU session.  usage: tools/gpu_round.sh [tests] [bench] [configs] [shapes] [vae] [ncu]   (default: tests bench)
 # Everything is written under gpurun_out/ (merged back by gpurun).
 mkdir -p gpurun_out
 what="${*:-tests bench}"
@@ -21,6 +21,9 @@ fi
 if has shapes; then
   python tools/step_shapes.py > gpurun_out/step_shapes.txt 2>&1; tail -14 gpurun_out/step_shapes.txt
   FLUXB200_GEMM_WIDE=0 python tools/step_shapes.py > gpurun_out/step_shapes_narrow.txt 2>&1; tail -14 gpurun_out/step_shapes_narrow.txt
+fi
+if has vae; then
+  for r in 1024 768 1536; do python tools/vae_profile.py $r 1 > gpurun_out/vae_profile_$r.txt 2>&1; head -1 gpurun_out/vae_profile_$r.txt; tail -8 gpurun_out/vae_profile_$r.txt; done
 fi
 if has quad; then
   FLUXB200_GEMM_MC=2 python tools/step_shapes.py > gpurun_out/step_shapes_quad.txt 2>&1; tail -14 gpurun_out/step_shapes_quad.txt
