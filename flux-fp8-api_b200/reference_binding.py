@@ -7,6 +7,7 @@ The reference has no FFI / plugin registry; its boundary for this path is the mo
     import modules.flux_model as flux_model
     from flux_fp8_api_b200 import reference_binding
     reference_binding.bind(float8_quantize, flux_model, lora_loading)      # before the model is constructed
+    # ... bind(..., autoencoder=modules.autoencoder) also redirects the VAE's decode half (before util.load_autoencoder)
 
 after which `util.load_flow_model`, `quantize_flow_transformer_and_dispatch_float8`, `FluxPipeline.generate` and
 `Flux.load_lora` run unchanged on the sm_100a kernels.  tests/test_reference_binding.py executes exactly this against
@@ -20,6 +21,7 @@ from __future__ import annotations
 from types import ModuleType
 from typing import Optional
 
+from . import autoencoder as _ae
 from . import blocks as _blocks
 from . import f8linear as _f8
 from . import lora as _lora
@@ -35,8 +37,13 @@ F8_NAMES = ("F8Linear", "recursive_swap_linears", "quantize_flow_transformer_and
 CONTAINER_NAMES = ("Flux", "MLPEmbedder", "LastLayer", "timestep_embedding")
 
 
+#: modules/autoencoder.py names replaced by autoencoder.py (the decode half; Encoder / Downsample /
+#: DiagonalGaussian stay the reference's)
+AE_NAMES = ("AttnBlock", "ResnetBlock", "Upsample", "Decoder", "AutoEncoder")
+
+
 def bind(float8_quantize: ModuleType, flux_model: ModuleType, lora_loading: Optional[ModuleType] = None,
-         replace_container: bool = True) -> dict:
+         replace_container: bool = True, autoencoder: Optional[ModuleType] = None) -> dict:
     """Point the reference's module attributes at the B200 implementations.  Returns {qualified name: original object}
     so `unbind` can restore them.
 
@@ -58,6 +65,11 @@ def bind(float8_quantize: ModuleType, flux_model: ModuleType, lora_loading: Opti
     if replace_container:
         for name in CONTAINER_NAMES:
             put(flux_model, name, getattr(_model, name))
+    if autoencoder is not None:
+        # util.load_autoencoder (util.py:280-287) builds `AutoEncoder(config.ae_params)` by this name and loads the
+        # checkpoint with strict=False; FluxPipeline.vae_decode (flux_pipeline.py:422-438) then calls `.decode`
+        for name in AE_NAMES:
+            put(autoencoder, name, getattr(_ae, name))
     if lora_loading is not None:
         # lora_loading.py:13-14 imported F8Linear / Flux by value; its fuse / unfuse entry points are replaced by the
         # on-device versions (same names, same argument order; the key-layout conversion helpers stay the reference's)

@@ -255,3 +255,36 @@ def test_full_size_decode_against_the_reference_on_this_gpu(res):
     assert d_32.max().item() <= 1.5 * floor.max().item()
     # and no further from the reference's bf16 run than that run is from fp32 (both are bf16 perturbations of the same thing)
     assert d_ref.mean().item() <= 1.5 * floor.mean().item()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not staged (python oracle/fetch_ref.py)")
+@pytest.mark.parametrize("B,height,width", [(5, 128, 192), (2, 720, 1280)])
+def test_decoder_shapes_outside_the_fast_paths_against_the_reference(B, height, width):
+    """Batch 5 (more images than the convolution epilogue keeps statistics for: the GroupNorms reduce by themselves) and a
+    720 x 1280 image (latent 90 x 160: strips of 32 pixels, rows clipped, 14 400 attention positions) -- same bars as the
+    full-size test, against the staged reference under CUDA autocast."""
+    ref = R.load()
+    if ref.ae is None:
+        pytest.skip("modules/autoencoder.py not staged (re-run oracle/fetch_ref.py)")
+    params = dict(resolution=256, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=16,
+                  scale_factor=0.3611, shift_factor=0.1159)
+    rae = ref.ae.AutoEncoder(ref.ae.AutoEncoderParams(**params))
+    sd = V.synthetic_state(rae, seed=91)
+    rae.load_state_dict(sd, strict=False)
+    rae = rae.to(DEV, BF16).eval()
+    ours = A.AutoEncoder(A.AutoEncoderParams(**params))
+    ours.load_state_dict(sd, strict=True)
+    ours = ours.to(DEV, BF16).eval()
+    z = torch.randn(B, 16, height // 8, width // 8, device=DEV, generator=torch.Generator(device=DEV).manual_seed(92)) * 1.2
+    with torch.inference_mode():
+        with torch.autocast(device_type="cuda", dtype=BF16, cache_enabled=False):
+            y_ref = rae.decode(z)
+        y = ours.decode(z)
+        y32 = rae.float().decode(z)
+    assert y.shape == (B, 3, height, width)
+    floor = (y_ref.float() - y32).abs()
+    d32 = (y.float() - y32).abs()
+    print(f"{B} x {height}x{width}: reference bf16-vs-fp32 mean {floor.mean().item():.4g} max {floor.max().item():.4g}; "
+          f"ours-vs-fp32 mean {d32.mean().item():.4g} max {d32.max().item():.4g}")
+    assert torch.isfinite(y).all()
+    assert d32.mean().item() <= 1.25 * floor.mean().item() and d32.max().item() <= 1.5 * floor.max().item()

@@ -69,6 +69,32 @@ def test_autoencoder_surface_matches_the_reference():
 
 
 @needs_ref
+def test_bind_redirects_the_autoencoder_and_a_reference_checkpoint_loads():
+    """bind(..., autoencoder=modules.autoencoder): the name util.load_autoencoder constructs (util.py:281) is ours, a state
+    dict minted by the reference class loads with strict=False exactly as util.py:285 loads it, unbind restores."""
+    from flux_fp8_api_b200 import autoencoder as A, reference_binding as RB
+
+    ref = R.load()
+    params = dict(resolution=64, in_channels=3, ch=64, out_ch=3, ch_mult=[1, 2], num_res_blocks=1, z_channels=16,
+                  scale_factor=0.3611, shift_factor=0.1159)
+    orig = ref.ae.AutoEncoder
+    theirs = orig(ref.ae.AutoEncoderParams(**params))
+    saved = RB.bind(ref.f8, ref.fm, ref.lora, replace_container=False, autoencoder=ref.ae)
+    try:
+        assert ref.ae.AutoEncoder is A.AutoEncoder and ref.ae.Decoder is A.Decoder
+        built = ref.ae.AutoEncoder(ref.ae.AutoEncoderParams(**params))  # the reference's own params class
+        missing, unexpected = built.load_state_dict(theirs.state_dict(), strict=False, assign=True)
+        assert not missing and unexpected and all(k.startswith("encoder.") for k in unexpected)
+        assert torch.equal(built.decoder.conv_in.weight, theirs.decoder.conv_in.weight)
+        assert built.scale_factor == theirs.scale_factor and built.shift_factor == theirs.shift_factor
+        with pytest.raises(Exception):
+            built.decode(torch.zeros(1, 16, 8, 8))  # CPU tensors: no fallback
+    finally:
+        RB.unbind(saved)
+    assert ref.ae.AutoEncoder is orig
+
+
+@needs_ref
 def test_signatures_match_the_reference():
     import inspect
 
