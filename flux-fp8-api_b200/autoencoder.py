@@ -25,6 +25,7 @@ from pydantic import BaseModel
 from torch import Tensor, nn
 
 from . import ops
+from .blocks import tensor_version
 
 BF16 = torch.bfloat16
 
@@ -62,12 +63,25 @@ class _Packed:
 
     def get(self, conv: nn.Conv2d):
         w, b = conv.weight, conv.bias
-        key = (w.data_ptr(), w._version, w.device, w.dtype, None if b is None else (b.data_ptr(), b._version))
+        # (inference tensors carry no version counter: a state loaded under inference_mode is keyed on storage alone and has
+        # to be re-assigned, not edited in place, to be picked up -- `invalidate()` forces a re-pack)
+        key = (w.data_ptr(), tensor_version(w), w.device, w.dtype, None if b is None else (b.data_ptr(), tensor_version(b)))
         if key != self.key:
             self.w = ops.pack_conv_weight(w)
             self.b = None if b is None else b.detach().to(BF16).contiguous()
             self.key = key
         return self.w, self.b
+
+    def invalidate(self) -> None:
+        self.key = None
+
+
+def invalidate_packed(module: nn.Module) -> None:
+    """Drop every cached kernel-layout weight below `module` (after editing Conv2d parameters in place under inference_mode)."""
+    for m in module.modules():
+        for v in vars(m).values():
+            if isinstance(v, _Packed):
+                v.invalidate()
 
 
 def _conv(conv: nn.Conv2d, cache: _Packed, x: Tensor, residual: Optional[Tensor] = None, out_mode: int = 0,

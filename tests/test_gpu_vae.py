@@ -288,3 +288,27 @@ def test_decoder_shapes_outside_the_fast_paths_against_the_reference(B, height, 
           f"ours-vs-fp32 mean {d32.mean().item():.4g} max {d32.max().item():.4g}")
     assert torch.isfinite(y).all()
     assert d32.mean().item() <= 1.25 * floor.mean().item() and d32.max().item() <= 1.5 * floor.max().item()
+
+
+def test_packed_weights_follow_parameter_updates(golden_dir):
+    """The kernel-layout weight cache is keyed on parameter storage / version: load_state_dict and in-place edits are seen,
+    also for a model built and loaded under inference_mode (no version counters there: invalidate_packed)."""
+    g, m, sd = _tiny(golden_dir)
+    z = g["z"].to(DEV)
+    with torch.inference_mode():
+        y0 = m.decode(z).clone()
+    with torch.no_grad():
+        m.decoder.conv_out.weight.mul_(2.0)  # version bump
+        m.decoder.conv_out.bias.zero_()
+    with torch.inference_mode():
+        y1 = m.decode(z).clone()
+    assert not torch.equal(y0, y1)
+    m.load_state_dict({k: v.to(DEV) for k, v in sd.items()})  # copies in place: version bump again
+    with torch.inference_mode():
+        assert torch.equal(m.decode(z), y0)
+        m2 = A.AutoEncoder(A.AutoEncoderParams(**g["params"])).to(DEV, BF16)
+        m2.load_state_dict({k: v.to(DEV) for k, v in sd.items()})
+        assert torch.equal(m2.decode(z), y0)
+        m2.decoder.conv_out.weight.mul_(2.0)  # inference tensor: no version counter
+        A.invalidate_packed(m2)
+        assert not torch.equal(m2.decode(z), y0)
