@@ -432,18 +432,18 @@ static int launch_conv(const ConvParams& P, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------------------------
 // GroupNorm.  x bf16 NHWC [B, HW, C]; 32 groups of C / 32 adjacent channels; statistics over (HW, C / 32) per (b, group).
 // ---------------------------------------------------------------------------------------------------------------------
-// stats[b][g] = {sum, sum of squares} (fp64, zeroed by the caller).  Thread = one 8-channel vector of a pixel.
+// stats[b][g] = {sum, sum of squares} (fp64, zeroed by the caller).  Thread = one 8-channel vector of a pixel.  The block's
+// partial sums are combined in a FIXED order (no shared-memory float atomics: their arrival order would make the result,
+// and with it the whole decode, differ from run to run in the last bit).
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ stats,
                                                        int64_t HW, int C, int pix_per_block) {
-  __shared__ float acc[32][2];
+  __shared__ float part[256][8];  // [thread][bf16 pair j][sum, squares]
   const int b = blockIdx.y;
   const int vec_per_pix = C >> 3;
-  const int cg = C >> 5;  // channels per group: 4, 8 or 16 ...
-  if (threadIdx.x < 64) acc[threadIdx.x >> 1][threadIdx.x & 1] = 0.f;
-  __syncthreads();
+  const int cg = C >> 5;  // channels per group: 2, 4, 8, 16 ...
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
   const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
-  const int vc = threadIdx.x % vec_per_pix;       // which 8-channel vector (requires 256 % vec_per_pix == 0)
+  const int vc = threadIdx.x % vec_per_pix;       // which 8-channel vector (256 % vec_per_pix == 0)
   const int prow = threadIdx.x / vec_per_pix;
   const int rows = 256 / vec_per_pix;
   float sp[4] = {0.f, 0.f, 0.f, 0.f}, qp[4] = {0.f, 0.f, 0.f, 0.f};  // per bf16 pair: cg may be as small as 2
@@ -458,22 +458,19 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* __re
       qp[j] += f.x * f.x + f.y * f.y;
     }
   }
-  if (cg >= 8) {
-    const int g = (vc * 8) / cg;
-    atomicAdd(&acc[g][0], (sp[0] + sp[1]) + (sp[2] + sp[3]));
-    atomicAdd(&acc[g][1], (qp[0] + qp[1]) + (qp[2] + qp[3]));
-  } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (vc * 8 + 2 * j) / cg;
-      atomicAdd(&acc[g][0], sp[j]);
-      atomicAdd(&acc[g][1], qp[j]);
-    }
-  }
+  for (int j = 0; j < 4; ++j) part[threadIdx.x][2 * j] = sp[j], part[threadIdx.x][2 * j + 1] = qp[j];
   __syncthreads();
-  if (threadIdx.x < 64)
-    atomicAdd(&stats[(static_cast<int64_t>(b) * 32 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1)],
-              static_cast<double>(acc[threadIdx.x >> 1][threadIdx.x & 1]));
+  if (threadIdx.x < 64) {
+    // group g = channels [g cg, (g+1) cg) = pairs [g cg/2, (g+1) cg/2); pair p lives in vector p / 4, slot p % 4, of every
+    // pixel row r of the block: rows * cg / 2 = 32 terms per group and statistic, summed in index order
+    const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
+    const int pairs = cg >> 1;
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r)
+      for (int pp = g * pairs; pp < (g + 1) * pairs; ++pp) acc += part[r * vec_per_pix + (pp >> 2)][2 * (pp & 3) + st];
+    atomicAdd(&stats[(static_cast<int64_t>(b) * 32 + g) * 2 + st], static_cast<double>(acc));
+  }
 }
 
 // x * sigmoid(x) with ONE transcendental: e = 2^(-x log2 e) on the MUFU, 1 / (1 + e) by three Newton steps on the FMA pipe
