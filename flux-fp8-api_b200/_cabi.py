@@ -49,6 +49,9 @@ EXPORTS = (
     "fluxb200_upsample2x_nhwc",
     "fluxb200_softmax_rows",
     "fluxb200_vae_latent_prep",
+    "fluxb200_rows_norm",
+    "fluxb200_gated_act",
+    "fluxb200_attention_d64",
     "fluxb200_debug_counters",
     "fluxb200_gemm_probe_mode",
     "fluxb200_gemm_force_tiling",
@@ -246,6 +249,11 @@ def load() -> C.CDLL:
     lib.fluxb200_softmax_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
     lib.fluxb200_vae_latent_prep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float,
                                              C.c_float, C.c_void_p]
+    lib.fluxb200_rows_norm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                       C.c_float, C.c_void_p]
+    lib.fluxb200_gated_act.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.fluxb200_attention_d64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
     lib.fluxb200_debug_counters.argtypes = [C.POINTER(C.c_ulonglong)]
     lib.fluxb200_gemm_probe_mode.argtypes = [C.c_int]
     lib.fluxb200_gemm_force_tiling.argtypes = [C.c_int, C.c_int]

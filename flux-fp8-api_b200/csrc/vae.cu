@@ -668,7 +668,10 @@ int fluxb200_conv2d_nhwc(const fluxb200_conv_args* a, fluxb200_stream_t stream_)
   P.tiles_x = (a->W + P.tw - 1) / P.tw;
   P.tiles_y = (a->H + P.th - 1) / P.th;
   P.m_tiles = a->B * P.tiles_x * P.tiles_y;
-  const int bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  int bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  // a launch that cannot even fill the machine once with 256-wide tiles (dense layers over a few hundred rows: the text
+  // encoders' o / wo projections) takes 128-wide tiles: twice the CTAs, same bytes per flop from L2
+  if (bn == 256 && static_cast<int64_t>((P.m_tiles + 1) / 2) * ((a->N + 255) / 256) < sm_count() / 2) bn = 128;
   P.n_tiles = (a->N + bn - 1) / bn;
   P.num_tiles = ((P.m_tiles + 1) / 2) * P.n_tiles;
   P.kchunks = a->Cin / 64;

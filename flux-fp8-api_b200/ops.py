@@ -679,3 +679,70 @@ def vae_latent_prep(z: Tensor, scale_factor: float, shift_factor: float, cpad: i
            lambda: cabi.check(cabi.load().fluxb200_vae_latent_prep(z.data_ptr(), out.data_ptr(), B, Cn, H * W, cpad, scale_factor,
                                                                    shift_factor, cabi.stream_ptr()), "fluxb200_vae_latent_prep"))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Text-encoder ops (second half): T5 / CLIP pieces that are not dense layers
+# ---------------------------------------------------------------------------------------------------------------------
+def dense(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+          out: Optional[Tensor] = None) -> Tensor:
+    """bf16 F.linear on the tcgen05 implicit-GEMM kernel in its dense form: out[M, N] = x[M, K] weight[N, K]^T (+ bias)
+    (+ residual), fp32 accumulate, the roundings of conv2d_nhwc's NHWC mode.  K % 64 == 0, N % 8 == 0."""
+    if x.dim() != 2 or x.stride(1) != 1 or weight.dim() != 2 or weight.stride(1) != 1 or weight.shape[1] != x.shape[1]:
+        raise ValueError(f"dense: x {tuple(x.shape)} / weight {tuple(weight.shape)} must be row-major [M, K] and [N, K]")
+    M, K = x.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=BF16, device=x.device)
+    xv = x.as_strided((1, 1, M, K), (M * x.stride(0), M * x.stride(0), x.stride(0), 1))
+    conv2d_nhwc(xv, weight, bias, 1, residual=None if residual is None else residual.view(1, 1, M, N), out=out.view(1, 1, M, N))
+    return out
+
+
+def rows_norm(x: Tensor, weight: Tensor, bias: Optional[Tensor], eps: float, out: Optional[Tensor] = None) -> Tensor:
+    """bias None: T5LayerNorm (RMS); else nn.LayerNorm with affine.  x bf16 [rows, D] (row stride allowed)."""
+    cabi.require_cuda(x, weight)
+    _want(x, BF16, "rows_norm: x"), _want(weight, BF16, "rows_norm: weight"), _want(bias, BF16, "rows_norm: bias")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("rows_norm: x must be [rows, D] with contiguous rows")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), dtype=BF16, device=x.device)
+    _timed("rows_norm", 0.0,
+           lambda: cabi.check(cabi.load().fluxb200_rows_norm(x.data_ptr(), x.stride(0), weight.data_ptr(), cabi.ptr(bias), out.data_ptr(),
+                                                             out.stride(0), rows, D, eps, cabi.stream_ptr()), "fluxb200_rows_norm"))
+    return out
+
+
+def gated_act(x: Tensor, F: int, mode: int, out: Optional[Tensor] = None) -> Tensor:
+    """mode 0: bf16(gelu_new(x[:, :F])) * x[:, F:2F] (T5);  mode 1: quick_gelu(x[:, :F]) (CLIP)."""
+    cabi.require_cuda(x)
+    _want(x, BF16, "gated_act: x")
+    if x.dim() != 2 or x.stride(1) != 1 or x.shape[1] < (2 * F if mode == 0 else F):
+        raise ValueError("gated_act: x must be [rows, >= F (2 F for the gated form)] with contiguous rows")
+    rows = x.shape[0]
+    if out is None:
+        out = torch.empty((rows, F), dtype=BF16, device=x.device)
+    _timed("gated_act", 0.0,
+           lambda: cabi.check(cabi.load().fluxb200_gated_act(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, F, mode,
+                                                             cabi.stream_ptr()), "fluxb200_gated_act"))
+    return out
+
+
+def attention_d64(qkv: Tensor, B: int, S: int, H: int, bias: Optional[Tensor], scale: float, causal: bool,
+                  out: Optional[Tensor] = None) -> Tensor:
+    """qkv bf16 [B*S, 3*H*64] (q | k | v, head h at columns [64 h, 64 h + 64) of each third) -> bf16 [B*S, H*64]."""
+    cabi.require_cuda(qkv)
+    _want(qkv, BF16, "attention_d64: qkv"), _want(bias, BF16, "attention_d64: bias")
+    if qkv.dim() != 2 or qkv.shape != (B * S, 3 * H * 64) or qkv.stride(1) != 1:
+        raise ValueError(f"attention_d64: qkv must be [{B * S}, {3 * H * 64}], got {tuple(qkv.shape)}")
+    if bias is not None and (tuple(bias.shape) != (H, S, S) or not bias.is_contiguous()):
+        raise ValueError("attention_d64: bias must be a contiguous [H, S, S]")
+    if out is None:
+        out = torch.empty((B * S, H * 64), dtype=BF16, device=qkv.device)
+    es = qkv.element_size()
+    q, k, v = qkv.data_ptr(), qkv.data_ptr() + H * 64 * es, qkv.data_ptr() + 2 * H * 64 * es
+    _timed("attention_d64", 4.0 * B * H * S * S * 64,
+           lambda: cabi.check(cabi.load().fluxb200_attention_d64(q, k, v, qkv.stride(0), cabi.ptr(bias), out.data_ptr(), out.stride(0),
+                                                                 B, H, S, scale, int(causal), cabi.stream_ptr()), "fluxb200_attention_d64"))
+    return out

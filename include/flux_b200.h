@@ -236,6 +236,32 @@ int fluxb200_vae_latent_prep(const float* z_nchw, void* y_nhwc_bf16, int B, int 
                              float scale_factor, float shift_factor, fluxb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Text encoders (second half): modules/conditioner.py:HFEmbedder wraps Hugging Face `T5EncoderModel`
+ * (t5-v1_1-xxl) and `CLIPTextModel` (clip-vit-large-patch14) (:80-92) and calls them with attention_mask=None
+ * (:101-117).  The arithmetic therefore lives in the third-party `transformers` package (5.5.0 in this image; the
+ * reference does not pin it): models/t5/modeling_t5.py (T5LayerNorm, T5Attention, T5DenseGatedActDense, T5Block) and
+ * models/clip/modeling_clip.py (CLIPTextTransformer).  Dense layers run on fluxb200_conv2d_nhwc in its dense form
+ * (H = 1, taps = 1; bias and residual in the epilogue); the rest:
+ *
+ * fluxb200_rows_norm:  bias == NULL: T5LayerNorm  y = bf16( w * bf16( x * rsqrt(mean(x^2) + eps) ) )
+ *                      else nn.LayerNorm(affine)  y = bf16( (x - mean) * rsqrt(var + eps) * w + b ), fp32 statistics.
+ * fluxb200_gated_act:  mode 0: out = bf16( bf16(gelu_new(in[:, :F])) * in[:, F:2F] )   (T5DenseGatedActDense, wi_0 | wi_1
+ *                      concatenated along N);  mode 1: out = bf16( x * sigmoid(1.702 x) )   (CLIP quick_gelu).
+ * fluxb200_attention_d64:  multi-head attention, head dim 64, q / k / v rows `ld` elements apart (head h at columns
+ *                      [64 h, 64 h + 64): three pointers into one fused QKV buffer work), optional additive bias bf16
+ *                      [H, S, S] shared by the batch (T5's relative position bias), softmax scale (1 for T5, 1/8 for
+ *                      CLIP), optional causal mask (CLIP).  scores are rounded to bf16 after the product, after the scale
+ *                      and after the bias as the eager modules do; softmax in fp32; out bf16 [B*S, ldo].
+ * ------------------------------------------------------------------------------------------- */
+int fluxb200_rows_norm(const void* x_bf16, int64_t ldx, const void* weight_bf16, const void* bias_bf16, void* y_bf16,
+                       int64_t ldy, int rows, int D, float eps, fluxb200_stream_t stream);
+int fluxb200_gated_act(const void* in_bf16, int64_t ld_in, void* out_bf16, int64_t ld_out, int rows, int F, int mode,
+                       fluxb200_stream_t stream);
+int fluxb200_attention_d64(const void* q_bf16, const void* k_bf16, const void* v_bf16, int64_t ld, const void* bias_bf16,
+                           void* out_bf16, int64_t ldo, int B, int H, int S, float scale, int causal,
+                           fluxb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Modulation prologue: y = quantize( bf16(silu(x)), scale )   (modules/flux_model.py:249,252 +
  * float8_quantize.py:274-276).  y_bf16 (optional) receives bf16(silu(x)) for unquantised lins.
  * ------------------------------------------------------------------------------------------- */

@@ -417,6 +417,43 @@ def golden_vae():
                 "h_conv_in": h0, "h_mid_block_1": h1, "h_mid_attn_1": h2}, os.path.join(OUT, "vae_tiny.pt"))
 
 
+def golden_text():
+    """tests/golden/text_tiny.pt: outputs of the installed Hugging Face T5EncoderModel / CLIPTextModel (the third-party code
+    the reference's HFEmbedder calls, conditioner.py:80-114) on tiny configurations with seeded weights, and the oracle
+    pinned against them."""
+    import transformers
+    from transformers import CLIPTextConfig, CLIPTextModel, T5Config, T5EncoderModel
+
+    from oracle import text_oracle as T
+
+    print("text_tiny.pt   (transformers", transformers.__version__ + ")")
+    t5 = T5EncoderModel(T5Config(**T.T5_TINY)).eval()
+    sd_t5 = T.seeded_state(t5, 3)
+    t5.load_state_dict(sd_t5, strict=False)
+    g = torch.Generator().manual_seed(41)
+    ids_t5 = torch.randint(0, T.T5_TINY["vocab_size"], (2, 40), generator=g)
+    clip = CLIPTextModel(CLIPTextConfig(**T.CLIP_TINY)).eval()
+    sd_clip = T.seeded_state(clip, 4)
+    clip.load_state_dict(sd_clip, strict=False)
+    ids_clip = torch.randint(3, T.CLIP_TINY["vocab_size"] - 1, (2, 77), generator=g)
+    ids_clip[:, 0] = 0
+    ids_clip[0, 19], ids_clip[0, 20:] = 511, 1   # end-of-text = the largest id, then padding
+    ids_clip[1, 12], ids_clip[1, 13:] = 511, 1
+    with torch.inference_mode():
+        y_t5 = t5(input_ids=ids_t5, attention_mask=None, output_hidden_states=False)["last_hidden_state"]
+        r = clip(input_ids=ids_clip, attention_mask=None, output_hidden_states=False)
+        o_t5 = T.t5_encoder(sd_t5, T.T5_TINY, ids_t5)
+        o_h, o_p = T.clip_text(sd_clip, T.CLIP_TINY, ids_clip)
+    report("t5 last_hidden_state", y_t5, o_t5, 1e-5)
+    report("clip last_hidden_state", r["last_hidden_state"], o_h, 1e-5)
+    report("clip pooler_output", r["pooler_output"], o_p, 1e-5)
+    torch.save({"transformers": transformers.__version__, "t5_seed": 3, "clip_seed": 4, "ids_t5": ids_t5, "ids_clip": ids_clip,
+                "y_t5": y_t5, "y_clip_hidden": r["last_hidden_state"], "y_clip_pooled": r["pooler_output"],
+                "t5_shapes": {k: (tuple(v.shape), str(v.dtype)) for k, v in sd_t5.items()},
+                "clip_shapes": {k: (tuple(v.shape), str(v.dtype)) for k, v in sd_clip.items()}},
+               os.path.join(OUT, "text_tiny.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -428,4 +465,5 @@ if __name__ == "__main__":
     golden_flux_variants()
     golden_lora()
     golden_vae()
+    golden_text()
     print("golden fixtures written to", OUT)

@@ -198,3 +198,21 @@ def test_vae_oracle_reproduces_the_reference_decode(golden_dir):
     ya = V.decode(g["z"], sd, p["ch_mult"], p["num_res_blocks"], p["scale_factor"], p["shift_factor"], policy="autocast")
     assert torch.equal(ya, g["y_oracle_autocast"])
     assert (ya.float() - g["y_ref_fp32"]).abs().mean().item() <= 0.01 * g["y_ref_fp32"].abs().max().item()
+
+
+def test_text_encoder_oracle_reproduces_the_hugging_face_modules(golden_dir):
+    """oracle/text_oracle.py against the outputs of the installed transformers T5EncoderModel / CLIPTextModel committed in
+    tests/golden/text_tiny.pt (the third-party arithmetic behind the reference's HFEmbedder, conditioner.py:80-114)."""
+    from oracle import text_oracle as T
+
+    g = torch.load(os.path.join(golden_dir, "text_tiny.pt"))
+    sd = T.seeded_state_from_shapes(g["t5_shapes"], g["t5_seed"])
+    y = T.t5_encoder(sd, T.T5_TINY, g["ids_t5"])
+    assert (y - g["y_t5"]).abs().max().item() <= 1e-5 * g["y_t5"].abs().max().item()
+    sd = T.seeded_state_from_shapes(g["clip_shapes"], g["clip_seed"])
+    h, p = T.clip_text(sd, T.CLIP_TINY, g["ids_clip"])
+    assert (h - g["y_clip_hidden"]).abs().max().item() <= 1e-5 * g["y_clip_hidden"].abs().max().item()
+    assert (p - g["y_clip_pooled"]).abs().max().item() <= 1e-5 * g["y_clip_pooled"].abs().max().item()
+    # the relative-position buckets of T5 (32 buckets, distances up to 128) at the boundaries
+    rel = torch.tensor([[-200, -128, -17, -16, -8, -7, -1, 0, 1, 7, 8, 16, 17, 127, 128, 200]])
+    assert T.t5_relative_position_bucket(rel).tolist() == [[15, 15, 10, 10, 8, 7, 1, 0, 17, 23, 24, 26, 26, 31, 31, 31]]

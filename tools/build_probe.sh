@@ -8,4 +8,4 @@ mkdir -p ../../tools/ab
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I../../include --expt-relaxed-constexpr \
   -cudart static -DFLUXB200_ATTN_PROBE -DFLUXB200_ATTN_EXPERIMENTS $EXTRA -c attention.cu -o /tmp/attention_probe.o
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o ../../tools/ab/libflux_probe.so \
-  host_util.o elementwise.o f8_gemm.o /tmp/attention_probe.o lora.o vae.o
+  host_util.o elementwise.o f8_gemm.o /tmp/attention_probe.o lora.o vae.o text_encoder.o
