@@ -23,6 +23,7 @@ One JSON line on stdout (rank 0):
                 pass, against the FP8 tensor-pipe ceiling MEASURED on this box in the same run (fluxb200_fp8_mma_probe)
   vae_decode    one AutoEncoder.decode of the config's image size through our kernels, with the reference's
                 cuDNN decode on the same GPU beside it when gpu_reference ran
+  text_encoders the T5-XXL / CLIP-L text encoders through conditioner.accelerate and the Hugging Face modules themselves
   gpu_reference the UNMODIFIED reference modules (oracle/_ref) timed on the same GPU: eager, and torch.compile'd blocks
   cpu_baseline  the reference's bf16 blocks on the host cores (bounded sample)
 
@@ -387,6 +388,48 @@ def measure_vae_ours(cfg, dev):
             "ms": ms, "tflops": fl / (ms * 1e-3) / 1e12, "flop": fl, "c_abi_calls": calls, "dtype": "bf16, fp32 accumulate"}
 
 
+def measure_text_encoders(dev):
+    """SURVEY.md 8f N4 beside the headline metric: the two text encoders of a request (t5-v1_1-xxl encoder, 512 tokens;
+    clip-vit-large-patch14 text tower, 77 tokens; seeded weights) through conditioner.accelerate, and the Hugging Face
+    modules themselves (what the reference's HFEmbedder runs, modules/conditioner.py:109-113) on the same GPU."""
+    import math
+
+    from transformers import CLIPTextConfig, CLIPTextModel, T5Config, T5EncoderModel
+
+    from flux_fp8_api_b200 import conditioner as CD
+
+    def init(m, gain):
+        g = torch.Generator(device=dev).manual_seed(17)
+        with torch.no_grad():
+            for k, p in sorted(m.state_dict().items()):
+                if p.dtype.is_floating_point:
+                    if "norm" in k and k.endswith("weight"):
+                        p.copy_(1.0 + 0.1 * torch.randn(p.shape, device=dev, generator=g))
+                    else:
+                        p.copy_(torch.randn(p.shape, device=dev, generator=g) * (gain / math.sqrt(p.shape[-1]) if p.dim() > 1 else 0.05))
+
+    out = {}
+    with torch.device(dev):
+        models = (("t5-v1_1-xxl encoder, 512 tokens", lambda: T5EncoderModel(T5Config(
+                       vocab_size=32128, d_model=4096, d_kv=64, d_ff=10240, num_layers=24, num_heads=64, dropout_rate=0.0,
+                       feed_forward_proj="gated-gelu", is_encoder_decoder=False, use_cache=False, tie_word_embeddings=False)), 512, 0.5),
+                  ("clip-vit-large-patch14 text, 77 tokens", lambda: CLIPTextModel(CLIPTextConfig(
+                       vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                       max_position_embeddings=77, hidden_act="quick_gelu", eos_token_id=2, bos_token_id=0, pad_token_id=1)), 77, 1.0))
+        for name, build, S, gain in models:
+            m = build().to(torch.bfloat16).eval()
+            init(m, gain)
+            ids = torch.randint(3, 30000, (1, S), device=dev)
+            ours = CD.accelerate(m)
+            with torch.inference_mode():
+                ms = time_cuda(lambda: ours(input_ids=ids, attention_mask=None, output_hidden_states=False), 5)
+                ms_hf = time_cuda(lambda: m(input_ids=ids, attention_mask=None, output_hidden_states=False), 5)
+            out[name] = {"ms": ms, "hugging_face_ms": ms_hf, "speedup_ours_over_hugging_face": ms_hf / ms}
+            del m, ours
+            torch.cuda.empty_cache()
+    return out
+
+
 def measure_vae_reference(ref, cfg, dev):
     """The unmodified reference AutoEncoder on the same GPU, as flux_pipeline.py:431-434 runs it."""
     from oracle import vae_oracle as V
@@ -594,7 +637,8 @@ def main():
     ap.add_argument("--gpu-reference", default="both", choices=["none", "eager", "compiled", "both"],
                     help="time the unmodified reference modules on the same GPU after our arm (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode measurement (SURVEY 8f N4) beside the metric")
+    ap.add_argument("--no-vae", action="store_true",
+                    help="skip the VAE decode and text-encoder measurements (SURVEY 8f N4) beside the metric")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -781,8 +825,13 @@ def main():
     gpu_ref = None
     h2d_bytes, d2h_bytes = sess.h2d_bytes_per_step, sess.d2h_bytes_per_step
     vae = None
+    text = None
     if rank == 0 and world == 1 and not args.no_vae:
         vae = measure_vae_ours(cfg, dev)
+        try:
+            text = measure_text_encoders(dev)
+        except Exception as ex:  # noqa: BLE001  (transformers missing / changed: the headline line must still print)
+            text = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
     if rank == 0 and world == 1 and args.gpu_reference != "none":
         del sess
         torch.cuda.empty_cache()
@@ -823,6 +872,7 @@ def main():
             "roofline": roof,
             "gpu_reference": gpu_ref,
             "vae_decode": vae,
+            "text_encoders": text,
             "cpu_baseline": cpu,
             "broadcast": {"bytes": bcast_bytes, "ms": bcast_ms},
         }

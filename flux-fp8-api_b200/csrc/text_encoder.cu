@@ -19,11 +19,12 @@ namespace fb {
 
 // y[r, :] = bf16( w * bf16( x * rsqrt(mean(x^2) + eps) ) )                      (bias == nullptr: T5LayerNorm)
 // y[r, :] = bf16( (x - mean) * rsqrt(var + eps) * w + b )                        (nn.LayerNorm, biased variance)
-__global__ void __launch_bounds__(256) rows_norm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+constexpr int kNormRowsPerBlock = 2;  // few hundred rows in all: small blocks so that every SM gets some
+__global__ void __launch_bounds__(kNormRowsPerBlock * 32) rows_norm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
                                                         const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
                                                         __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int D, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
+  const int r = blockIdx.x * kNormRowsPerBlock + warp;
   if (r >= rows) return;
   const __nv_bfloat16* xr = x + static_cast<int64_t>(r) * ldx;
   __nv_bfloat16* yr = y + static_cast<int64_t>(r) * ldy;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(128) attention_d64_kernel(const __nv_bfloat16*
                                                             int64_t ldo, int H, int S, float scale, int causal) {
   __shared__ __align__(16) __nv_bfloat16 Qs[64][kA64Pitch];
   __shared__ __align__(16) __nv_bfloat16 Ks[64][kA64Pitch];   // [key][d]
-  __shared__ __align__(16) __nv_bfloat16 Vt[64][kA64Pitch];   // [d][key]
+  __shared__ __align__(16) __nv_bfloat16 Vs[64][kA64Pitch];   // [key][d]: the P V product reads it through ldmatrix.trans
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
@@ -162,9 +163,7 @@ __global__ void __launch_bounds__(128) attention_d64_kernel(const __nv_bfloat16*
         vv = *reinterpret_cast<const uint4*>(v + (row_base + k0 + r) * ld + h * 64 + c);
       }
       *reinterpret_cast<uint4*>(&Ks[r][c]) = kv;
-      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) Vt[c + e][r] = ve[e];
+      *reinterpret_cast<uint4*>(&Vs[r][c]) = vv;
     }
     __syncthreads();
     float s[8][4];
@@ -222,14 +221,20 @@ __global__ void __launch_bounds__(128) attention_d64_kernel(const __nv_bfloat16*
     for (int j = 0; j < 8; ++j) {
       o[j][0] *= a0, o[j][1] *= a0, o[j][2] *= a1, o[j][3] *= a1;
     }
-    // O += P V: k-step i covers keys [16 i, 16 i + 16) = score n-tiles 2 i and 2 i + 1; n-tile j of the output = d [8 j, 8 j + 8)
+    // O += P V: k-step i covers keys [16 i, 16 i + 16) = score n-tiles 2 i and 2 i + 1; n-tile j of the output = d [8 j, 8 j + 8).
+    // The B fragment of mma.m16n8k16 wants {V[k][n], V[k+1][n]} pairs (k = key, n = d): ldmatrix.trans hands them out
+    // straight from the row-major [key][d] tile, four 8x8 matrices (two k halves x two n-tiles) per instruction.
+    const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8, lm_col = (lane >> 4) * 8;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[j * 8 + g][i * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[j * 8 + g][i * 16 + 2 * t + 8]);
-        mma_bf16_16816(o[j], pa[2 * i][0], pa[2 * i][1], pa[2 * i + 1][0], pa[2 * i + 1][1], b0, b1);
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t b00, b01, b10, b11;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b00), "=r"(b01), "=r"(b10), "=r"(b11)
+                     : "r"(smem_u32(&Vs[i * 16 + lm_row][j * 8 + lm_col])));
+        mma_bf16_16816(o[j], pa[2 * i][0], pa[2 * i][1], pa[2 * i + 1][0], pa[2 * i + 1][1], b00, b01);
+        mma_bf16_16816(o[j + 1], pa[2 * i][0], pa[2 * i][1], pa[2 * i + 1][0], pa[2 * i + 1][1], b10, b11);
       }
     }
   }
@@ -259,7 +264,7 @@ int fluxb200_rows_norm(const void* x_bf16, int64_t ldx, const void* weight_bf16,
   FB_REQUIRE(rows > 0 && D > 0 && D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "fluxb200_rows_norm: D, ldx, ldy must be multiples of 8");
   FB_REQUIRE(((reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(weight_bf16) |
                reinterpret_cast<uintptr_t>(bias_bf16)) & 15) == 0, "fluxb200_rows_norm: operands must be 16-byte aligned");
-  rows_norm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ldx,
+  rows_norm_kernel<<<(rows + kNormRowsPerBlock - 1) / kNormRowsPerBlock, kNormRowsPerBlock * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ldx,
                                                        reinterpret_cast<const __nv_bfloat16*>(weight_bf16),
                                                        reinterpret_cast<const __nv_bfloat16*>(bias_bf16),
                                                        reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, rows, D, eps);
