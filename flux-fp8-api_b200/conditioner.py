@@ -25,6 +25,7 @@ the modules' own bf16-vs-fp32 distance as the floor.
 """
 from __future__ import annotations
 
+import gc
 import math
 from typing import Optional
 
@@ -62,6 +63,38 @@ class _Fused:
         return self.t
 
 
+class _GraphedForward:
+    """Replays a module's `_forward(input_ids)` as one CUDA graph per (batch, tokens) shape.  The text encoders are ~200
+    (T5) / ~100 (CLIP) small launches of a few-hundred-row problem: issued one by one from Python they are bound by the
+    host, not the GPU.  The graph is re-captured when any parameter of the wrapped module changes storage or version.
+    Holds no reference to its owner (a reference cycle would leave the destruction of a captured graph to the cyclic
+    garbage collector, i.e. possibly to the middle of somebody else's stream capture, which it invalidates)."""
+
+    def __init__(self):
+        self.graphs = {}
+
+    def __call__(self, owner: nn.Module, input_ids: Tensor):
+        if not owner.use_graph:
+            return owner._forward(input_ids)
+        key = (tuple(input_ids.shape), input_ids.device)
+        wkey = tuple((p.data_ptr(), tensor_version(p)) for p in owner.hf_module.parameters())
+        hit = self.graphs.get(key)
+        if hit is None or hit[3] != wkey:
+            self.graphs.pop(key, None)
+            static_ids = input_ids.clone()
+            owner._forward(static_ids)  # warm-up: fused weights, position bias, allocator pools
+            gc.collect()                # nothing may be torn down while the stream is capturing
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = owner._forward(static_ids)
+            self.graphs[key] = hit = (g, static_ids, out, wkey)
+        g, static_ids, out, _ = hit
+        static_ids.copy_(input_ids)
+        g.replay()
+        return _Output({k: v.clone() for k, v in out.items()})
+
+
 def t5_relative_position_bucket(relative_position: Tensor, num_buckets: int = 32, max_distance: int = 128) -> Tensor:
     """T5Attention._relative_position_bucket, bidirectional (encoder) form."""
     num_buckets //= 2
@@ -96,6 +129,8 @@ class T5EncoderB200(nn.Module):
         self._qkv = [_Fused() for _ in enc.block]
         self._wi = [_Fused() for _ in enc.block]
         self._bias_cache = {}
+        self.use_graph = True
+        self._graphed = _GraphedForward()
 
     @property
     def device(self):
@@ -105,19 +140,22 @@ class T5EncoderB200(nn.Module):
         """compute_bias of block 0 (shared by all blocks): bf16 [H, S, S]."""
         emb = self.hf_module.encoder.block[0].layer[0].SelfAttention.relative_attention_bias.weight
         key = (S, emb.data_ptr(), tensor_version(emb))
-        hit = self._bias_cache.get("b")
+        hit = self._bias_cache.get(S)  # one entry per length: captured graphs keep reading the tensor they were built with
         if hit is None or hit[0] != key:
             pos = torch.arange(S, dtype=torch.long, device=emb.device)
             bucket = t5_relative_position_bucket(pos[None, :] - pos[:, None], self.cfg.relative_attention_num_buckets,
                                                  self.cfg.relative_attention_max_distance)
             bias = emb.detach()[bucket].permute(2, 0, 1).contiguous().to(BF16)  # [H, S, S]
-            self._bias_cache["b"] = hit = (key, bias)
+            self._bias_cache[S] = hit = (key, bias)
         return hit[1]
 
     @torch.inference_mode()
     def forward(self, input_ids: Tensor, attention_mask: Optional[Tensor] = None, output_hidden_states: bool = False, **kwargs):
         if attention_mask is not None:
             raise NotImplementedError("T5EncoderB200: the reference always passes attention_mask=None (conditioner.py:111)")
+        return self._graphed(self, input_ids)
+
+    def _forward(self, input_ids: Tensor):
         enc, cfg = self.hf_module.encoder, self.cfg
         B, S = input_ids.shape
         H, D, F = cfg.num_heads, cfg.d_model, cfg.d_ff
@@ -160,6 +198,8 @@ class CLIPTextB200(nn.Module):
         self.cfg = cfg
         self._qkv_w = [_Fused() for _ in tm.encoder.layers]
         self._qkv_b = [_Fused() for _ in tm.encoder.layers]
+        self.use_graph = True
+        self._graphed = _GraphedForward()
 
     @property
     def device(self):
@@ -169,6 +209,9 @@ class CLIPTextB200(nn.Module):
     def forward(self, input_ids: Tensor, attention_mask: Optional[Tensor] = None, output_hidden_states: bool = False, **kwargs):
         if attention_mask is not None:
             raise NotImplementedError("CLIPTextB200: the reference always passes attention_mask=None (conditioner.py:111)")
+        return self._graphed(self, input_ids)
+
+    def _forward(self, input_ids: Tensor):
         tm, cfg = self.hf_module.text_model, self.cfg
         B, S = input_ids.shape
         H, D, F = cfg.num_attention_heads, cfg.hidden_size, cfg.intermediate_size

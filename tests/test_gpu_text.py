@@ -179,6 +179,28 @@ def test_full_size_encoders_against_hugging_face_on_this_gpu(kind):
     assert mine.max().item() <= 2.0 * floor.max().item()
 
 
+def test_graph_replay_equals_eager_launches_and_follows_weight_updates():
+    """The CUDA-graph replay of an encoder returns the bits of its launch-by-launch run, for new token ids too, and is
+    re-captured when a parameter of the wrapped module changes."""
+    t5 = _hf("t5", T.T5_TINY, 3)
+    ours = CD.accelerate(t5)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    ids1 = torch.randint(0, 512, (2, 40), device=DEV, generator=g)
+    ids2 = torch.randint(0, 512, (2, 40), device=DEV, generator=g)
+    with torch.inference_mode():
+        ours.use_graph = False
+        e1, e2 = ours(input_ids=ids1).last_hidden_state.clone(), ours(input_ids=ids2).last_hidden_state.clone()
+        ours.use_graph = True
+        g1, g2, g1b = ours(input_ids=ids1).last_hidden_state, ours(input_ids=ids2).last_hidden_state, ours(input_ids=ids1).last_hidden_state
+        assert torch.equal(g1, e1) and torch.equal(g2, e2) and torch.equal(g1b, e1)
+        with torch.no_grad():
+            t5.encoder.block[0].layer[1].DenseReluDense.wo.weight.mul_(0.5)
+        changed = ours(input_ids=ids1).last_hidden_state
+        assert not torch.equal(changed, e1)
+        ours.use_graph = False
+        assert torch.equal(ours(input_ids=ids1).last_hidden_state, changed)
+
+
 def test_loud_failures_of_the_wrapper():
     from transformers import T5Config, T5EncoderModel
 
