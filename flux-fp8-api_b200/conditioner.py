@@ -41,7 +41,11 @@ BF16 = torch.bfloat16
 class _Output(dict):
     """Dict with attribute access: `outputs["last_hidden_state"]` and `outputs.last_hidden_state` (as ModelOutput allows)."""
 
-    __getattr__ = dict.__getitem__
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
 
 
 def _plain_bf16_linear(lin) -> bool:
