@@ -97,6 +97,7 @@ class ConvArgs(C.Structure):
         ("taps", C.c_int32),
         ("out_mode", C.c_int32),
         ("alpha", C.c_float),
+        ("stride", C.c_int32),
         ("gn_stats", C.c_void_p),
     ]
 

@@ -1,8 +1,8 @@
-"""VAE decode on the B200 kernels: the reference's `modules/autoencoder.py` decoder half.
+"""The VAE on the B200 kernels: the reference's `modules/autoencoder.py`.
 
 Same class names, constructor signatures, sub-module names and state-dict keys as the reference (`AttnBlock` :22-50,
-`ResnetBlock` :53-94, `Upsample` :112-123, `Decoder` :203-283, `AutoEncoder` :300-337), so a reference `ae.safetensors`
-loads with `load_state_dict(strict=False)` exactly as `util.py:283-286` does it.  The `nn.Conv2d` / `nn.GroupNorm`
+`ResnetBlock` :53-94, `Downsample` :97-110, `Upsample` :112-123, `Encoder` :126-200, `Decoder` :203-283, `AutoEncoder`
+:300-337), so a reference `ae.safetensors` loads exactly as `util.py:283-286` does it.  The `nn.Conv2d` / `nn.GroupNorm`
 children are parameter containers only: every forward runs through `libflux_b200.so` (`fluxb200_conv2d_nhwc`,
 `fluxb200_group_norm_nhwc`, `fluxb200_upsample2x_nhwc`, `fluxb200_softmax_rows`, `fluxb200_vae_latent_prep`) on
 channels-last bf16 activations; there is no torch fallback.
@@ -12,8 +12,10 @@ convolutions and attention take bf16 inputs, accumulate in fp32 and round to bf1
 `at::_convolution` does around cuDNN); GroupNorm and swish are evaluated in fp32 and rounded once, by the consuming
 convolution's input cast; residual sums are bf16 + bf16.
 
-The encoder half (`Encoder`, `Downsample`, `DiagonalGaussian`: image -> latent, used only by img2img) is outside the
-scope table; `AutoEncoder.encode` raises.
+The encoder half (`Encoder` :126-200, `Downsample` :97-110, `DiagonalGaussian` :286-298; image -> latent, used by img2img,
+flux_pipeline.py:489-500) runs on the same kernels: the stride-2 convolution of `Downsample` is the implicit GEMM with a
+TMA box that is traversed with element stride 2; the Gaussian sample and `scale_factor * (z - shift_factor)` stay eager
+torch (a [B, 16, H/8, W/8] tensor, and `torch.randn_like` has to be torch's generator to match the reference's draw).
 """
 from __future__ import annotations
 
@@ -93,7 +95,7 @@ def _conv(conv: nn.Conv2d, cache: _Packed, x: Tensor, residual: Optional[Tensor]
     stats = None
     if want_stats and out_mode == 0 and ops.conv_can_fuse_gn_stats(x.shape[0], w.shape[0]):
         stats = torch.empty((x.shape[0], 32, 2), dtype=torch.float64, device=x.device)
-    y = ops.conv2d_nhwc(x, w, b, taps, residual=residual, out_mode=out_mode, gn_stats=stats)
+    y = ops.conv2d_nhwc(x, w, b, taps, residual=residual, out_mode=out_mode, gn_stats=stats, stride=conv.stride[0])
     return (y, stats) if want_stats else y
 
 
@@ -204,6 +206,99 @@ class Upsample(nn.Module):
         return _to_nchw(self.forward_nhwc(_to_nhwc(x))[0])
 
 
+class Downsample(nn.Module):
+    """modules/autoencoder.py:97-110: F.pad(x, (0, 1, 0, 1)) then a 3x3 stride-2 convolution without padding."""
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
+        self._p = _Packed()
+
+    def forward_nhwc(self, x: Tensor, stats: Optional[Tensor] = None):
+        return _conv(self.conv, self._p, x, want_stats=True)  # the kernel's stride-2 form pads right / bottom by itself
+
+    def forward(self, x: Tensor) -> Tensor:
+        return _to_nchw(self.forward_nhwc(_to_nhwc(x))[0])
+
+
+class Encoder(nn.Module):
+    """modules/autoencoder.py:126-200"""
+
+    def __init__(self, resolution: int, in_channels: int, ch: int, ch_mult: List[int], num_res_blocks: int, z_channels: int):
+        super().__init__()
+        self.ch = ch
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.resolution = resolution
+        self.in_channels = in_channels
+        self.conv_in = nn.Conv2d(in_channels, self.ch, kernel_size=3, stride=1, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.in_ch_mult = in_ch_mult
+        self.down = nn.ModuleList()
+        block_in = self.ch
+        for i_level in range(self.num_resolutions):
+            block = nn.ModuleList()
+            attn = nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for _ in range(self.num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out))
+                block_in = block_out
+            down = nn.Module()
+            down.block = block
+            down.attn = attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in)
+        self.norm_out = nn.GroupNorm(num_groups=32, num_channels=block_in, eps=1e-6, affine=True)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels, kernel_size=3, stride=1, padding=1)
+        self._pin, self._pout = _Packed(), _Packed()
+
+    def forward_nhwc(self, h: Tensor) -> Tensor:
+        """h: bf16 [B, H, W, 64-padded image channels] -> bf16 NCHW moments [B, 2 z_channels, H/8, W/8]."""
+        h, st = _conv(self.conv_in, self._pin, h, want_stats=True)
+        for i_level in range(self.num_resolutions):
+            for i_block in range(self.num_res_blocks):
+                h, st = self.down[i_level].block[i_block].forward_nhwc(h, st)
+                if len(self.down[i_level].attn) > 0:
+                    h, st = self.down[i_level].attn[i_block].forward_nhwc(h, st)
+            if i_level != self.num_resolutions - 1:
+                h, st = self.down[i_level].downsample.forward_nhwc(h)
+        h, st = self.mid.block_1.forward_nhwc(h, st)
+        h, st = self.mid.attn_1.forward_nhwc(h, st)
+        h, st = self.mid.block_2.forward_nhwc(h, st)
+        h = _norm(self.norm_out, h, swish=True, stats=st)
+        return _conv(self.conv_out, self._pout, h, out_mode=2)
+
+    def forward(self, x: Tensor) -> Tensor:
+        c = self.conv_in.in_channels
+        if x.dim() != 4 or x.shape[1] != c:
+            raise ValueError(f"Encoder: x must be [B, {c}, H, W], got {tuple(x.shape)}")
+        return self.forward_nhwc(ops.vae_latent_prep(x.float().contiguous(), 1.0, 0.0, cpad=((c + 63) // 64) * 64))
+
+
+class DiagonalGaussian(nn.Module):
+    """modules/autoencoder.py:286-298 (eager torch: a tiny tensor, and the sample has to come from torch's generator)."""
+
+    def __init__(self, sample: bool = True, chunk_dim: int = 1):
+        super().__init__()
+        self.sample = sample
+        self.chunk_dim = chunk_dim
+
+    def forward(self, z: Tensor) -> Tensor:
+        mean, logvar = torch.chunk(z, 2, dim=self.chunk_dim)
+        if self.sample:
+            std = torch.exp(0.5 * logvar)
+            return mean + std * torch.randn_like(mean)
+        return mean
+
+
 class Decoder(nn.Module):
     """modules/autoencoder.py:203-283"""
 
@@ -267,18 +362,22 @@ class Decoder(nn.Module):
 
 
 class AutoEncoder(nn.Module):
-    """modules/autoencoder.py:300-337 (decode half)."""
+    """modules/autoencoder.py:300-337"""
 
     def __init__(self, params: AutoEncoderParams):
         super().__init__()
+        self.encoder = Encoder(resolution=params.resolution, in_channels=params.in_channels, ch=params.ch, ch_mult=params.ch_mult,
+                               num_res_blocks=params.num_res_blocks, z_channels=params.z_channels)
         self.decoder = Decoder(resolution=params.resolution, in_channels=params.in_channels, ch=params.ch, out_ch=params.out_ch,
                                ch_mult=params.ch_mult, num_res_blocks=params.num_res_blocks, z_channels=params.z_channels)
+        self.reg = DiagonalGaussian()
         self.scale_factor = params.scale_factor
         self.shift_factor = params.shift_factor
 
     def encode(self, x: Tensor) -> Tensor:
-        raise NotImplementedError("flux-fp8-api_b200 implements the decode half of the VAE (SURVEY.md 8f N4); "
-                                  "use the reference Encoder for img2img latents")
+        """:325-328: `reg(encoder(x))` then `scale_factor * (z - shift_factor)`; x [B, 3, H, W] in [-1, 1]."""
+        z = self.reg(self.encoder(x))
+        return self.scale_factor * (z - self.shift_factor)
 
     def decode(self, z: Tensor) -> Tensor:
         """`z / scale_factor + shift_factor` (:331) then the decoder; z [B, z_channels, H, W] -> bf16 [B, out_ch, 8H, 8W]."""

@@ -102,7 +102,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0
 }
 
 int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                 const uint32_t box[4]) {
+                 const uint32_t box[4], const uint32_t* elem_strides) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(FLUXB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides_bytes[0] & 15) || (strides_bytes[1] & 15) || (strides_bytes[2] & 15))
@@ -111,6 +111,8 @@ int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint6
   cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (elem_strides != nullptr)
+    for (int i = 0; i < 4; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(out, dtype_of(elem_bytes), 4, const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

@@ -72,7 +72,8 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0
 // 4-D tensor [d3, d2, d1, d0] (d0 innermost, contiguous; NHWC activations: d0 = C, d1 = W, d2 = H, d3 = B), strides in
 // bytes for d1..d3, SWIZZLE_128B (box0 * elem_bytes must be 128), out-of-bounds elements (negative coordinates
 // included) read as zero -- the zero padding of a convolution.
+// elem_strides (optional): traversal stride per dimension (a box of box[i] elements loads ceil(box[i] / stride) of them).
 int make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                 const uint32_t box[4]);
+                 const uint32_t box[4], const uint32_t* elem_strides = nullptr);
 
 }  // namespace fb

@@ -30,7 +30,8 @@ constexpr int kConvABytes = 128 * 128;  // 128 pixels x 64 channels x bf16
 struct ConvParams {
   CUtensorMap tmap_a;  // activations [B][H][W][Cin]
   CUtensorMap tmap_b;  // weights [N][taps * Cin]
-  int B, H, W, Cin, N, taps;
+  int B, H, W, Cin, N, taps;  // H, W: OUTPUT rows / columns (= the input's for stride 1)
+  int stride;                 // 1 (padding 1 all round) | 2 (Downsample: padding 0 left / top, 1 right / bottom)
   int tw, tw_shift, th;  // pixel tile: th rows x tw columns, th * tw = 128
   int tiles_x, tiles_y, m_tiles, n_tiles, num_tiles;  // num_tiles counts (pair of pixel tiles) x (channel tile)
   int kchunks;                                        // Cin / 64
@@ -139,14 +140,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       tile_origin(mt, b, y0, x0);
       const int n0 = n_blk * BN + static_cast<int>(rank) * S::kBRows;
       for (int tap = 0; tap < (HALO ? 3 : P.taps); ++tap) {
-        const int dy = HALO ? tap - 1 : (P.taps == 9 ? tap / 3 - 1 : 0);
-        const int dx = HALO ? -1 : (P.taps == 9 ? tap % 3 - 1 : 0);  // HALO: the box starts one pixel to the left
+        const int pad = P.stride == 1 ? 1 : 0;
+        const int dy = HALO ? tap - 1 : (P.taps == 9 ? tap / 3 - pad : 0);
+        const int dx = HALO ? -1 : (P.taps == 9 ? tap % 3 - pad : 0);  // HALO: the box starts one pixel to the left
         for (int kc = 0; kc < P.kchunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStage;
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kTxBytes);
-            tma_load_4d_2sm(sa, &P.tmap_a, &full_bar[stage], kc * 64, x0 + dx, y0 + dy, b);
+            tma_load_4d_2sm(sa, &P.tmap_a, &full_bar[stage], kc * 64, x0 * P.stride + dx, y0 * P.stride + dy, b);
             if constexpr (HALO) {
 #pragma unroll
               for (int t = 0; t < 3; ++t)
@@ -649,24 +651,30 @@ int fluxb200_conv2d_nhwc(const fluxb200_conv_args* a, fluxb200_stream_t stream_)
     FB_REQUIRE(a->bias == nullptr && a->residual == nullptr, "fluxb200_conv2d_nhwc(fp32): no bias / residual in this mode");
   } else {
     FB_REQUIRE(a->residual == nullptr, "fluxb200_conv2d_nhwc(NCHW): no residual in this mode");
-    FB_REQUIRE(a->ldo >= static_cast<int64_t>(a->H) * a->W, "fluxb200_conv2d_nhwc(NCHW): ldo (channel stride) must be >= H*W");
+    FB_REQUIRE(a->stride != 2 && a->ldo >= static_cast<int64_t>(a->H) * a->W,
+               "fluxb200_conv2d_nhwc(NCHW): stride 1 only; ldo (channel stride) must be >= H*W");
   }
+  const int stride = a->stride == 2 ? 2 : 1;
+  FB_REQUIRE(a->stride == 0 || a->stride == 1 || (a->stride == 2 && a->taps == 9 && a->H >= 2 && a->W >= 2),
+             "fluxb200_conv2d_nhwc: stride must be 1, or 2 with a 3x3 kernel (Downsample)");
+  // Downsample (autoencoder.py:97-110): pad (0, 1, 0, 1) then 3x3 stride 2 padding 0 -> floor((H - 2) / 2) + 1 rows
+  const int Ho = stride == 1 ? a->H : (a->H - 2) / 2 + 1, Wo = stride == 1 ? a->W : (a->W - 2) / 2 + 1;
   ConvParams P{};
-  P.B = a->B, P.H = a->H, P.W = a->W, P.Cin = a->Cin, P.N = a->N, P.taps = a->taps;
+  P.B = a->B, P.H = Ho, P.W = Wo, P.Cin = a->Cin, P.N = a->N, P.taps = a->taps, P.stride = stride;
   // pixel tile th x tw = 128 pixels: the power-of-two strip width that wastes the fewest out-of-image pixels
   // (ties -> the wider strip: longer contiguous runs per TMA box row)
   int tw = 128;
   int64_t best = -1;
   for (int t = 128; t >= 8; t /= 2) {
     const int h = 128 / t;
-    const int64_t area = static_cast<int64_t>((a->W + t - 1) / t) * t * ((a->H + h - 1) / h) * h;
+    const int64_t area = static_cast<int64_t>((Wo + t - 1) / t) * t * ((Ho + h - 1) / h) * h;
     if (best < 0 || area < best) best = area, tw = t;
   }
   P.tw = tw, P.th = 128 / tw;
   P.tw_shift = 0;
   while ((1 << P.tw_shift) < tw) ++P.tw_shift;
-  P.tiles_x = (a->W + P.tw - 1) / P.tw;
-  P.tiles_y = (a->H + P.th - 1) / P.th;
+  P.tiles_x = (Wo + P.tw - 1) / P.tw;
+  P.tiles_y = (Ho + P.th - 1) / P.th;
   P.m_tiles = a->B * P.tiles_x * P.tiles_y;
   int bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
   // a launch that cannot even fill the machine once with 256-wide tiles (dense layers over a few hundred rows: the text
@@ -698,9 +706,13 @@ int fluxb200_conv2d_nhwc(const fluxb200_conv_args* a, fluxb200_stream_t stream_)
                                static_cast<uint64_t>(ldx) * 2 * a->W * a->H};
   // 3x3 on 128-pixel row strips: the halo form (one 130-pixel row box serves the three horizontal taps)
   static const bool halo_on = [] { const char* e = getenv("FLUXB200_CONV_HALO"); return e == nullptr || atoi(e) != 0; }();
-  const bool halo = halo_on && a->taps == 9 && P.tw == 128;
-  const uint32_t box[4] = {64, static_cast<uint32_t>(halo ? kHaloRows : P.tw), static_cast<uint32_t>(P.th), 1};
-  int rc = make_tmap_4d(&P.tmap_a, a->x, 2, dims, strides, box);
+  const bool halo = halo_on && a->taps == 9 && P.tw == 128 && stride == 1;
+  // stride 2: the box spans 2 tw x 2 th input pixels and the TMA unit traverses it with element stride 2 in W and H, so the
+  // tile that lands in shared memory is again th x tw pixels x 64 channels (out-of-bounds pixels, here the one-pixel padding
+  // on the right / bottom, still read as zero)
+  const uint32_t box[4] = {64, static_cast<uint32_t>((halo ? kHaloRows : P.tw) * stride), static_cast<uint32_t>(P.th * stride), 1};
+  const uint32_t estr[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+  int rc = make_tmap_4d(&P.tmap_a, a->x, 2, dims, strides, box, estr);
   if (rc) return rc;
   const int64_t K = static_cast<int64_t>(a->taps) * a->Cin;
   const int64_t ldw = a->ldw > 0 ? a->ldw : K;

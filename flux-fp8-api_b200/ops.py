@@ -565,10 +565,11 @@ def pack_conv_weight(weight: Tensor, cin_pad: Optional[int] = None) -> Tensor:
 
 def conv2d_nhwc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], taps: int, residual: Optional[Tensor] = None,
                 out: Optional[Tensor] = None, out_mode: int = 0, alpha: float = 1.0, nchw_plane: Optional[int] = None,
-                gn_stats: Optional[Tensor] = None) -> Tensor:
+                gn_stats: Optional[Tensor] = None, stride: int = 1) -> Tensor:
     """fluxb200_conv2d_nhwc.  x bf16 [B, H, W, Cin] (Cin % 64 == 0); w_packed from pack_conv_weight.
     out_mode 0 -> bf16 [B, H, W, N] (+ bias, + residual); 1 -> fp32 [B, H, W, N] = alpha * acc; 2 -> bf16 NCHW [B, N, H, W].
-    gn_stats (fp64 [B, 32, 2], out_mode 0): filled with the GroupNorm(32) sums of the stored output by the epilogue."""
+    gn_stats (fp64 [B, 32, 2], out_mode 0): filled with the GroupNorm(32) sums of the stored output by the epilogue.
+    stride 2 (3x3 only): the reference's Downsample = F.pad(x, (0, 1, 0, 1)) then stride-2 convolution without padding."""
     cabi.require_cuda(x, w_packed)
     _want(x, BF16, "conv2d_nhwc: x"), _want(w_packed, BF16, "conv2d_nhwc: w"), _want(bias, BF16, "conv2d_nhwc: bias")
     _want(residual, BF16, "conv2d_nhwc: residual")
@@ -580,11 +581,14 @@ def conv2d_nhwc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], taps: int, 
     N = w_packed.shape[0]
     if w_packed.shape[1] != taps * Cin or w_packed.stride(1) != 1:
         raise ValueError(f"conv2d_nhwc: packed weight {tuple(w_packed.shape)} does not match taps={taps} Cin={Cin}")
+    if stride not in (1, 2) or (stride == 2 and (taps != 9 or out_mode == 2 or H < 2 or W < 2)):
+        raise ValueError("conv2d_nhwc: stride 2 is the 3x3 Downsample convolution (NHWC / fp32 output)")
+    Ho, Wo = (H, W) if stride == 1 else ((H - 2) // 2 + 1, (W - 2) // 2 + 1)
     if out is None:
         if out_mode == 0:
-            out = torch.empty((B, H, W, N), dtype=BF16, device=x.device)
+            out = torch.empty((B, Ho, Wo, N), dtype=BF16, device=x.device)
         elif out_mode == 1:
-            out = torch.empty((B, H, W, N), dtype=torch.float32, device=x.device)
+            out = torch.empty((B, Ho, Wo, N), dtype=torch.float32, device=x.device)
         else:
             out = torch.empty((B, N, H, W), dtype=BF16, device=x.device)
     _contig(out, "conv2d_nhwc: out")
@@ -594,19 +598,21 @@ def conv2d_nhwc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], taps: int, 
     a.ldx, a.ldw = x.stride(2), w_packed.stride(0)
     if residual is not None:
         _contig(residual, "conv2d_nhwc: residual")
-        if residual.numel() != B * H * W * N:
+        if residual.numel() != B * Ho * Wo * N:
             raise ValueError("conv2d_nhwc: residual must have the output's shape")
         a.residual, a.ld_res = residual.data_ptr(), N
     a.ldo = N if out_mode != 2 else (nchw_plane or H * W)
-    a.B, a.H, a.W, a.Cin, a.N, a.taps, a.out_mode, a.alpha = B, H, W, Cin, N, taps, out_mode, alpha
+    a.B, a.H, a.W, a.Cin, a.N, a.taps, a.out_mode, a.alpha, a.stride = B, H, W, Cin, N, taps, out_mode, alpha, stride
+    if out.numel() != B * Ho * Wo * N and out_mode != 2:
+        raise ValueError("conv2d_nhwc: out has the wrong number of elements")
     if gn_stats is not None:
         _want(gn_stats, torch.float64, "conv2d_nhwc: gn_stats")
         if gn_stats.numel() != B * 64 or not gn_stats.is_contiguous():
             raise ValueError("conv2d_nhwc: gn_stats must be a contiguous fp64 [B, 32, 2]")
         a.gn_stats = gn_stats.data_ptr()
-    _timed("conv2d", 2.0 * B * H * W * N * taps * Cin,
+    _timed("conv2d", 2.0 * B * Ho * Wo * N * taps * Cin,
            lambda: cabi.check(cabi.load().fluxb200_conv2d_nhwc(C.byref(a), cabi.stream_ptr()), "fluxb200_conv2d_nhwc"),
-           f"{B}x{H}x{W} {Cin}->{N} taps {taps}" if KERNEL_TIMELINE is not None else "")
+           f"{B}x{H}x{W} {Cin}->{N} taps {taps}{' stride 2' if stride == 2 else ''}" if KERNEL_TIMELINE is not None else "")
     return out
 
 

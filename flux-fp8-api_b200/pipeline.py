@@ -68,7 +68,7 @@ def vae_decode(ae, x: Tensor, height: int, width: int) -> Tensor:
         return ae.decode(unpack(x.float(), height, width).contiguous())
 
 
-def init_synthetic_vae_weights(ae: nn.Module, seed: int = 77, dtype=BF16) -> None:
+def init_synthetic_vae_weights(ae: nn.Module, seed: int = 77, dtype=BF16, prefixes=("decoder.",)) -> None:
     """Seeded parameters for an AutoEncoder (there are no weights to download): N(0, 1/fan_in) convolutions, GroupNorm affine
     1 + 0.1 N / 0.1 N, biases 0.05 N, the attention's q / k projections x3 so its softmax is not uniform.  Keys are visited in
     sorted order, so the same seed gives the same tensors to any module with the reference's decoder keys."""
@@ -76,7 +76,7 @@ def init_synthetic_vae_weights(ae: nn.Module, seed: int = 77, dtype=BF16) -> Non
     full = ae.state_dict()
     new = {}
     for k in sorted(full):
-        if not k.startswith("decoder."):
+        if not k.startswith(tuple(prefixes)):
             continue
         shape = full[k].shape
         if ".norm" in k and k.endswith(".weight"):

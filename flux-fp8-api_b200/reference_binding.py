@@ -37,9 +37,8 @@ F8_NAMES = ("F8Linear", "recursive_swap_linears", "quantize_flow_transformer_and
 CONTAINER_NAMES = ("Flux", "MLPEmbedder", "LastLayer", "timestep_embedding")
 
 
-#: modules/autoencoder.py names replaced by autoencoder.py (the decode half; Encoder / Downsample /
-#: DiagonalGaussian stay the reference's)
-AE_NAMES = ("AttnBlock", "ResnetBlock", "Upsample", "Decoder", "AutoEncoder")
+#: modules/autoencoder.py names replaced by autoencoder.py
+AE_NAMES = ("AttnBlock", "ResnetBlock", "Upsample", "Downsample", "Encoder", "Decoder", "DiagonalGaussian", "AutoEncoder")
 
 
 def bind(float8_quantize: ModuleType, flux_model: ModuleType, lora_loading: Optional[ModuleType] = None,

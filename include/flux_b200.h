@@ -221,6 +221,8 @@ typedef struct fluxb200_conv_args {
   int64_t ldx, ldw, ld_res, ldo;
   int32_t B, H, W, Cin, N, taps, out_mode;
   float alpha;          /* out_mode 1 */
+  int32_t stride;       /* 0 / 1: stride 1, padding 1 all round.  2 (taps = 9): Downsample.forward (autoencoder.py:97-110) =
+                           F.pad(x, (0, 1, 0, 1)) then 3x3 stride 2 padding 0; output [B, (H-2)/2+1, (W-2)/2+1, N] */
   double* gn_stats;     /* optional (out_mode 0, B <= 4, N % 64 == 0): receives the GroupNorm(32) statistics of the STORED
                            output, [B][32]{sum, sum of squares} -- pass it to fluxb200_group_norm_nhwc with stats_ready = 1
                            and the normalisation of this tensor skips its own reduction pass */

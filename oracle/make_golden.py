@@ -390,9 +390,10 @@ def golden_vae():
 
     print("vae_tiny.pt")
     ae = ref_ae.AutoEncoder(ref_ae.AutoEncoderParams(**VAE_TINY))
-    sd = V.synthetic_state(ae, seed=31)
-    missing, unexpected = ae.load_state_dict({k: v.float() for k, v in sd.items()}, strict=False)
-    assert not unexpected and all(k.startswith("encoder.") for k in missing), (missing, unexpected)
+    sd = V.synthetic_state(ae, seed=31)                                      # decoder tensors (fingerprinted below)
+    sd_all = V.synthetic_state(ae, seed=31, prefixes=("decoder.", "encoder."))  # + encoder tensors, decoder ones unchanged
+    assert all(torch.equal(sd[k], sd_all[k]) for k in sd)
+    missing, unexpected = ae.load_state_dict({k: v.float() for k, v in sd_all.items()}, strict=True)
     ae = ae.float().eval()
     g = torch.Generator().manual_seed(32)
     z = torch.randn(2, 16, 8, 8, generator=g) * 1.2
@@ -406,6 +407,15 @@ def golden_vae():
         h0 = ae.decoder.conv_in(z / VAE_TINY["scale_factor"] + VAE_TINY["shift_factor"])
         h1 = ae.decoder.mid.block_1(h0)
         h2 = ae.decoder.mid.attn_1(h1)
+        # encoder half (img2img): the Gaussian's moments of a seeded image, reference fp32 vs oracle
+        img = torch.randn(2, 3, 64, 64, generator=g).clamp(-1, 1)
+        m_ref = ae.encoder(img)
+        m_ora32 = V.encoder(img, sd_all, VAE_TINY["ch_mult"], VAE_TINY["num_res_blocks"], policy="fp32")
+        m_auto = V.encoder(img, sd_all, VAE_TINY["ch_mult"], VAE_TINY["num_res_blocks"], policy="autocast")
+    dm = maxdiff(m_ref, m_ora32)
+    print(f"  encoder: oracle(fp32) vs reference(fp32) max|d| {dm:.3g} on amax {m_ref.abs().max().item():.3g}; "
+          f"oracle(autocast) mean|d| {(m_ref - m_auto.float()).abs().mean().item():.3g}")
+    assert dm <= 2e-4 * max(1.0, m_ref.abs().max().item()), dm
     d = maxdiff(y_ref, y_ora32)
     print(f"  oracle(fp32) vs reference(fp32): max|d| {d:.3g} on amax {y_ref.abs().max().item():.3g}")
     assert d <= 2e-4 * max(1.0, y_ref.abs().max().item()), d
@@ -414,7 +424,8 @@ def golden_vae():
     # the 12 M parameters are not stored: tests regenerate them with V.synthetic_state(<any module with the reference's
     # decoder keys>, seed=31) and check the fingerprint
     torch.save({"params": VAE_TINY, "state_seed": 31, "state_checksum": V.state_checksum(sd), "z": z, "y_ref_fp32": y_ref, "y_oracle_autocast": y_auto,
-                "h_conv_in": h0, "h_mid_block_1": h1, "h_mid_attn_1": h2}, os.path.join(OUT, "vae_tiny.pt"))
+                "h_conv_in": h0, "h_mid_block_1": h1, "h_mid_attn_1": h2,
+                "img": img, "moments_ref_fp32": m_ref, "moments_oracle_autocast": m_auto}, os.path.join(OUT, "vae_tiny.pt"))
 
 
 def golden_text():

@@ -97,13 +97,36 @@ def decoder(z: Tensor, sd: Dict[str, Tensor], ch_mult: List[int], num_res_blocks
     return _conv(h, sd, prefix + ".conv_out", 1, policy)
 
 
+def encoder(x: Tensor, sd: Dict[str, Tensor], ch_mult: List[int], num_res_blocks: int, policy: str = "autocast",
+            prefix: str = "encoder") -> Tensor:
+    """Encoder.forward :177-200 -> the Gaussian's moments [B, 2 z_channels, H/8, W/8]; Downsample.forward :106-110 pads
+    (0, 1, 0, 1) and convolves 3x3 with stride 2."""
+    h = _conv(x, sd, prefix + ".conv_in", 1, policy)
+    for i_level in range(len(ch_mult)):
+        for i_block in range(num_res_blocks):
+            h = resnet_block(h, sd, f"{prefix}.down.{i_level}.block.{i_block}", policy)
+        if i_level != len(ch_mult) - 1:
+            name = f"{prefix}.down.{i_level}.downsample.conv"
+            w, b = sd[name + ".weight"], sd[name + ".bias"]
+            hp = F.pad(h.float() if policy == "fp32" else h.to(BF16).float(), (0, 1, 0, 1))
+            if policy == "fp32":
+                h = F.conv2d(hp, w.float(), b.float(), stride=2)
+            else:
+                h = (F.conv2d(hp, w.to(BF16).float(), None, stride=2).to(BF16).float() + b.to(BF16).float().view(1, -1, 1, 1)).to(BF16)
+    h = resnet_block(h, sd, prefix + ".mid.block_1", policy)
+    h = attn_block(h, sd, prefix + ".mid.attn_1", policy)
+    h = resnet_block(h, sd, prefix + ".mid.block_2", policy)
+    h = swish(_gn(h, sd, prefix + ".norm_out"))
+    return _conv(h, sd, prefix + ".conv_out", 1, policy)
+
+
 def decode(z: Tensor, sd: Dict[str, Tensor], ch_mult: List[int], num_res_blocks: int, scale_factor: float, shift_factor: float,
            policy: str = "autocast") -> Tensor:
     """AutoEncoder.decode :330-333 on an fp32 latent (flux_pipeline.py:430 hands over `x.float()`)."""
     return decoder(z.float() / scale_factor + shift_factor, sd, ch_mult, num_res_blocks, policy)
 
 
-def synthetic_state(ref_ae_module, seed: int, dtype=torch.bfloat16) -> Dict[str, Tensor]:
+def synthetic_state(ref_ae_module, seed: int, dtype=torch.bfloat16, prefixes=("decoder.",)) -> Dict[str, Tensor]:
     """Seeded, better-conditioned-than-default parameters for a reference AutoEncoder (there are no weights to download):
     default Conv2d init, GroupNorm affine 1 + 0.1 N / 0.1 N, q / k projections x3 so the attention is not uniform.  Rounded
     to `dtype` (the reference keeps the VAE in bf16, util.py:287)."""
@@ -112,7 +135,7 @@ def synthetic_state(ref_ae_module, seed: int, dtype=torch.bfloat16) -> Dict[str,
     full = ref_ae_module.state_dict()
     for k in sorted(full):  # sorted: the stream of random numbers does not depend on module construction order
         v = full[k]
-        if not k.startswith("decoder."):
+        if not k.startswith(tuple(prefixes)):  # ("decoder.", "encoder."): the decoder's tensors come first and are unchanged
             continue
         t = v.detach().float().clone()
         if ".norm" in k and k.endswith(".weight"):

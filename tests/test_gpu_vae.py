@@ -148,7 +148,8 @@ def _tiny(golden_dir):
     m = A.AutoEncoder(A.AutoEncoderParams(**g["params"]))
     sd = V.synthetic_state(m, g["state_seed"])
     assert V.state_checksum(sd) == g["state_checksum"]
-    missing, unexpected = m.load_state_dict(sd, strict=True)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("encoder.") for k in missing)
     return g, m.to(DEV, BF16).eval(), sd
 
 
@@ -191,10 +192,12 @@ def test_loud_failures():
         ops.conv2d_nhwc(_rand((1, 8, 8, 64), 42), _rand((64, 9 * 64), 43).float(), None, 9)  # fp32 weights
     m = A.AutoEncoder(A.AutoEncoderParams(resolution=64, in_channels=3, ch=64, out_ch=3, ch_mult=[1, 2], num_res_blocks=1,
                                           z_channels=16, scale_factor=1.0, shift_factor=0.0))
-    with pytest.raises(NotImplementedError):
-        m.encode(torch.zeros(1, 3, 64, 64))
     with pytest.raises(ValueError):
         m.to(DEV, BF16).decode(torch.zeros(1, 4, 8, 8, device=DEV))
+    with pytest.raises(ValueError):
+        m.encode(torch.zeros(1, 4, 64, 64, device=DEV))
+    with pytest.raises(ValueError):
+        ops.conv2d_nhwc(x.new_zeros((1, 8, 8, 64)), _rand((64, 64), 44), None, 1, stride=2)  # stride 2 is the 3x3 Downsample only
 
 
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref not staged (python oracle/fetch_ref.py)")
@@ -212,7 +215,7 @@ def test_full_size_decode_against_the_reference_on_this_gpu(res):
     rae.load_state_dict(sd, strict=False)
     rae = rae.to(DEV, BF16).eval()  # util.py:287: the reference keeps the VAE in bf16
     ours = A.AutoEncoder(A.AutoEncoderParams(**params))
-    ours.load_state_dict(sd, strict=True)
+    ours.load_state_dict(sd, strict=False)
     ours = ours.to(DEV, BF16).eval()
     z = torch.randn(1, 16, res // 8, res // 8, device=DEV, generator=torch.Generator(device=DEV).manual_seed(78)) * 1.2
 
@@ -273,7 +276,7 @@ def test_decoder_shapes_outside_the_fast_paths_against_the_reference(B, height, 
     rae.load_state_dict(sd, strict=False)
     rae = rae.to(DEV, BF16).eval()
     ours = A.AutoEncoder(A.AutoEncoderParams(**params))
-    ours.load_state_dict(sd, strict=True)
+    ours.load_state_dict(sd, strict=False)
     ours = ours.to(DEV, BF16).eval()
     z = torch.randn(B, 16, height // 8, width // 8, device=DEV, generator=torch.Generator(device=DEV).manual_seed(92)) * 1.2
     with torch.inference_mode():
@@ -314,12 +317,97 @@ def test_packed_weights_follow_parameter_updates(golden_dir):
     with torch.inference_mode():
         y1 = m.decode(z).clone()
     assert not torch.equal(y0, y1)
-    m.load_state_dict({k: v.to(DEV) for k, v in sd.items()})  # copies in place: version bump again
+    m.load_state_dict({k: v.to(DEV) for k, v in sd.items()}, strict=False)  # copies in place: version bump again
     with torch.inference_mode():
         assert torch.equal(m.decode(z), y0)
         m2 = A.AutoEncoder(A.AutoEncoderParams(**g["params"])).to(DEV, BF16)
-        m2.load_state_dict({k: v.to(DEV) for k, v in sd.items()})
+        m2.load_state_dict({k: v.to(DEV) for k, v in sd.items()}, strict=False)
         assert torch.equal(m2.decode(z), y0)
         m2.decoder.conv_out.weight.mul_(2.0)  # inference tensor: no version counter
         A.invalidate_packed(m2)
         assert not torch.equal(m2.decode(z), y0)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N", [(1, 16, 16, 64, 64), (2, 64, 64, 128, 128), (1, 256, 256, 128, 128), (1, 30, 44, 64, 256),
+                                         (1, 17, 23, 64, 64)])
+def test_downsample_convolution_stride_2(B, H, W, Cin, N):
+    """Downsample.forward (autoencoder.py:106-110): F.pad(x, (0, 1, 0, 1)) then 3x3 stride 2 padding 0, through the TMA box
+    with element stride 2 (odd sizes included: the pad column / row is the TMA unit's out-of-bounds zero)."""
+    x = _rand((B, H, W, Cin), 60)
+    w = _rand((N, Cin, 3, 3), 61, 1.0 / math.sqrt(Cin * 9))
+    b = _rand((N,), 62, 0.1)
+    out = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), b, 9, stride=2)
+    acc = F.conv2d(F.pad(x.permute(0, 3, 1, 2).float(), (0, 1, 0, 1)), w.float(), None, stride=2)
+    ref = (acc.to(BF16).float() + b.float().view(1, -1, 1, 1)).to(BF16)
+    assert out.shape == (B, ref.shape[2], ref.shape[3], N)
+    _close_in_ulps(out.permute(0, 3, 1, 2), ref, ref.float().abs().max().item(), f"downsample {B}x{H}x{W} {Cin}->{N}")
+
+
+def test_tiny_encoder_against_the_golden_moments(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "vae_tiny.pt"))
+    m = A.AutoEncoder(A.AutoEncoderParams(**g["params"]))
+    m.load_state_dict(V.synthetic_state(m, g["state_seed"], prefixes=("decoder.", "encoder.")), strict=True)
+    m = m.to(DEV, BF16).eval()
+    with torch.inference_mode():
+        mom = m.encoder(g["img"].to(DEV)).float().cpu()
+        torch.manual_seed(5)
+        z = m.encode(g["img"].to(DEV))
+    ref32, auto = g["moments_ref_fp32"], g["moments_oracle_autocast"].float()
+    floor, mine = (auto - ref32).abs().mean().item(), (mom - ref32).abs().mean().item()
+    print(f"tiny encoder moments: ours-vs-fp32 {mine:.4g}, autocast-oracle-vs-fp32 {floor:.4g}")
+    assert mom.shape == ref32.shape and mine <= 1.25 * floor
+    assert z.shape == (2, 16, 8, 8) and torch.isfinite(z).all()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not staged (python oracle/fetch_ref.py)")
+def test_full_size_encode_against_the_reference_on_this_gpu():
+    """Flux's VAE encoder at 1024 x 1024 (img2img, flux_pipeline.py:489-500): the Gaussian's moments against the staged reference
+    under CUDA autocast with its own bf16-vs-fp32 distance as the floor; the sampled latent with the same torch seed."""
+    ref = R.load()
+    if ref.ae is None:
+        pytest.skip("modules/autoencoder.py not staged (re-run oracle/fetch_ref.py)")
+    params = dict(resolution=256, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2, z_channels=16,
+                  scale_factor=0.3611, shift_factor=0.1159)
+    rae = ref.ae.AutoEncoder(ref.ae.AutoEncoderParams(**params))
+    sd = V.synthetic_state(rae, seed=93, prefixes=("decoder.", "encoder."))
+    rae.load_state_dict(sd, strict=True)
+    rae = rae.to(DEV, BF16).eval()
+    ours = A.AutoEncoder(A.AutoEncoderParams(**params))
+    ours.load_state_dict(sd, strict=True)
+    ours = ours.to(DEV, BF16).eval()
+    img = (torch.rand(1, 3, 1024, 1024, device=DEV, generator=torch.Generator(device=DEV).manual_seed(94)) * 2 - 1).to(BF16)
+
+    def timed(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            out = fn()
+        e.record()
+        torch.cuda.synchronize()
+        return out, s.elapsed_time(e) / n
+
+    with torch.inference_mode():
+        def run_ref():
+            with torch.autocast(device_type="cuda", dtype=BF16, cache_enabled=False):
+                return rae.encoder(img)
+
+        m_ref, ms_ref = timed(run_ref)
+        m_ours, ms_ours = timed(lambda: ours.encoder(img))
+        torch.manual_seed(11)
+        with torch.autocast(device_type="cuda", dtype=BF16, cache_enabled=False):
+            z_ref = rae.encode(img)
+            torch.manual_seed(11)
+            z_ours = ours.encode(img)
+        m32 = rae.float().encoder(img.float())
+    floor, d32 = (m_ref.float() - m32).abs(), (m_ours.float() - m32).abs()
+    rep = {"moments_amax": m32.abs().max().item(), "reference_autocast_vs_fp32": {"mean": floor.mean().item(), "max": floor.max().item()},
+           "ours_vs_fp32": {"mean": d32.mean().item(), "max": d32.max().item()},
+           "latent_ours_vs_reference": {"mean": (z_ours.float() - z_ref.float()).abs().mean().item()},
+           "ms_reference_autocast": ms_ref, "ms_ours": ms_ours}
+    print(json.dumps(rep))
+    with open(os.path.join(ROOT, "gpurun_out", "vae_encode_parity_1024.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    assert m_ours.shape == m_ref.shape == (1, 32, 128, 128) and z_ours.shape == (1, 16, 128, 128)
+    assert d32.mean().item() <= 1.25 * floor.mean().item() and d32.max().item() <= 1.5 * floor.max().item()

@@ -284,7 +284,7 @@ def test_vae_host_side_keys_packing_and_loud_failure():
     m = A.AutoEncoder(A.AutoEncoderParams(resolution=256, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4, 4], num_res_blocks=2,
                                           z_channels=16, scale_factor=0.3611, shift_factor=0.1159))
     keys = set(m.state_dict())
-    assert len(keys) == 138 and all(k.startswith("decoder.") for k in keys)
+    assert len(keys) == 244 and sum(k.startswith("decoder.") for k in keys) == 138 and sum(k.startswith("encoder.") for k in keys) == 106
     for k in ("decoder.conv_in.weight", "decoder.mid.attn_1.q.weight", "decoder.mid.block_1.norm1.weight",
               "decoder.up.0.block.0.nin_shortcut.weight", "decoder.up.3.upsample.conv.bias", "decoder.up.1.block.2.conv2.weight",
               "decoder.norm_out.bias", "decoder.conv_out.weight"):
@@ -307,8 +307,10 @@ def test_vae_host_side_keys_packing_and_loud_failure():
         with pytest.raises(Exception) as ei:
             m.decode(torch.zeros(1, 16, 8, 8))
         assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
-    with pytest.raises(NotImplementedError):
-        m.encode(torch.zeros(1, 3, 64, 64))
+    assert m.state_dict()["encoder.down.1.downsample.conv.weight"].shape == (256, 256, 3, 3) and m.encoder.down[1].downsample.conv.stride == (2, 2)
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            m.encode(torch.zeros(1, 3, 64, 64))
 
 
 def test_unpack_inverts_patchify_like_the_reference_rearrange():
@@ -336,4 +338,8 @@ def test_synthetic_vae_weights_match_the_oracle_generator():
     want = V.synthetic_state(ae, seed=5)
     PL.init_synthetic_vae_weights(ae, seed=5)
     got = ae.state_dict()
-    assert set(got) == set(want) and all(torch.equal(got[k].to(torch.bfloat16), want[k]) for k in want)
+    assert set(want) == {k for k in got if k.startswith("decoder.")} and all(torch.equal(got[k].to(torch.bfloat16), want[k]) for k in want)
+    want_all = V.synthetic_state(ae, seed=5, prefixes=("decoder.", "encoder."))
+    PL.init_synthetic_vae_weights(ae, seed=5, prefixes=("decoder.", "encoder."))
+    got = ae.state_dict()
+    assert set(want_all) == set(got) and all(torch.equal(got[k].to(torch.bfloat16), want_all[k]) for k in want_all)

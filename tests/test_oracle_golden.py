@@ -198,6 +198,11 @@ def test_vae_oracle_reproduces_the_reference_decode(golden_dir):
     ya = V.decode(g["z"], sd, p["ch_mult"], p["num_res_blocks"], p["scale_factor"], p["shift_factor"], policy="autocast")
     assert torch.equal(ya, g["y_oracle_autocast"])
     assert (ya.float() - g["y_ref_fp32"]).abs().mean().item() <= 0.01 * g["y_ref_fp32"].abs().max().item()
+    # encoder half: the Gaussian's moments of the reference Encoder (fp32)
+    sd_all = V.synthetic_state(shapes, g["state_seed"], prefixes=("decoder.", "encoder."))
+    m32 = V.encoder(g["img"], sd_all, p["ch_mult"], p["num_res_blocks"], policy="fp32")
+    assert (m32 - g["moments_ref_fp32"]).abs().max().item() <= 2e-4 * g["moments_ref_fp32"].abs().max().item()
+    assert torch.equal(V.encoder(g["img"], sd_all, p["ch_mult"], p["num_res_blocks"], policy="autocast"), g["moments_oracle_autocast"])
 
 
 def test_text_encoder_oracle_reproduces_the_hugging_face_modules(golden_dir):

@@ -52,7 +52,7 @@ def test_autoencoder_surface_matches_the_reference():
 
     ref = R.load()
     assert ref.ae is not None, getattr(ref, "ae_error", "")
-    for name in ("AttnBlock", "ResnetBlock", "Upsample", "Decoder", "AutoEncoder"):
+    for name in ("AttnBlock", "ResnetBlock", "Upsample", "Downsample", "Encoder", "Decoder", "DiagonalGaussian", "AutoEncoder"):
         ours, theirs = getattr(A, name), getattr(ref.ae, name)
         assert [p.name for p in inspect.signature(ours.__init__).parameters.values()] == \
                [p.name for p in inspect.signature(theirs.__init__).parameters.values()], name
@@ -61,11 +61,10 @@ def test_autoencoder_surface_matches_the_reference():
                   scale_factor=0.3611, shift_factor=0.1159)
     theirs = ref.ae.AutoEncoder(ref.ae.AutoEncoderParams(**params)).state_dict()
     ours = A.AutoEncoder(A.AutoEncoderParams(**params)).state_dict()
-    dec = {k: v.shape for k, v in theirs.items() if k.startswith("decoder.")}
-    assert {k: v.shape for k, v in ours.items()} == dec
-    # a reference checkpoint loads the way util.py:285 loads it (strict=False: the encoder half is not ours)
+    assert {k: v.shape for k, v in ours.items()} == {k: v.shape for k, v in theirs.items()}
+    # a reference checkpoint loads the way util.py:285 loads it
     missing, unexpected = A.AutoEncoder(A.AutoEncoderParams(**params)).load_state_dict(theirs, strict=False)
-    assert not missing and all(k.startswith("encoder.") for k in unexpected)
+    assert not missing and not unexpected
 
 
 @needs_ref
@@ -84,7 +83,7 @@ def test_bind_redirects_the_autoencoder_and_a_reference_checkpoint_loads():
         assert ref.ae.AutoEncoder is A.AutoEncoder and ref.ae.Decoder is A.Decoder
         built = ref.ae.AutoEncoder(ref.ae.AutoEncoderParams(**params))  # the reference's own params class
         missing, unexpected = built.load_state_dict(theirs.state_dict(), strict=False, assign=True)
-        assert not missing and unexpected and all(k.startswith("encoder.") for k in unexpected)
+        assert not missing and not unexpected
         assert torch.equal(built.decoder.conv_in.weight, theirs.decoder.conv_in.weight)
         assert built.scale_factor == theirs.scale_factor and built.shift_factor == theirs.shift_factor
         with pytest.raises(Exception):

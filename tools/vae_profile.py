@@ -17,7 +17,7 @@ params = dict(resolution=256, in_channels=3, ch=128, out_ch=3, ch_mult=[1, 2, 4,
               scale_factor=0.3611, shift_factor=0.1159)
 m = A.AutoEncoder(A.AutoEncoderParams(**params))
 sd = V.synthetic_state(m, seed=77)
-m.load_state_dict(sd)
+m.load_state_dict(sd, strict=False)
 m = m.to("cuda", torch.bfloat16).eval()
 z = torch.randn(B, 16, res // 8, res // 8, device="cuda") * 1.2
 
