@@ -679,7 +679,16 @@ int fluxb200_conv2d_nhwc(const fluxb200_conv_args* a, fluxb200_stream_t stream_)
   int bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
   // a launch that cannot even fill the machine once with 256-wide tiles (dense layers over a few hundred rows: the text
   // encoders' o / wo projections) takes 128-wide tiles: twice the CTAs, same bytes per flop from L2
-  if (bn == 256 && static_cast<int64_t>((P.m_tiles + 1) / 2) * ((a->N + 255) / 256) < sm_count() / 2) bn = 128;
+  // ... and, for the few-wave launches of the dense layers (M of a few hundred rows), whichever of 256 / 128 leaves the
+  // smaller idle tail in its last wave (e.g. T5's q | k | v projection: 96 tiles = 1.3 waves of 74 pairs at 256, 192 tiles
+  // = 2.6 waves at 128)
+  if (bn == 256 && a->N % 128 == 0 && a->taps == 1) {
+    const int64_t pairs = sm_count() / 2, mp = (P.m_tiles + 1) / 2;
+    const int64_t t256 = mp * ((a->N + 255) / 256), t128 = mp * (a->N / 128);
+    const double e256 = static_cast<double>(t256) / (((t256 + pairs - 1) / pairs) * pairs);
+    const double e128 = static_cast<double>(t128) / (((t128 + pairs - 1) / pairs) * pairs);
+    if (t256 < pairs || (t256 < 4 * pairs && e128 > e256 + 0.1)) bn = 128;
+  }
   P.n_tiles = (a->N + bn - 1) / bn;
   P.num_tiles = ((P.m_tiles + 1) / 2) * P.n_tiles;
   P.kchunks = a->Cin / 64;
