@@ -346,9 +346,8 @@ __device__ __forceinline__ void epi_qkv_head(const fluxb200_gemm_args& g, const 
       // fp32 sum of squares of the bf16-rounded linear output (F.rms_norm on x.float())
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float2 f = unpack_bf16x2(yp[c][j]);
-        ss = fmaf(f.x, f.x, ss);
-        ss = fmaf(f.y, f.y, ss);
+        ss = fma_sq_f32_bf16lo(yp[c][j], ss);  // the bf16 halves enter the fp32 FMA directly (FHFMA.BF16)
+        ss = fma_sq_f32_bf16hi(yp[c][j], ss);
       }
     }
   }

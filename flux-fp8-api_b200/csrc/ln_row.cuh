@@ -45,7 +45,8 @@ __device__ __forceinline__ void ln_mod_quant_row(const LnSeg& G, int row, int D,
   constexpr int kIter = NI ? NI : kLnMaxIter;
   const uint4* xp = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
   uint4 xv[kIter];
-  float sum = 0.f;
+  // the bf16 halves enter the fp32 arithmetic directly (FHADD.BF16: no unpack instructions in any of the three passes)
+  float sum = 0.f, sum1 = 0.f;  // low / high halves: two independent chains
 #pragma unroll
   for (int i = 0; i < kIter; ++i) {
     if (NI || i < ni) {
@@ -53,11 +54,12 @@ __device__ __forceinline__ void ln_mod_quant_row(const LnSeg& G, int row, int D,
       uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float2 f = unpack_bf16x2(w[t]);
-        sum += f.x + f.y;
+        sum = add_f32_bf16lo(w[t], sum);
+        sum1 = add_f32_bf16hi(w[t], sum1);
       }
     }
   }
+  sum += sum1;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / D;
@@ -67,14 +69,14 @@ __device__ __forceinline__ void ln_mod_quant_row(const LnSeg& G, int row, int D,
   for (int i = 0; i < kIter; ++i)
     asm volatile("" : "+r"(xv[i].x), "+r"(xv[i].y), "+r"(xv[i].z), "+r"(xv[i].w));
   float var = 0.f;
+  const float neg_mean = -mean;
 #pragma unroll
   for (int i = 0; i < kIter; ++i) {
     if (NI || i < ni) {
       uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float2 f = unpack_bf16x2(w[t]);
-        float d0 = f.x - mean, d1 = f.y - mean;
+        const float d0 = add_f32_bf16lo(w[t], neg_mean), d1 = add_f32_bf16hi(w[t], neg_mean);
         var = fmaf(d0, d0, var);
         var = fmaf(d1, d1, var);
       }
@@ -113,8 +115,8 @@ __device__ __forceinline__ void ln_mod_quant_row(const LnSeg& G, int row, int D,
       float q[8];       // quantiser inputs (pre-clamp)
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float2 f = unpack_bf16x2(w[t]);
-        const __nv_bfloat162 n2 = __floats2bfloat162_rn((f.x - mean) * rstd, (f.y - mean) * rstd);
+        const __nv_bfloat162 n2 =
+            __floats2bfloat162_rn(add_f32_bf16lo(w[t], neg_mean) * rstd, add_f32_bf16hi(w[t], neg_mean) * rstd);
         const __nv_bfloat162 sc2 = *reinterpret_cast<const __nv_bfloat162*>(&scw[t]);
         const __nv_bfloat162 sh2 = *reinterpret_cast<const __nv_bfloat162*>(&shw[t]);
         // (1 + scale) * ln + shift with eager bf16 rounding after each op
@@ -123,10 +125,10 @@ __device__ __forceinline__ void ln_mod_quant_row(const LnSeg& G, int row, int D,
         mb[t] = *reinterpret_cast<const uint32_t*>(&m2);
         if (kPacked) {
           const __nv_bfloat162 p2 = __hmul2_rn(m2, s2);
-          const float2 pf = __bfloat1622float2(p2);
+          const float2 pf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&p2));
           q[t * 2] = pf.x, q[t * 2 + 1] = pf.y;
         } else {
-          const float2 mf = __bfloat1622float2(m2);
+          const float2 mf = unpack_bf16x2(mb[t]);
           q[t * 2] = bf16r(mf.x * s), q[t * 2 + 1] = bf16r(mf.y * s);
         }
       }

@@ -576,9 +576,35 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// sm_100a mixed-precision scalar arithmetic (PTX add / fma .f32.bf16, SASS FHADD.BF16 / FHFMA.BF16): a bf16 operand --
+// either half of a packed pair, selected in the instruction, no unpack -- enters an fp32 add or multiply-add.  The result
+// is the fp32 operation on the exactly converted operand(s): bit-identical to unpack + FADD / FFMA, one instruction fewer
+// per element.
+__device__ __forceinline__ float add_f32_bf16lo(uint32_t pair, float c) {
+  float d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %2;\n\t}" : "=f"(d) : "r"(pair), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float add_f32_bf16hi(uint32_t pair, float c) {
+  float d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, hi, %2;\n\t}" : "=f"(d) : "r"(pair), "f"(c));
+  return d;
+}
+// c + a * a for the low / high bf16 of a pair, fp32 (FHFMA.BF16: exact product, one rounding -- the same value as
+// fmaf(float(a), float(a), c))
+__device__ __forceinline__ float fma_sq_f32_bf16lo(uint32_t pair, float c) {
+  float d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tfma.rn.f32.bf16 %0, lo, lo, %2;\n\t}" : "=f"(d) : "r"(pair), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fma_sq_f32_bf16hi(uint32_t pair, float c) {
+  float d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tfma.rn.f32.bf16 %0, hi, hi, %2;\n\t}" : "=f"(d) : "r"(pair), "f"(c));
+  return d;
+}
+// (shift + mask: two ALU instructions per pair; `__bfloat1622float2` compiles to PRMT + 2 SHF, three)
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(t);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 // fp8 cast of a value that is already clamped to the format's finite range: RNE, saturating.
 template <int FMT>  // 0 = e4m3, 1 = e5m2
@@ -616,7 +642,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 template <int FMT>
 __device__ __forceinline__ uint16_t quant_pair_bf16scale(float x0, float x1, __nv_bfloat162 s2) {
   const __nv_bfloat162 p = __hmul2_rn(__floats2bfloat162_rn(x0, x1), s2);
-  const float2 pf = __bfloat1622float2(p);
+  const float2 pf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&p));
   return to_fp8x2<FMT>(pf.x, pf.y);
 }
 // 0.5 x (1 + tanh(u)) == x * sigmoid(2u) == x / (1 + 2^(-2 u log2 e)):  8 instructions instead of 12.

@@ -12,6 +12,7 @@ from flux_fp8_api_b200 import ops  # noqa: E402
 
 BF16 = torch.bfloat16
 variants = [int(a) for a in sys.argv[1:]] or [17, 16]
+SIZES = [int(x) for x in os.environ.get("ATTN_AB_SIZES", "4608,1000,9728,2816").split(",")]
 
 
 def timed(fn, iters, warm=3):
@@ -27,7 +28,7 @@ def timed(fn, iters, warm=3):
     return s.elapsed_time(e) / iters
 
 
-for S in (4608, 1000, 9728, 2816):
+for S in SIZES:
     B, H = 1, 24
     g = torch.Generator(device="cuda").manual_seed(S)
     q = (torch.randn(B, H, S, 128, device="cuda", generator=g) * 1.5).to(BF16)
