@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
     // Ping-pong token between the two softmax warpgroups (named barriers 1 and 2): only one of them is in its
     // MUFU-bound exp phase at a time, so while one exponentiates the tensor pipe works on the other's tiles.
     // Without it both run in lock-step and the exp phases and the MMAs serialise (profiles/r1_attention.md).
-    if (NQ == 2 && P.debug != 4) {
+    if (NQ == 2 && (CHUNK || P.debug != 4)) {
       if (g == 1) named_bar_arrive(1, 256);  // hand the first turn to warpgroup 0
     }
 
@@ -453,7 +453,10 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
           }
         }
         if (dbg) { tB = clk(); d_max += tB - tA; tA = tB; }
-        if (P.debug != 4) named_bar_sync(1 + g, 256);  // wait for our turn
+        // UNCONDITIONAL on purpose: ptxas sinks a predicated BAR.SYNC below the first ~67 exponentials of the pass (it moves
+        // MUFU freely across barriers), the two warpgroups' passes then overlap by half, and that costs 1-3.5 %
+        // (profiles/r2_attention.md, experiment 5)
+        named_bar_sync(1 + g, 256);  // wait for our turn
         const float2 sl2v = make_float2(sl2, sl2), negmv = make_float2(-m_used, -m_used);
         const float2 magic = make_float2(12582912.f, 12582912.f);
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(AttnCfg<NQ, TS>::kThreads, 1) attention_kernel
           __syncwarp();
           if (lane == 0) mbar_arrive(hh == 0 ? &p_lo[g] : &p_ready[g]);
         }
-        if (P.debug != 4) named_bar_arrive(1 + (g ^ 1), 256);  // pass the turn
+        named_bar_arrive(1 + (g ^ 1), 256);  // pass the turn
         const float2 acc = fadd2(acc0, acc1);
         l += acc.x + acc.y;
         if (dbg) { tB = clk(); d_exp += tB - tA; tA = tB; }
