@@ -525,6 +525,16 @@ def attention(q: Tensor, k: Tensor, v: Tensor, out: Optional[Tensor] = None, out
     _contig(q, "q"), _contig(k, "k"), _contig(v, "v")
     if out is None:
         out = torch.empty((B, S, H * D), dtype=BF16, device=q.device)
+    else:
+        rows = split_row if out1 is not None else S
+        if out.dim() != 3 or out.shape[0] != B or out.shape[1] < rows or out.shape[2] != H * D or out.stride(2) != 1:
+            raise ValueError(f"attention: out {tuple(out.shape)} (strides {out.stride()}) does not hold [{B}, {rows}, {H * D}] "
+                             "rows with unit column stride")
+        if out.dtype != BF16 and out_scale0 is None:
+            raise ValueError("attention: an fp8 `out` needs out_scale0")
+    if out1 is not None and (out1.dim() != 3 or out1.shape[0] != B or out1.shape[1] < S - split_row
+                             or out1.shape[2] != H * D or out1.stride(2) != 1):
+        raise ValueError(f"attention: out1 {tuple(out1.shape)} does not hold [{B}, {S - split_row}, {H * D}] rows")
     a = cabi.AttentionArgs()
     a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     a.ldo, a.out_batch_stride = out.stride(1), out.stride(0)
